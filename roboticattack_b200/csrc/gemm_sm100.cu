@@ -1,0 +1,432 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: Y = epilogue(A . W^T), bf16 in, fp32 accumulate.
+//
+// Replaces the cuBLASLt calls behind every nn.Linear / Conv2d-as-GEMM on the reference's hot path
+// (timm Block qkv/proj/fc1/fc2, PrismaticProjector fc1-3 -- prismatic/extern/hf/modeling_prismatic.py:146-158,
+// HF LlamaDecoderLayer q/k/v/o/gate/up/down, lm_head) and their input-gradient GEMMs (dX = dY . W, run here as
+// the same TN kernel against a pre-transposed weight copy).
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0   : TMA producer  - cp.async.bulk.tensor 128B-swizzled A (128x64) and W (BLOCK_Nx64) tiles into a
+//                              STAGES-deep shared-memory ring, completion on `full` mbarriers
+//   warp 1   : MMA issuer    - one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16),
+//                              accumulating in TMEM; tcgen05.commit releases ring slots / publishes the tile
+//   warps 2-5: epilogue      - tcgen05.ld the fp32 accumulator (one TMEM lane quarter per warp), apply
+//                              bias / GELU / LayerScale / residual with the eager path's bf16 rounding points,
+//                              store bf16 (or fp32) rows
+// Two TMEM accumulator stages (2 x BLOCK_N columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <unordered_map>
+
+#include "gemm.h"
+
+long long g_vla_launch_count = 0;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+struct GemmArgs {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks;
+  int64_t ldc;
+  void* out;
+  GemmEpilogue epi;
+};
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO).
+// Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) with SWIZZLE_128B = 2.
+__device__ __forceinline__ uint64_t make_umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Instruction descriptor (InstrDescriptor): c_format F32=1 [4,6), a/b_format BF16=1 [7,10)/[10,13),
+// a/b major K=0 [15]/[16], N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 or 256: power of two >= 32
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+};
+
+// One row x 32 columns of the accumulator -> global, with the fused epilogue.
+__device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const uint32_t (&acc)[32], int row, int col0) {
+  const GemmEpilogue& e = g.epi;
+  const bool full = (col0 + 32 <= g.N);
+  float x[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(acc[j]);
+
+  if (full) {
+    if (e.bias) {
+      const uint4* bp = reinterpret_cast<const uint4*>(e.bias + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 u = __ldg(bp + q);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_bf16x2(w[t]);
+          x[q * 8 + t * 2] += f.x;
+          x[q * 8 + t * 2 + 1] += f.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = rbf(x[j]);
+    if (e.preact_out) {
+      uint4* pp = reinterpret_cast<uint4*>(e.preact_out + static_cast<int64_t>(row) * g.ldc + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        pp[q] = make_uint4(pack_bf16x2(x[q * 8], x[q * 8 + 1]), pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]),
+                           pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]));
+    }
+    if (e.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = rbf(gelu_erf(x[j]));
+    }
+    if (e.gamma) {
+      const uint4* gp = reinterpret_cast<const uint4*>(e.gamma + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 u = __ldg(gp + q);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_bf16x2(w[t]);
+          x[q * 8 + t * 2] = rbf(x[q * 8 + t * 2] * f.x);
+          x[q * 8 + t * 2 + 1] = rbf(x[q * 8 + t * 2 + 1] * f.y);
+        }
+      }
+    }
+    if (e.resid) {
+      const uint4* rp = reinterpret_cast<const uint4*>(e.resid + static_cast<int64_t>(row) * e.ldr + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 u = rp[q];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_bf16x2(w[t]);
+          x[q * 8 + t * 2] = rbf(f.x + x[q * 8 + t * 2]);
+          x[q * 8 + t * 2 + 1] = rbf(f.y + x[q * 8 + t * 2 + 1]);
+        }
+      }
+    }
+    if (e.out_f32) {
+      float4* op = reinterpret_cast<float4*>(static_cast<float*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) op[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+    } else {
+      uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        op[q] = make_uint4(pack_bf16x2(x[q * 8], x[q * 8 + 1]), pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]),
+                           pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]));
+    }
+  } else {
+    // ragged N edge: scalar path
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+      const int n = col0 + j;
+      if (n >= g.N) break;
+      float v = x[j];
+      if (e.bias) v += b2f(e.bias[n]);
+      v = rbf(v);
+      if (e.preact_out) e.preact_out[static_cast<int64_t>(row) * g.ldc + n] = f2b(v);
+      if (e.act == 1) v = rbf(gelu_erf(v));
+      if (e.gamma) v = rbf(v * b2f(e.gamma[n]));
+      if (e.resid) v = rbf(b2f(e.resid[static_cast<int64_t>(row) * e.ldr + n]) + v);
+      if (e.out_f32)
+        static_cast<float*>(g.out)[static_cast<int64_t>(row) * g.ldc + n] = v;
+      else
+        static_cast<bf16*>(g.out)[static_cast<int64_t>(row) * g.ldc + n] = f2b(v);
+    }
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const GemmArgs g) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES +
+                                                                         8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_tiles = g.num_m_blocks * g.num_n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % g.num_m_blocks, n_blk = tile / g.num_m_blocks;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(sa, &map_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(sa + A_TILE_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t da = make_umma_desc_sw128(sa);
+          const uint64_t db = make_umma_desc_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 B (= UMMA_K bf16) inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % g.num_m_blocks, n_blk = tile / g.num_m_blocks;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (col0 >= g.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+        if (row < g.M) epilogue_store_chunk(g, v, row, col0);
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  int64_t ld;
+  int rows, cols, box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && ld == o.ld && rows == o.rows && cols == o.cols && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= static_cast<size_t>(k.ld) * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= (static_cast<size_t>(k.rows) << 32 | static_cast<uint32_t>(k.cols)) + (h << 6) + (h >> 2);
+    h ^= static_cast<size_t>(k.box_rows) * 0xC2B2AE3D27D4EB4Full;
+    return h;
+  }
+};
+
+// 2-D bf16 row-major [rows, cols] (ld elements between rows) -> tensor map with a (box_rows x 64) box,
+// 128B swizzle, zero fill out of bounds.
+int get_tmap(const bf16* ptr, int64_t ld, int rows, int cols, int box_rows, CUtensorMap* out) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, ld, rows, cols, box_rows};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  VLA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {BLOCK_K, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VLA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: CUresult %d (ptr %p ld %lld rows %d cols %d)", (int)r,
+              (const void*)ptr, (long long)ld, rows, cols);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
+int g_num_sms = 0;
+
+template <int BLOCK_N>
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    VLA_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = g.num_m_blocks * g.num_n_blocks;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_bf16_tn_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, g);
+  VLA_LAUNCH_CHECK();
+  ++g_vla_launch_count;
+  return 0;
+}
+
+}  // namespace
+
+int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
+                 const GemmEpilogue& epi, cudaStream_t stream) {
+  VLA_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  VLA_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "gemm: leading dims must be multiples of 8 elements");
+  VLA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "gemm: operands must be 16-byte aligned");
+  VLA_REQUIRE(!epi.resid || epi.ldr % 8 == 0, "gemm: residual ld must be a multiple of 8");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    VLA_CHECK_CUDA(cudaGetDevice(&dev));
+    VLA_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // Tile-N choice: fewest (waves x tile cost) over the SMs; ties -> wider tile (half the A re-reads).
+  const int mb = ceil_div(M, BLOCK_M);
+  int block_n = 256;
+  {
+    static int forced = -1;
+    if (forced < 0) {
+      const char* s = getenv("VLA_GEMM_BLOCK_N");
+      forced = s ? atoi(s) : 0;
+    }
+    if (forced == 128 || forced == 256) {
+      block_n = forced;
+    } else {
+      const long c256 = static_cast<long>(ceil_div(mb * ceil_div(N, 256), g_num_sms)) * 256;
+      const long c128 = static_cast<long>(ceil_div(mb * ceil_div(N, 128), g_num_sms)) * 128;
+      block_n = (c128 < c256) ? 128 : 256;
+    }
+  }
+  GemmArgs g;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.num_m_blocks = mb;
+  g.num_n_blocks = ceil_div(N, block_n);
+  g.ldc = ldc;
+  g.out = out;
+  g.epi = epi;
+  CUtensorMap ma, mbm;
+  if (int rc = get_tmap(A, lda, M, K, BLOCK_M, &ma)) return rc;
+  if (int rc = get_tmap(W, ldw, N, K, block_n, &mbm)) return rc;
+  return block_n == 256 ? launch_gemm<256>(ma, mbm, g, stream) : launch_gemm<128>(ma, mbm, g, stream);
+}
