@@ -1,0 +1,138 @@
+"""Shapes of the models on the hot path and the constants of the attack front end.
+
+Reference: ``prismatic/extern/hf/configuration_prismatic.py:15-45,72-140`` (model ids, image size, LLM dims),
+``VLAAttacker/white_patch/UADA.py:56-57`` (normalisation constants), ``prismatic/vla/action_tokenizer.py:28-36``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Tuple
+
+IGNORE_INDEX = -100
+PAD_TOKEN_ID = 32000
+EOS_TOKEN_ID = 2
+VOCAB_TOKENIZER = 32000          # LlamaTokenizer vocab (action ids are the last 256 of it)
+N_ACTION_BINS = 256
+ACTION_TOKEN_BEGIN_IDX = VOCAB_TOKENIZER - (N_ACTION_BINS + 1)   # 31743
+ACTION_LOGIT_LO = 31744          # logits[..., 31744:32000] are the 256 action classes (UADA.py:384)
+ACTION_LOGIT_HI = 32000
+ZERO_ACTION_TOKEN = 31872
+
+# index 0 = DINOv2 (ImageNet stats rounded to bf16), index 1 = SigLIP  (UADA.py:56-57)
+NORM_MEAN = ((0.484375, 0.455078125, 0.40625), (0.5, 0.5, 0.5))
+NORM_STD = ((0.228515625, 0.2236328125, 0.224609375), (0.5, 0.5, 0.5))
+
+
+@dataclass(frozen=True)
+class ViTConfig:
+    dim: int
+    depth: int
+    heads: int
+    mlp_hidden: int
+    num_prefix: int          # cls + register tokens prepended after the position embedding
+    layerscale: bool
+    img: int = 224
+    patch: int = 14
+    ln_eps: float = 1e-6
+
+    @property
+    def head_dim(self) -> int:
+        return self.dim // self.heads
+
+    @property
+    def grid(self) -> int:
+        return self.img // self.patch
+
+    @property
+    def num_patches(self) -> int:
+        return self.grid * self.grid
+
+    @property
+    def tokens(self) -> int:
+        return self.num_patches + self.num_prefix
+
+    @property
+    def blocks_used(self) -> int:
+        """get_intermediate_layers(n={depth-2}) takes the output of block index depth-2 (modeling_prismatic.py:85-87)."""
+        return self.depth - 1
+
+
+@dataclass(frozen=True)
+class LlamaConfig:
+    hidden: int
+    layers: int
+    heads: int
+    ffn: int
+    vocab: int = 32064
+    rms_eps: float = 1e-6
+    rope_theta: float = 10000.0
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.heads
+
+
+@dataclass(frozen=True)
+class OpenVLAConfig:
+    dino: ViTConfig
+    siglip: ViTConfig
+    llm: LlamaConfig
+    name: str = "custom"
+
+    @property
+    def img(self) -> int:
+        return self.dino.img
+
+    @property
+    def num_patches(self) -> int:
+        return self.dino.num_patches
+
+    @property
+    def vision_dim(self) -> int:
+        return self.dino.dim + self.siglip.dim
+
+    @property
+    def proj_hidden(self) -> int:
+        return 4 * self.vision_dim
+
+
+def openvla_7b() -> OpenVLAConfig:
+    """OpenVLA-7B: DINOv2-L/14 reg4 + SigLIP-so400m/14 @224, Llama-2-7B."""
+    return OpenVLAConfig(
+        dino=ViTConfig(dim=1024, depth=24, heads=16, mlp_hidden=4096, num_prefix=5, layerscale=True),
+        siglip=ViTConfig(dim=1152, depth=27, heads=16, mlp_hidden=4304, num_prefix=0, layerscale=False),
+        llm=LlamaConfig(hidden=4096, layers=32, heads=32, ffn=11008),
+        name="openvla-7b",
+    )
+
+
+def tiny(img: int = 56, llm_layers: int = 2, vit_depth: int = 3) -> OpenVLAConfig:
+    """Same structure, toy widths: same head dims (64 / 72 / 128) so every kernel variant is exercised."""
+    return OpenVLAConfig(
+        dino=ViTConfig(dim=128, depth=vit_depth, heads=2, mlp_hidden=512, num_prefix=5, layerscale=True, img=img),
+        siglip=ViTConfig(dim=144, depth=vit_depth, heads=2, mlp_hidden=536, num_prefix=0, layerscale=False, img=img),
+        llm=LlamaConfig(hidden=256, layers=llm_layers, heads=2, ffn=688),
+        name=f"tiny-{img}",
+    )
+
+
+def flops_per_sample(cfg: OpenVLAConfig, text_len: int, supervised_rows: int = 8) -> dict:
+    """Algorithmic FLOPs of one attack iteration for one sample:
+    F_iter = 2*F_lin + 3*F_att (forward + input-gradient for linears, forward + 2x for attention; no dW)."""
+    def vit(c: ViTConfig):
+        n = c.tokens
+        lin = c.blocks_used * 2 * n * (4 * c.dim * c.dim + 2 * c.dim * c.mlp_hidden)
+        att = c.blocks_used * 4 * n * n * c.dim
+        pe = 2 * c.num_patches * (3 * c.patch * c.patch) * c.dim
+        return lin + pe, att
+    dl, da = vit(cfg.dino)
+    sl, sa = vit(cfg.siglip)
+    vd, ph, hd = cfg.vision_dim, cfg.proj_hidden, cfg.llm.hidden
+    proj = 2 * cfg.num_patches * (vd * ph + ph * hd + hd * hd)
+    L = text_len + cfg.num_patches
+    llm_lin = cfg.llm.layers * 2 * L * (4 * hd * hd + 3 * hd * cfg.llm.ffn)
+    llm_att = cfg.llm.layers * 4 * L * L * hd / 2
+    head = 2 * supervised_rows * hd * cfg.llm.vocab
+    f_lin = dl + sl + proj + llm_lin + head
+    f_att = da + sa + llm_att
+    return {"f_lin": f_lin, "f_att": f_att, "fwd": f_lin + f_att, "iter": 2 * f_lin + 3 * f_att}

@@ -1,0 +1,134 @@
+"""Pin the oracle against outputs of the reference's own functions (tests/golden/make_golden.py)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import frontend as ofe
+from oracle import llama as ollama
+from oracle import losses as ol
+from oracle import optim as oo
+from roboticattack_b200.config import NORM_MEAN, NORM_STD, tiny
+from roboticattack_b200.weights import LM, random_state_dict
+
+MODES = {"warp": (ofe.MODE_WARP, True), "paste20": (ofe.MODE_PASTE20, False), "fix": (ofe.MODE_FIX, False),
+         "rpaste": (ofe.MODE_FIX, False)}
+
+
+@pytest.mark.parametrize("tag", ["s64", "s224"])
+@pytest.mark.parametrize("mode", list(MODES))
+def test_frontend_matches_reference(golden, tag, mode):
+    obs = torch.from_numpy(golden[f"fe_{tag}_obs"])
+    patch = torch.from_numpy(golden[f"fe_{tag}_patch"]).clone().requires_grad_(True)
+    B, S = obs.shape[0], obs.shape[1]
+    m, geometry = MODES[mode]
+    random.seed(42)
+    np.random.seed(42)
+    xy, theta = ofe.draw_placements(B, (S, S), patch.shape[1:], geometry)
+    y = ofe.apply_patch_batch(obs, patch, xy, theta, m, NORM_MEAN, NORM_STD)
+    gw = torch.from_numpy(np.random.default_rng(7).standard_normal(tuple(y.shape)).astype(np.float32))
+    (y * gw).sum().backward()
+    if tag == "s64":
+        np.testing.assert_allclose(y.detach().numpy(), golden[f"fe_{tag}_{mode}_out"], rtol=0, atol=1e-6)
+    else:
+        np.testing.assert_allclose(y.detach()[:, :, ::5, ::5].numpy(), golden[f"fe_{tag}_{mode}_out_strided"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(y.detach().double().sum(dim=(2, 3)).numpy(), golden[f"fe_{tag}_{mode}_out_sum"], rtol=1e-9)
+    np.testing.assert_allclose(patch.grad.numpy(), golden[f"fe_{tag}_{mode}_grad"], rtol=1e-5, atol=1e-5)
+
+
+def test_frontend_no_patch(golden):
+    obs = torch.from_numpy(golden["fe_s64_obs"])
+    y = ofe.apply_patch_batch(obs, torch.zeros(3, 4, 4), None, None, ofe.MODE_NONE, NORM_MEAN, NORM_STD)
+    np.testing.assert_allclose(y.double().sum(dim=(2, 3)).numpy(), golden["fe_s64_none_out_sum"], rtol=1e-9)
+
+
+def test_action_tokenizer(golden):
+    np.testing.assert_array_equal(ol.decode_token_ids_to_actions(golden["tok_ids"]), golden["tok_decode"])
+    np.testing.assert_array_equal(ol.encode_actions_to_token_ids(golden["tok_actions"]), golden["tok_encode_ids"])
+    from roboticattack_b200.config import ACTION_TOKEN_BEGIN_IDX, ZERO_ACTION_TOKEN
+    assert ACTION_TOKEN_BEGIN_IDX == int(golden["tok_begin_idx"])
+    assert ol.encode_actions_to_token_ids(np.zeros(1))[0] == ZERO_ACTION_TOKEN
+
+
+def _full_logits(golden):
+    z = torch.from_numpy(golden["loss_zslice"])
+    B, Tm1, _ = z.shape
+    L = 256 + Tm1 + 1
+    logits = torch.zeros(B, L, 32064)
+    logits[:, 256:L - 1, 31744:32000] = z
+    return logits, L
+
+
+@pytest.mark.parametrize("mi", range(4))
+def test_uada_heads(golden, mi):
+    labels = torch.from_numpy(golden["loss_labels"]).clone()
+    maskidx = golden[f"uada_mask{mi}_idx"].tolist()
+    ml = ol.mask_labels_uada(labels, maskidx)
+    np.testing.assert_array_equal(ml.numpy(), golden[f"uada_mask{mi}_labels"])
+    logits, L = _full_logits(golden)
+    lg = logits.clone().requires_grad_(True)
+    loss, uad = ol.weighted_loss_uada(lg, ml, 5)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), golden[f"uada_mask{mi}_loss"], rtol=1e-6)
+    np.testing.assert_allclose(float(uad), golden[f"uada_mask{mi}_uad"], rtol=1e-6)
+    np.testing.assert_allclose(lg.grad[:, 256:L - 1, 31744:32000].numpy(), golden[f"uada_mask{mi}_dz"], rtol=1e-5, atol=1e-8)
+    for w in (1, 5):
+        l2, u2 = ol.weighted_loss_uada(logits, ml, w)
+        np.testing.assert_allclose(l2.item(), golden[f"ddp_mask{mi}_w{w}_loss"], rtol=1e-6)
+        np.testing.assert_allclose(float(u2), golden[f"ddp_mask{mi}_w{w}_uad"], rtol=1e-6)
+    # relative distance per (sample, dof)
+    preds = logits[:, 256:-1].argmax(dim=2)
+    gt = ml[:, 1:]
+    m = gt > 31743
+    cp = torch.tensor(ol.decode_token_ids_to_actions(preds[m].numpy())).view(-1, len(maskidx))
+    cg = torch.tensor(ol.decode_token_ids_to_actions(gt[m].numpy())).view(-1, len(maskidx))
+    rd = ol.relative_distance(cp, cg).t().numpy()
+    np.testing.assert_allclose(rd, golden[f"uada_mask{mi}_rd"], rtol=1e-9)
+
+
+def test_upa_heads(golden):
+    labels = torch.from_numpy(golden["loss_labels"]).clone()
+    logits, L = _full_logits(golden)
+    lg = logits.clone().requires_grad_(True)
+    total, ang, dist = ol.weighted_loss_upa(lg, labels, 0.8, 0.2, 256)
+    total.backward()
+    np.testing.assert_allclose(total.item(), golden["upa_loss"], rtol=1e-6)
+    np.testing.assert_allclose(ang.item(), golden["upa_angle"], rtol=1e-6)
+    np.testing.assert_allclose(dist.item(), golden["upa_dist"], rtol=1e-6)
+    np.testing.assert_allclose(lg.grad[:, 256:L - 1, 31744:32000].numpy(), golden["upa_dz"], rtol=1e-5, atol=1e-9)
+    for mi in range(3):
+        ml = ol.mask_labels_upa(torch.from_numpy(golden["loss_labels"]).clone(), golden[f"upa_mask{mi}_idx"].tolist())
+        np.testing.assert_array_equal(ml.numpy(), golden[f"upa_mask{mi}_labels"])
+
+
+def test_cosine_schedule(golden):
+    lrs = np.array([2e-3 * oo.cosine_with_warmup_lambda(s, 20, 2000) for s in range(2000)])
+    np.testing.assert_allclose(lrs, golden["sched_lrs"], rtol=1e-12, atol=1e-18)
+    assert lrs[0] == 0.0   # lr is 0 for the whole of outer iteration 0
+
+
+def test_llama_matches_hf(golden):
+    cfg = tiny()
+    sd = random_state_dict(cfg, seed=3, dtype=torch.float32, init="test")
+    emb = torch.from_numpy(golden["llama_emb"])
+    mask = torch.from_numpy(golden["llama_mask"])
+    lab = torch.from_numpy(golden["llama_labels"])
+    loss, logits = ollama.llama_forward(sd, LM, cfg.llm, emb, mask, lab)
+    np.testing.assert_allclose(loss.item(), golden["llama_loss"], rtol=2e-5)
+    sup = lab[:, 1:] != -100
+    got = logits[:, :-1][sup][:, 31744:32000].numpy()
+    np.testing.assert_allclose(got, golden["llama_sup_logits_action"], rtol=1e-3, atol=2e-4)
+
+
+def test_adamw_rule_matches_definition():
+    """eps is added before the bias correction (transformers.AdamW), unlike torch.optim.AdamW."""
+    torch.manual_seed(0)
+    p = torch.rand(3, 5, 5)
+    opt = oo.HFAdamW(p.shape, lr=2e-3)
+    p0 = p.clone()
+    g = torch.randn_like(p)
+    opt.step(p, g)
+    # first step: m = 0.1 g, v = 0.001 g^2, step = lr*sqrt(0.001)/0.1
+    expect = p0 - 2e-3 * (0.001 ** 0.5) / 0.1 * (0.1 * g) / ((0.001 * g * g).sqrt() + 1e-6)
+    torch.testing.assert_close(p, expect, rtol=1e-5, atol=1e-7)
