@@ -1,16 +1,150 @@
-/* placeholder, filled in below */
+/* vla_b200.h -- C ABI of the B200 (sm_100a) adversarial-patch attack engine.
+ *
+ * Drop-in boundary for the inner loop of William-wAng618/roboticAttack's OpenVLAAttacker (file:line below are
+ * relative to that repository @ a0bef502).  The reference is pure Python and has no FFI of its own; the entry
+ * points here are what a binding for this path needs, one per reference call site.  Conventions:
+ *   - every function returns 0 on success, non-zero on failure; vla_last_error() gives the message (thread local);
+ *   - plain pointers and sizes only; device pointers unless a parameter says "host";
+ *   - no function allocates device memory or synchronises the device, except the vla_engine_set_* staging calls,
+ *     which synchronise the given stream once (they copy from pageable host staging);
+ *   - all kernels are launched on the caller's stream (a cudaStream_t passed as void*);
+ *   - one engine per process / GPU; an engine is not thread safe.
+ */
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
+
 #define VLA_B200_ABI_VERSION 1
+
 #ifdef __cplusplus
 extern "C" {
 #endif
+
 const char* vla_last_error(void);
 int vla_abi_version(void);
+/* number of kernel launches issued by this library since process start */
 long long vla_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Front end.  Replaces RandomPatchTransform.apply_random_patch_batch (VLAAttacker/white_patch/
+ * appply_random_transform.py:104-136), .paste_patch_fix (:160-188) / .random_paste_patch (:138-158), .im_process
+ * (:190-197) plus the `.to(torch.bfloat16)` of UADA.py:142, and their autograd backward.
+ *   obs    u8  [B,H,W,3]   clean observations (what torchvision ToTensor would read from the PIL images)
+ *   patch  f32 [3,ph,pw]
+ *   xy     i32 [B,2]       paste position (x, y) drawn by random.randint (:123-124)
+ *   theta  f32 [B,2,3]     first two rows of S.R from combined_transform_matrix (:80-91); ignored unless WARP
+ *   out    bf16 [B,6,H,W]  channels 0-2 DINOv2-normalised, 3-5 SigLIP-normalised (UADA.py:56-57)
+ *   norm   f32 [12]        mean[2][3] then std[2][3]
+ */
+enum { VLA_FE_WARP = 0,    /* geometry=True : affine_grid + grid_sample(border), keep where canvas >= -20 (:127-131) */
+       VLA_FE_PASTE20 = 1, /* geometry=False: no warp, same `canvas < -20` test */
+       VLA_FE_FIX = 2,     /* paste_patch_fix / random_paste_patch: `canvas != -100` test (:153,:179) */
+       VLA_FE_NONE = 3 };  /* im_process: no patch */
+int vla_patch_frontend_fwd(const uint8_t* obs, const float* patch, const int32_t* xy, const float* theta, void* out_bf16,
+                           int B, int H, int W, int ph, int pw, int mode, const float* norm, void* stream);
+/* dpatch f32 [3,ph,pw] = d loss / d patch given dout bf16 [B,6,H,W]; overwrites dpatch */
+int vla_patch_frontend_bwd(const void* dout_bf16, const float* patch, const int32_t* xy, const float* theta,
+                           float* dpatch, int B, int H, int W, int ph, int pw, int mode, const float* norm, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Loss heads (UADA.py:145-147,381-418; UADA_ddp.py:99-136,203-206; UPA.py:145-150,367-387; TMA.py:148) */
+enum { VLA_LOSS_UADA = 0,      /* mean((w e - w t)^2) + 1/CE,  w = mse_weight (5 in UADA.py:396) */
+       VLA_LOSS_UADA_DDP = 1,  /* mean((w e - w t)^2),         w = MSE_weights (UADA_ddp.py:114) */
+       VLA_LOSS_UPA = 2,       /* alpha*(cos+1).mean + belta/(mean||d|| + 1e-3) on the first 3 DoF */
+       VLA_LOSS_CE = 3,        /* ce_scale * CE  (TMA: 1/accumulate_steps; UPA guide) */
+       VLA_LOSS_NEG_CE = 4 };  /* -CE (UPA reverse_direction=False) */
+typedef struct vla_loss_params {
+  int kind;
+  float mse_weight;
+  float alpha, belta;
+  float ce_scale;
+} vla_loss_params;
+/* indices into the per-step scalar record (device float[VLA_NUM_SCALARS]) */
+enum { VLA_S_LOSS = 0, VLA_S_CE = 1, VLA_S_AUX0 = 2 /* UADA: MSE term; UPA: angle loss */, VLA_S_AUX1 = 3 /* UPA: distance loss */,
+       VLA_S_UAD = 4, VLA_S_NTOK = 5, VLA_S_NACT = 6, VLA_S_GRAD_MEAN = 7 /* patch.grad.mean(), written by the update */,
+       VLA_NUM_SCALARS = 8 };
+/* logits f32 [R,V] of the R supervised rows; meta i32 [R,3] = {label, sample, index among the sample's supervised rows};
+ * row_stats: scratch f32 [8*R]; dlogits bf16 [R,V]; pred_ids i32 [R] (argmax action id, -1 for non-action rows) */
+int vla_loss_head(const float* logits, const int32_t* meta, int R, int V, int B, const vla_loss_params* lp,
+                  float* row_stats, void* dlogits_bf16, float* scalars, int32_t* pred_ids, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Patch update.  transformers.AdamW(lr, betas=(0.9,0.999), eps=1e-6, wd=0) + clamp(0,1) (UADA.py:107-115,155-156),
+ * with the optional clip_grad_norm_(max_norm=clip_l1, norm_type=1) of UPA.py:157; or sign-PGD (TMA.py:171-175).
+ * grad is multiplied by grad_scale first (1/world_size after an all-reduce(sum): DDP's gradient mean). */
+enum { VLA_OPT_ADAMW = 0, VLA_OPT_PGD = 1 };
+int vla_patch_update(float* patch, const float* grad, float* exp_avg, float* exp_avg_sq, int n, int step, float lr,
+                     float beta1, float beta2, float eps, int kind, float grad_scale, float clip_l1, float* scalars,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Building blocks, exported for the parity tests (each is checked against the oracle on its own). */
 int vla_gemm_bf16_tn(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
                      const void* bias, const void* gamma, const void* resid, int64_t ldr, int act, void* preact_out,
                      int out_f32, void* stream);
+int vla_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t M, int d,
+                      float eps, void* stream);
+int vla_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
+                      const void* dres, void* dx, int64_t M, int d, void* stream);
+int vla_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t M, int d, float eps, void* stream);
+int vla_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+                    int64_t M, int d, void* stream);
+/* qkv bf16 [B*N, 3*H*hd]; o bf16 [B*N, H*hd]; lse f32 [B,H,N]; kv_len i32 [B] or NULL */
+int vla_attention_fwd(const void* qkv, void* o, float* lse, const int32_t* kv_len, int B, int N, int H, int hd,
+                      int causal, void* stream);
+int vla_attention_bwd(const void* qkv, const void* o, const void* dout, const float* lse, float* delta_scratch,
+                      void* dqkv, const int32_t* kv_len, int B, int N, int H, int hd, int causal, void* stream);
+int vla_rope_inplace(void* qkv, const float* cos_tab, const float* sin_tab, int64_t M, int L, int H, int hd, int dir,
+                     void* stream);
+int vla_swiglu_fwd(const void* gu, void* act, int64_t M, int F, void* stream);
+int vla_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t M, int F, void* stream);
+int vla_gelu_bwd(const void* dy, const void* pre, void* dx, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Engine: forward + input-gradient of OpenVLAForActionPrediction for one attack iteration.
+ * Replaces `self.vla(input_ids, attention_mask, pixel_values, labels)` + loss + `.backward()` of
+ * UADA.py:139-148 / UADA_ddp.py:196-206 / UPA.py:139-152 / TMA.py:142-162 (prismatic/extern/hf/
+ * modeling_prismatic.py:362-415 and the timm / HF-Llama bodies behind it). */
+typedef struct vla_config {
+  int img, patch;                                            /* 224, 14 */
+  int dino_dim, dino_depth, dino_heads, dino_mlp, dino_prefix, dino_layerscale;   /* 1024,24,16,4096,5,1 */
+  int sig_dim, sig_depth, sig_heads, sig_mlp, sig_prefix, sig_layerscale;         /* 1152,27,16,4304,0,0 */
+  float vit_ln_eps;                                          /* 1e-6 */
+  int llm_hidden, llm_layers, llm_heads, llm_ffn, vocab;     /* 4096,32,32,11008,32064 */
+  float rms_eps;                                             /* 1e-6 */
+  float norm_mean[2][3], norm_std[2][3];                     /* UADA.py:56-57 */
+} vla_config;
+typedef struct vla_engine vla_engine;
+
+int vla_engine_create(const vla_config* cfg, vla_engine** out);
+void vla_engine_destroy(vla_engine* e);
+/* bytes of the weight arena (forward copies + the transposed copies the input-gradient GEMMs read) */
+size_t vla_engine_weight_bytes(const vla_engine* e);
+/* bytes of the activation arena for per-GPU batch B and text length T (sequence L = T + num_patches) */
+size_t vla_engine_workspace_bytes(vla_engine* e, int B, int T);
+int vla_engine_set_buffers(vla_engine* e, void* weight_arena, size_t weight_bytes, void* workspace,
+                           size_t workspace_bytes, int B, int T);
+/* one HF-checkpoint tensor (bf16, device), by its checkpoint name */
+int vla_engine_load_weight(vla_engine* e, const char* name, const void* src_bf16, int64_t numel, void* stream);
+int vla_engine_weights_ready(vla_engine* e);
+/* cos/sin f32 [L, head_dim/2] (host), as HF LlamaRotaryEmbedding computes them (values rounded to bf16) */
+int vla_engine_set_rope(vla_engine* e, const float* cos_host, const float* sin_host, int L, void* stream);
+/* one outer iteration's batch, as PaddedCollatorForActionPrediction yields it (prismatic/util/data_utils.py:183-217):
+ * obs u8 [B,H,W,3] (host unless obs_on_device), input_ids i64 [B,T] host, attention_mask u8 [B,T] host (right padded),
+ * labels i64 [B,T] host (-100 = ignore; already masked by mask_labels / target substitution) */
+int vla_engine_set_batch(vla_engine* e, const uint8_t* obs, int obs_on_device, const int64_t* input_ids,
+                         const uint8_t* attention_mask, const int64_t* labels, int B, int T, void* stream);
+/* placements of the next nsteps inner iterations: xy i32 [nsteps,B,2], theta f32 [nsteps,B,2,3] (host) */
+int vla_engine_set_placements(vla_engine* e, const int32_t* xy_host, const float* theta_host, int nsteps, void* stream);
+int vla_engine_num_supervised(const vla_engine* e);
+
+enum { VLA_FLAG_FORWARD_ONLY = 1 };   /* validation pass: loss heads + metrics, no backward */
+/* patch f32 [3,ph,pw] -> dpatch f32 [3,ph,pw], scalars f32 [VLA_NUM_SCALARS], pred_ids i32 [num_supervised] */
+int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, int step_idx, int fe_mode,
+                const vla_loss_params* lp, float* dpatch, float* scalars, int32_t* pred_ids, int flags, void* stream);
+/* test tap: copies a named internal activation ("px", "dino_out", "llm_out", "logits", ...) to dst (device) */
+int64_t vla_engine_debug_tap(vla_engine* e, const char* what, void* dst, int64_t max_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

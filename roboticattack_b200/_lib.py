@@ -1,27 +1,87 @@
-"""ctypes loader for the C-ABI library. There is no CPU fallback: if the library is missing or a call fails,
-the caller gets an exception."""
+"""ctypes binding of ``libvla_b200.so`` (declared in ``include/vla_b200.h``).
+
+There is no CPU fallback: if the library is missing or a call fails, the caller gets an exception.
+"""
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_void_p
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_uint8,
+                    c_void_p)
 from pathlib import Path
 
 _LIB = None
 LIB_PATH = Path(__file__).resolve().parent / "libvla_b200.so"
+
+FE_WARP, FE_PASTE20, FE_FIX, FE_NONE = 0, 1, 2, 3
+LOSS_UADA, LOSS_UADA_DDP, LOSS_UPA, LOSS_CE, LOSS_NEG_CE = 0, 1, 2, 3, 4
+OPT_ADAMW, OPT_PGD = 0, 1
+S_LOSS, S_CE, S_AUX0, S_AUX1, S_UAD, S_NTOK, S_NACT, S_GRAD_MEAN, NUM_SCALARS = 0, 1, 2, 3, 4, 5, 6, 7, 8
+FLAG_FORWARD_ONLY = 1
 
 
 class VLAError(RuntimeError):
     pass
 
 
-def _declare(lib):
-    lib.vla_last_error.restype = c_char_p
-    lib.vla_last_error.argtypes = []
-    lib.vla_abi_version.restype = c_int
-    lib.vla_launch_count.restype = c_longlong
-    lib.vla_gemm_bf16_tn.restype = c_int
-    lib.vla_gemm_bf16_tn.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
-                                     c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]
+class LossParams(Structure):
+    _fields_ = [("kind", c_int), ("mse_weight", c_float), ("alpha", c_float), ("belta", c_float), ("ce_scale", c_float)]
+
+
+class Config(Structure):
+    _fields_ = [("img", c_int), ("patch", c_int),
+                ("dino_dim", c_int), ("dino_depth", c_int), ("dino_heads", c_int), ("dino_mlp", c_int),
+                ("dino_prefix", c_int), ("dino_layerscale", c_int),
+                ("sig_dim", c_int), ("sig_depth", c_int), ("sig_heads", c_int), ("sig_mlp", c_int),
+                ("sig_prefix", c_int), ("sig_layerscale", c_int),
+                ("vit_ln_eps", c_float),
+                ("llm_hidden", c_int), ("llm_layers", c_int), ("llm_heads", c_int), ("llm_ffn", c_int), ("vocab", c_int),
+                ("rms_eps", c_float),
+                ("norm_mean", (c_float * 3) * 2), ("norm_std", (c_float * 3) * 2)]
+
+
+# name -> (restype, argtypes); every symbol include/vla_b200.h declares
+SIGNATURES = {
+    "vla_last_error": (c_char_p, []),
+    "vla_abi_version": (c_int, []),
+    "vla_launch_count": (c_longlong, []),
+    "vla_patch_frontend_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, POINTER(c_float), c_void_p]),
+    "vla_patch_frontend_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, POINTER(c_float), c_void_p]),
+    "vla_loss_head": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(LossParams), c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p]),
+    "vla_patch_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float,
+                                 c_float, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "vla_gemm_bf16_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
+    "vla_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float,
+                                  c_void_p]),
+    "vla_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                  c_void_p]),
+    "vla_rmsnorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
+    "vla_rmsnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "vla_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vla_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                  c_int, c_int, c_int, c_void_p]),
+    "vla_rope_inplace": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    "vla_swiglu_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "vla_swiglu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "vla_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "vla_engine_create": (c_int, [POINTER(Config), POINTER(c_void_p)]),
+    "vla_engine_destroy": (None, [c_void_p]),
+    "vla_engine_weight_bytes": (c_size_t, [c_void_p]),
+    "vla_engine_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "vla_engine_set_buffers": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int]),
+    "vla_engine_load_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
+    "vla_engine_weights_ready": (c_int, [c_void_p]),
+    "vla_engine_set_rope": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "vla_engine_set_batch": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "vla_engine_set_placements": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "vla_engine_num_supervised": (c_int, [c_void_p]),
+    "vla_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(LossParams), c_void_p, c_void_p,
+                            c_void_p, c_int, c_void_p]),
+    "vla_engine_debug_tap": (c_int64, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
+}
 
 
 def lib():
@@ -33,12 +93,15 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -m roboticattack_b200.build` "
                 "(there is no CPU fallback for the attack hot path)")
         handle = ctypes.CDLL(str(LIB_PATH))
-        _declare(handle)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)   # AttributeError if the header and the library diverge
+            fn.restype = res
+            fn.argtypes = args
         _LIB = handle
     return _LIB
 
 
-def check(rc: int, what: str = ""):
+def check(rc: int, what: str = "call"):
     if rc != 0:
         msg = lib().vla_last_error().decode("utf-8", "replace")
         raise VLAError(f"{what} failed (rc={rc}): {msg}")
@@ -52,3 +115,8 @@ def ptr(t):
 def cur_stream():
     import torch
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def norm_array(mean, std):
+    flat = [float(v) for s in mean for v in s] + [float(v) for s in std for v in s]
+    return (c_float * 12)(*flat)

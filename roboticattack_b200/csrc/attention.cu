@@ -1,0 +1,456 @@
+// Fused multi-head attention forward + backward (flash-style, no materialised score matrix or mask).
+//
+// Replaces F.scaled_dot_product_attention in timm Attention (DINOv2: 16 heads x 64, N=261; SigLIP: 16 heads x 72,
+// N=256; non-causal) and HF LlamaSdpaAttention (32 heads x 128, L~289, causal AND key-padding: the reference builds
+// an additive 4-D mask, which pushes SDPA onto its mem-efficient/math backend) and their autograd backward.
+// Masking is done in-kernel from (causal, kv_len[b]).
+//
+// Round-1 implementation: legacy warp-level tensor-core path (ldmatrix + mma.sync m16n8k16, fp32 softmax
+// statistics in registers).  Attention is ~1.3 % of the step's FLOPs; the tcgen05 GEMM carries the
+// rest.  Head dim is padded to a multiple of 16 in shared memory (72 -> 80, zero filled).
+//
+// Layout: qkv [B*N, 3*H*hd] = [q | k | v] with heads contiguous inside each third (the natural output of the fused
+// qkv GEMM); o, dout [B*N, H*hd]; lse, delta [B, H, N] fp32.
+#include <math.h>
+
+#include "kernels.h"
+
+namespace {
+
+constexpr int BM = 64;   // rows of the "outer" tile owned by a CTA (4 warps x 16 rows)
+constexpr int BN = 64;   // rows of the streamed tile
+constexpr int ATT_THREADS = 128;
+constexpr float LOG2E = 1.4426950408889634f;
+
+// ---- shared-memory tile helpers ------------------------------------------------------------------------
+// Copy rows [r0, r0+64) x cols [0, hd) of a head slice (global row stride ldg) into smem [64][LD], zero filling
+// rows >= nrows and the hd..HDP padding.
+template <int HDP>
+__device__ __forceinline__ void load_tile(bf16* __restrict__ s, const bf16* __restrict__ g, int64_t ldg, int r0, int nrows,
+                                          int hd) {
+  constexpr int LD = HDP + 8;
+  constexpr int CH = HDP / 8;
+  for (int idx = threadIdx.x; idx < 64 * CH; idx += ATT_THREADS) {
+    const int r = idx / CH, c = idx % CH;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r0 + r < nrows && c * 8 < hd) v = *reinterpret_cast<const uint4*>(g + static_cast<int64_t>(r0 + r) * ldg + c * 8);
+    *reinterpret_cast<uint4*>(s + r * LD + c * 8) = v;
+  }
+}
+
+// acc[NT][4] (16 x NT*8, fp32) += A(16 x K16*16) * B.
+//   A: registers a[K16][4] (mma A-fragment order) when A_REG, else smem rows a_row0.. (row stride lda), cols k.
+//   B_TRANS == false: Bs is [n][k] (contraction along smem columns), n range starts at b_row0.
+//   B_TRANS == true : Bs is [k][n] (contraction along smem rows),    k range starts at b_row0.
+template <int NT, int K16, bool B_TRANS, bool A_REG>
+__device__ __forceinline__ void warp_gemm(float (&acc)[NT][4], const uint32_t (*a_reg)[4], const bf16* __restrict__ As,
+                                          int lda, int a_row0, const bf16* __restrict__ Bs, int ldb, int b_row0) {
+  const int lane = threadIdx.x & 31;
+  const int mi = lane >> 3, r = lane & 7;
+#pragma unroll
+  for (int ks = 0; ks < K16; ++ks) {
+    uint32_t a[4];
+    if (A_REG) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = a_reg[ks][q];
+    } else {
+      ldmatrix_x4(a, smem_u32(As + (a_row0 + (mi & 1) * 8 + r) * lda + ks * 16 + (mi >> 1) * 8));
+    }
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t b[4];
+      if (!B_TRANS)
+        ldmatrix_x4(b, smem_u32(Bs + (b_row0 + (np * 2 + (mi >> 1)) * 8 + r) * ldb + ks * 16 + (mi & 1) * 8));
+      else
+        ldmatrix_x4_trans(b, smem_u32(Bs + (b_row0 + ks * 16 + (mi & 1) * 8 + r) * ldb + (np * 2 + (mi >> 1)) * 8));
+      mma_bf16_16816(acc[np * 2], a, b[0], b[1]);
+      mma_bf16_16816(acc[np * 2 + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+// C-fragment (16 x 64 fp32, 8 n-tiles) -> A-fragments (4 k-steps) in bf16
+__device__ __forceinline__ void acc_to_afrag(const float (&c)[8][4], uint32_t (&a)[4][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    a[ks][0] = pack_bf16x2(c[2 * ks][0], c[2 * ks][1]);
+    a[ks][1] = pack_bf16x2(c[2 * ks][2], c[2 * ks][3]);
+    a[ks][2] = pack_bf16x2(c[2 * ks + 1][0], c[2 * ks + 1][1]);
+    a[ks][3] = pack_bf16x2(c[2 * ks + 1][2], c[2 * ks + 1][3]);
+  }
+}
+
+template <int HDP>
+struct SmemLayout {
+  static constexpr int LD = HDP + 8;
+  static constexpr int TILE = 64 * LD;   // elements
+};
+
+// =========================================================================================================
+// forward
+// =========================================================================================================
+template <int HDP>
+__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
+                                                               float* __restrict__ lse, const int* __restrict__ kv_len, int N,
+                                                               int H, int hd, int causal, float scale) {
+  using L = SmemLayout<HDP>;
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_att);
+  bf16* sK = sQ + L::TILE;
+  bf16* sV = sK + L::TILE;
+
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int D = H * hd;
+  const int64_t ld = 3 * static_cast<int64_t>(D);
+  const bf16* base = qkv + static_cast<int64_t>(b) * N * ld + h * hd;
+  const int klen = kv_len ? min(kv_len[b], N) : N;
+  const float sl2 = scale * LOG2E;
+
+  load_tile<HDP>(sQ, base, ld, q0, N, hd);
+
+  float acc_o[HDP / 8][4];
+#pragma unroll
+  for (int i = 0; i < HDP / 8; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc_o[i][k] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+  const int kv_end = causal ? min(klen, q0 + BM) : klen;
+  for (int j0 = 0; j0 < kv_end; j0 += BN) {
+    __syncthreads();   // previous iteration's reads of sK/sV are done (also orders the sQ fill)
+    load_tile<HDP>(sK, base + D, ld, j0, N, hd);
+    load_tile<HDP>(sV, base + 2 * D, ld, j0, N, hd);
+    __syncthreads();
+
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[i][k] = 0.f;
+    warp_gemm<8, HDP / 16, false, false>(s, nullptr, sQ, L::LD, warp * 16, sK, L::LD, 0);
+
+    // mask + online softmax (rows g and g+8 of this warp's 16)
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int col = j0 + nt * 8 + 2 * t + (k & 1);
+        const int row = q0 + warp * 16 + g + (k >> 1) * 8;
+        const bool ok = (col < klen) && (!causal || col <= row);
+        s[nt][k] = ok ? s[nt][k] * sl2 : -INFINITY;
+        mx[k >> 1] = fmaxf(mx[k >> 1], s[nt][k]);
+      }
+    float alpha[2], mnew[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      mnew[r] = fmaxf(m_run[r], mx[r]);
+      const float mref = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
+      alpha[r] = exp2f(m_run[r] - mref);   // m_run = -inf -> 0
+      m_run[r] = mnew[r];
+      mnew[r] = mref;
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float p = exp2f(s[nt][k] - mnew[k >> 1]);
+        s[nt][k] = p;
+        rs[k >> 1] += p;
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+      l_run[r] = l_run[r] * alpha[r] + rs[r];
+    }
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) {
+      acc_o[i][0] *= alpha[0];
+      acc_o[i][1] *= alpha[0];
+      acc_o[i][2] *= alpha[1];
+      acc_o[i][3] *= alpha[1];
+    }
+    uint32_t pa[4][4];
+    acc_to_afrag(s, pa);
+    warp_gemm<HDP / 8, 4, true, true>(acc_o, pa, nullptr, 0, 0, sV, L::LD, 0);
+  }
+
+  // epilogue: O / l, LSE (natural log)
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = q0 + warp * 16 + g + r * 8;
+    if (row >= N) continue;
+    const float inv = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
+    bf16* orow = o + (static_cast<int64_t>(b) * N + row) * D + h * hd;
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) {
+      const int col = i * 8 + 2 * t;
+      if (col < hd)
+        *reinterpret_cast<uint32_t*>(orow + col) = pack_bf16x2(acc_o[i][r * 2] * inv, acc_o[i][r * 2 + 1] * inv);
+    }
+    if (t == 0)
+      lse[(static_cast<int64_t>(b) * H + h) * N + row] =
+          (l_run[r] > 0.f) ? (m_run[r] + log2f(l_run[r])) / LOG2E : -INFINITY;
+  }
+}
+
+// =========================================================================================================
+// backward
+// =========================================================================================================
+// delta[b,h,n] = sum_d dO * O   (one warp per (row, head))
+__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta, int B,
+                                  int N, int H, int hd) {
+  const int64_t w = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= static_cast<int64_t>(B) * N * H) return;
+  const int h = static_cast<int>(w % H);
+  const int64_t row = w / H;   // b*N + n
+  const bf16* po = o + row * H * hd + h * hd;
+  const bf16* pd = dout + row * H * hd + h * hd;
+  float s = 0.f;
+  for (int c = lane * 2; c < hd; c += 64) {
+    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(po + c));
+    const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(pd + c));
+    s += a.x * d.x + a.y * d.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const int n = static_cast<int>(row % N), b = static_cast<int>(row / N);
+    delta[(static_cast<int64_t>(b) * H + h) * N + n] = s;
+  }
+}
+
+// dQ: CTA owns 64 query rows, streams K/V tiles.
+template <int HDP>
+__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                                  const float* __restrict__ lse, const float* __restrict__ delta,
+                                                                  bf16* __restrict__ dqkv, const int* __restrict__ kv_len, int N,
+                                                                  int H, int hd, int causal, float scale) {
+  using L = SmemLayout<HDP>;
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_att);
+  bf16* sdO = sQ + L::TILE;
+  bf16* sK = sdO + L::TILE;
+  bf16* sV = sK + L::TILE;
+
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int D = H * hd;
+  const int64_t ld = 3 * static_cast<int64_t>(D);
+  const bf16* base = qkv + static_cast<int64_t>(b) * N * ld + h * hd;
+  const int klen = kv_len ? min(kv_len[b], N) : N;
+  const float sl2 = scale * LOG2E;
+
+  load_tile<HDP>(sQ, base, ld, q0, N, hd);
+  load_tile<HDP>(sdO, dout + static_cast<int64_t>(b) * N * D + h * hd, D, q0, N, hd);
+
+  float lse2[2], dl[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = q0 + warp * 16 + g + r * 8;
+    const bool ok = row < N;
+    const float l = ok ? lse[(static_cast<int64_t>(b) * H + h) * N + row] : INFINITY;
+    lse2[r] = (l == -INFINITY) ? INFINITY : l * LOG2E;   // fully masked / padded rows -> p = 0
+    dl[r] = ok ? delta[(static_cast<int64_t>(b) * H + h) * N + row] : 0.f;
+  }
+
+  float acc_dq[HDP / 8][4];
+#pragma unroll
+  for (int i = 0; i < HDP / 8; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc_dq[i][k] = 0.f;
+
+  const int kv_end = causal ? min(klen, q0 + BM) : klen;
+  for (int j0 = 0; j0 < kv_end; j0 += BN) {
+    __syncthreads();
+    load_tile<HDP>(sK, base + D, ld, j0, N, hd);
+    load_tile<HDP>(sV, base + 2 * D, ld, j0, N, hd);
+    __syncthreads();
+
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[i][k] = dp[i][k] = 0.f;
+    warp_gemm<8, HDP / 16, false, false>(s, nullptr, sQ, L::LD, warp * 16, sK, L::LD, 0);
+    warp_gemm<8, HDP / 16, false, false>(dp, nullptr, sdO, L::LD, warp * 16, sV, L::LD, 0);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int col = j0 + nt * 8 + 2 * t + (k & 1);
+        const int row = q0 + warp * 16 + g + (k >> 1) * 8;
+        const bool ok = (col < klen) && (!causal || col <= row);
+        const float p = ok ? exp2f(s[nt][k] * sl2 - lse2[k >> 1]) : 0.f;
+        s[nt][k] = p * (dp[nt][k] - dl[k >> 1]);   // dS
+      }
+    uint32_t dsa[4][4];
+    acc_to_afrag(s, dsa);
+    warp_gemm<HDP / 8, 4, true, true>(acc_dq, dsa, nullptr, 0, 0, sK, L::LD, 0);
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = q0 + warp * 16 + g + r * 8;
+    if (row >= N) continue;
+    bf16* drow = dqkv + (static_cast<int64_t>(b) * N + row) * ld + h * hd;
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) {
+      const int col = i * 8 + 2 * t;
+      if (col < hd)
+        *reinterpret_cast<uint32_t*>(drow + col) = pack_bf16x2(acc_dq[i][r * 2] * scale, acc_dq[i][r * 2 + 1] * scale);
+    }
+  }
+}
+
+// dK, dV: CTA owns 64 key/value rows, streams Q/dO tiles; works on the transposed score tile S^T = K Q^T.
+template <int HDP>
+__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                                   const float* __restrict__ lse, const float* __restrict__ delta,
+                                                                   bf16* __restrict__ dqkv, const int* __restrict__ kv_len, int N,
+                                                                   int H, int hd, int causal, float scale) {
+  using L = SmemLayout<HDP>;
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  bf16* sK = reinterpret_cast<bf16*>(smem_att);
+  bf16* sV = sK + L::TILE;
+  bf16* sQ = sV + L::TILE;
+  bf16* sdO = sQ + L::TILE;
+  float* sLse = reinterpret_cast<float*>(sdO + L::TILE);
+  float* sDelta = sLse + 64;
+
+  const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * BM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int D = H * hd;
+  const int64_t ld = 3 * static_cast<int64_t>(D);
+  const bf16* base = qkv + static_cast<int64_t>(b) * N * ld + h * hd;
+  const int klen = kv_len ? min(kv_len[b], N) : N;
+  const float sl2 = scale * LOG2E;
+
+  load_tile<HDP>(sK, base + D, ld, j0, N, hd);
+  load_tile<HDP>(sV, base + 2 * D, ld, j0, N, hd);
+
+  float acc_dk[HDP / 8][4], acc_dv[HDP / 8][4];
+#pragma unroll
+  for (int i = 0; i < HDP / 8; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc_dk[i][k] = acc_dv[i][k] = 0.f;
+
+  const bool tile_live = j0 < klen;   // a fully masked key tile gets zero gradients
+  const int q_begin = causal ? (j0 / BN) * BN : 0;   // queries before this key tile never see it
+  for (int q0 = q_begin; tile_live && q0 < N; q0 += BN) {
+    __syncthreads();
+    load_tile<HDP>(sQ, base, ld, q0, N, hd);
+    load_tile<HDP>(sdO, dout + static_cast<int64_t>(b) * N * D + h * hd, D, q0, N, hd);
+    if (threadIdx.x < 64) {
+      const int row = q0 + threadIdx.x;
+      const float l = row < N ? lse[(static_cast<int64_t>(b) * H + h) * N + row] : INFINITY;
+      sLse[threadIdx.x] = (l == -INFINITY) ? INFINITY : l * LOG2E;
+      sDelta[threadIdx.x] = row < N ? delta[(static_cast<int64_t>(b) * H + h) * N + row] : 0.f;
+    }
+    __syncthreads();
+
+    // S^T (16 kv x 64 q) and dP^T = V dO^T
+    float st[8][4], dpt[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st[i][k] = dpt[i][k] = 0.f;
+    warp_gemm<8, HDP / 16, false, false>(st, nullptr, sK, L::LD, warp * 16, sQ, L::LD, 0);
+    warp_gemm<8, HDP / 16, false, false>(dpt, nullptr, sV, L::LD, warp * 16, sdO, L::LD, 0);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int qc = nt * 8 + 2 * t + (k & 1);          // query index inside the tile (column of S^T)
+        const int qrow = q0 + qc;
+        const int kcol = j0 + warp * 16 + g + (k >> 1) * 8;   // key index (row of S^T)
+        const bool ok = (qrow < N) && (kcol < klen) && (!causal || kcol <= qrow);
+        const float p = ok ? exp2f(st[nt][k] * sl2 - sLse[qc]) : 0.f;
+        st[nt][k] = p;                                   // P^T
+        dpt[nt][k] = p * (dpt[nt][k] - sDelta[qc]);      // dS^T
+      }
+    uint32_t pa[4][4], dsa[4][4];
+    acc_to_afrag(st, pa);
+    acc_to_afrag(dpt, dsa);
+    warp_gemm<HDP / 8, 4, true, true>(acc_dv, pa, nullptr, 0, 0, sdO, L::LD, 0);   // dV += P^T dO
+    warp_gemm<HDP / 8, 4, true, true>(acc_dk, dsa, nullptr, 0, 0, sQ, L::LD, 0);   // dK += dS^T Q
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = j0 + warp * 16 + g + r * 8;
+    if (row >= N) continue;
+    bf16* drow = dqkv + (static_cast<int64_t>(b) * N + row) * ld + h * hd;
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) {
+      const int col = i * 8 + 2 * t;
+      if (col < hd) {
+        *reinterpret_cast<uint32_t*>(drow + D + col) = pack_bf16x2(acc_dk[i][r * 2] * scale, acc_dk[i][r * 2 + 1] * scale);
+        *reinterpret_cast<uint32_t*>(drow + 2 * D + col) = pack_bf16x2(acc_dv[i][r * 2], acc_dv[i][r * 2 + 1]);
+      }
+    }
+  }
+}
+
+template <int HDP>
+int launch_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
+               cudaStream_t s) {
+  constexpr int smem = 3 * SmemLayout<HDP>::TILE * 2;
+  static bool configured = false;
+  if (!configured) {
+    VLA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(N, BM), H, B);
+  attn_fwd_kernel<HDP><<<grid, ATT_THREADS, smem, s>>>(qkv, o, lse, kv_len, N, H, hd, causal, 1.f / sqrtf(static_cast<float>(hd)));
+  VLA_LAUNCH_CHECK();
+  ++g_vla_launch_count;
+  return 0;
+}
+
+template <int HDP>
+int launch_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
+               const int* kv_len, int B, int N, int H, int hd, int causal, cudaStream_t s) {
+  constexpr int smem_dq = 4 * SmemLayout<HDP>::TILE * 2;
+  constexpr int smem_dkv = 4 * SmemLayout<HDP>::TILE * 2 + 2 * 64 * 4;
+  static bool configured = false;
+  if (!configured) {
+    VLA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq));
+    VLA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv));
+    configured = true;
+  }
+  const float scale = 1.f / sqrtf(static_cast<float>(hd));
+  const int64_t nwarps = static_cast<int64_t>(B) * N * H;
+  attn_delta_kernel<<<static_cast<unsigned>(ceil_div64(nwarps * 32, 256)), 256, 0, s>>>(o, dout, delta, B, N, H, hd);
+  VLA_LAUNCH_CHECK();
+  dim3 grid(ceil_div(N, BM), H, B);
+  attn_bwd_dq_kernel<HDP><<<grid, ATT_THREADS, smem_dq, s>>>(qkv, dout, lse, delta, dqkv, kv_len, N, H, hd, causal, scale);
+  VLA_LAUNCH_CHECK();
+  attn_bwd_dkv_kernel<HDP><<<grid, ATT_THREADS, smem_dkv, s>>>(qkv, dout, lse, delta, dqkv, kv_len, N, H, hd, causal, scale);
+  VLA_LAUNCH_CHECK();
+  g_vla_launch_count += 3;
+  return 0;
+}
+
+}  // namespace
+
+int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
+                  cudaStream_t s) {
+  VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
+  if (hd <= 64) return launch_fwd<64>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
+  if (hd <= 80) return launch_fwd<80>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
+  return launch_fwd<128>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
+}
+
+int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
+                  const int* kv_len, int B, int N, int H, int hd, int causal, cudaStream_t s) {
+  VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
+  if (hd <= 64) return launch_bwd<64>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, s);
+  if (hd <= 80) return launch_bwd<80>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, s);
+  return launch_bwd<128>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, s);
+}

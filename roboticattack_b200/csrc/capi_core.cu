@@ -1,10 +1,9 @@
-// Error state + misc C-ABI entry points (see include/vla_b200.h).
+// Error state + the building-block entry points of include/vla_b200.h (thin casts onto kernels.h).
 #include <stdarg.h>
 #include <string.h>
 
 #include "../../include/vla_b200.h"
-#include "common.cuh"
-#include "gemm.h"
+#include "kernels.h"
 
 static thread_local char g_err[1024] = "";
 
@@ -15,21 +14,98 @@ void vla_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-extern "C" const char* vla_last_error(void) { return g_err; }
-extern "C" int vla_abi_version(void) { return VLA_B200_ABI_VERSION; }
-extern "C" long long vla_launch_count(void) { return g_vla_launch_count; }
+static_assert(VLA_FE_WARP == FE_MODE_WARP && VLA_FE_NONE == FE_MODE_NONE, "front-end mode enums diverged");
+static_assert(VLA_LOSS_UADA == LOSS_UADA && VLA_LOSS_NEG_CE == LOSS_NEG_CE, "loss enums diverged");
+static_assert(VLA_NUM_SCALARS == LOSS_NUM_SCALARS && VLA_S_GRAD_MEAN == LS_GRAD_MEAN, "scalar enums diverged");
+static_assert(VLA_OPT_PGD == OPT_PGD, "optimiser enums diverged");
 
-extern "C" int vla_gemm_bf16_tn(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldc, int M,
-                                int N, int K, const void* bias, const void* gamma, const void* resid, int64_t ldr,
-                                int act, void* preact_out, int out_f32, void* stream) {
+#define S(x) static_cast<cudaStream_t>(x)
+#define BF(x) static_cast<bf16*>(x)
+#define CBF(x) static_cast<const bf16*>(x)
+
+static FrontendNorm make_norm(const float* n) {
+  FrontendNorm r;
+  for (int s = 0; s < 2; ++s)
+    for (int c = 0; c < 3; ++c) {
+      r.mean[s][c] = n[s * 3 + c];
+      r.std[s][c] = n[6 + s * 3 + c];
+    }
+  return r;
+}
+
+extern "C" {
+
+const char* vla_last_error(void) { return g_err; }
+int vla_abi_version(void) { return VLA_B200_ABI_VERSION; }
+long long vla_launch_count(void) { return g_vla_launch_count; }
+
+int vla_patch_frontend_fwd(const uint8_t* obs, const float* patch, const int32_t* xy, const float* theta, void* out, int B,
+                           int H, int W, int ph, int pw, int mode, const float* norm, void* stream) {
+  VLA_REQUIRE(obs && out && norm, "vla_patch_frontend_fwd: null argument");
+  return patch_frontend_fwd(obs, patch, xy, theta, BF(out), B, H, W, ph, pw, mode, make_norm(norm), S(stream));
+}
+int vla_patch_frontend_bwd(const void* dout, const float* patch, const int32_t* xy, const float* theta, float* dpatch,
+                           int B, int H, int W, int ph, int pw, int mode, const float* norm, void* stream) {
+  VLA_REQUIRE(dout && dpatch && norm, "vla_patch_frontend_bwd: null argument");
+  return patch_frontend_bwd(CBF(dout), patch, xy, theta, dpatch, B, H, W, ph, pw, mode, make_norm(norm), S(stream));
+}
+int vla_loss_head(const float* logits, const int32_t* meta, int R, int V, int B, const vla_loss_params* lp, float* row_stats,
+                  void* dlogits, float* scalars, int32_t* pred_ids, void* stream) {
+  VLA_REQUIRE(logits && meta && lp && row_stats && dlogits && scalars && pred_ids, "vla_loss_head: null argument");
+  LossParams p{lp->kind, lp->mse_weight, lp->alpha, lp->belta, lp->ce_scale};
+  return loss_head_fwd_bwd(logits, meta, R, V, B, p, row_stats, BF(dlogits), scalars, pred_ids, S(stream));
+}
+int vla_patch_update(float* patch, const float* grad, float* m, float* v, int n, int step, float lr, float beta1, float beta2,
+                     float eps, int kind, float grad_scale, float clip_l1, float* scalars, void* stream) {
+  VLA_REQUIRE(patch && grad, "vla_patch_update: null argument");
+  return patch_update(patch, grad, m, v, n, step, lr, beta1, beta2, eps, kind, grad_scale, clip_l1, scalars, S(stream));
+}
+int vla_gemm_bf16_tn(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
+                     const void* bias, const void* gamma, const void* resid, int64_t ldr, int act, void* preact_out,
+                     int out_f32, void* stream) {
   GemmEpilogue e;
-  e.bias = static_cast<const bf16*>(bias);
-  e.gamma = static_cast<const bf16*>(gamma);
-  e.resid = static_cast<const bf16*>(resid);
+  e.bias = CBF(bias);
+  e.gamma = CBF(gamma);
+  e.resid = CBF(resid);
   e.ldr = ldr;
   e.act = act;
-  e.preact_out = static_cast<bf16*>(preact_out);
+  e.preact_out = BF(preact_out);
   e.out_f32 = out_f32;
-  return gemm_bf16_tn(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, out, ldc, M, N, K, e,
-                      static_cast<cudaStream_t>(stream));
+  return gemm_bf16_tn(CBF(A), lda, CBF(W), ldw, out, ldc, M, N, K, e, S(stream));
 }
+int vla_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t M, int d,
+                      float eps, void* stream) {
+  return layernorm_fwd(CBF(x), CBF(w), CBF(b), BF(y), mean, rstd, M, d, eps, S(stream));
+}
+int vla_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, const void* dres,
+                      void* dx, int64_t M, int d, void* stream) {
+  return layernorm_bwd(CBF(dy), CBF(x), CBF(w), mean, rstd, CBF(dres), BF(dx), M, d, S(stream));
+}
+int vla_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t M, int d, float eps, void* stream) {
+  return rmsnorm_fwd(CBF(x), CBF(w), BF(y), rstd, M, d, eps, S(stream));
+}
+int vla_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx, int64_t M,
+                    int d, void* stream) {
+  return rmsnorm_bwd(CBF(dy), CBF(x), CBF(w), rstd, CBF(dres), BF(dx), M, d, S(stream));
+}
+int vla_attention_fwd(const void* qkv, void* o, float* lse, const int32_t* kv_len, int B, int N, int H, int hd, int causal,
+                      void* stream) {
+  return attention_fwd(CBF(qkv), BF(o), lse, kv_len, B, N, H, hd, causal, S(stream));
+}
+int vla_attention_bwd(const void* qkv, const void* o, const void* dout, const float* lse, float* delta, void* dqkv,
+                      const int32_t* kv_len, int B, int N, int H, int hd, int causal, void* stream) {
+  return attention_bwd(CBF(qkv), CBF(o), CBF(dout), lse, delta, BF(dqkv), kv_len, B, N, H, hd, causal, S(stream));
+}
+int vla_rope_inplace(void* qkv, const float* cos_tab, const float* sin_tab, int64_t M, int L, int H, int hd, int dir,
+                     void* stream) {
+  return rope_inplace(BF(qkv), cos_tab, sin_tab, M, L, H, hd, dir, S(stream));
+}
+int vla_swiglu_fwd(const void* gu, void* act, int64_t M, int F, void* stream) { return swiglu_fwd(CBF(gu), BF(act), M, F, S(stream)); }
+int vla_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t M, int F, void* stream) {
+  return swiglu_bwd(CBF(dact), CBF(gu), BF(dgu), M, F, S(stream));
+}
+int vla_gelu_bwd(const void* dy, const void* pre, void* dx, int64_t n, void* stream) {
+  return gelu_bwd(CBF(dy), CBF(pre), BF(dx), n, S(stream));
+}
+
+}  // extern "C"

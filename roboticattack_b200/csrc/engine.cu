@@ -1,0 +1,833 @@
+// The attack-iteration engine: one forward + input-gradient pass of OpenVLA (DINOv2 + SigLIP ViTs -> projector ->
+// Llama -> action-logit loss) from the adversarial patch to d loss / d patch, as a fixed sequence of kernel launches
+// on one stream over a pre-planned activation arena (no allocation, no host synchronisation, no autograd graph).
+//
+// Replaces the body of the reference's inner loop -- UADA.py:134-148, UADA_ddp.py:192-206, UPA.py:134-152,
+// TMA.py:133-162: RandomPatchTransform -> self.vla(...) (modeling_prismatic.py:362-415 -> timm ViTs -> HF Llama)
+// -> loss head -> .backward().  Only input gradients are computed (the weights are frozen, as in UADA_ddp.py:50-51);
+// the unused last block of each vision tower and the lm_head rows without a label are skipped.
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vla_b200.h"
+#include "kernels.h"
+
+#define CK(expr)                  \
+  do {                            \
+    if (int _rc = (expr)) return _rc; \
+  } while (0)
+
+namespace {
+
+struct Slot {
+  size_t off = 0;   // element offset (bf16) into the weight arena
+  int rows = 0, cols = 0;
+  int loaded = 0, needed = 1;
+};
+
+struct VitDims {
+  int dim, depth, heads, mlp, npre, layerscale, used, ntok, hd;
+  std::string prefix;
+};
+
+struct VitBlockW {
+  const bf16 *n1w, *n1b, *qkv_w, *qkv_b, *proj_w, *proj_b, *ls1, *n2w, *n2b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *ls2;
+  const bf16 *qkv_t, *proj_t, *fc1_t, *fc2_t;
+};
+struct VitW {
+  const bf16 *pe_w, *pe_b, *pe_t, *pos, *cls, *reg;
+  std::vector<VitBlockW> blk;
+};
+struct LlamaLayerW {
+  const bf16 *n1, *n2, *qkv, *o, *gu, *down, *qkv_t, *o_t, *gu_t, *down_t;
+};
+
+struct VitActs {   // per tower
+  bf16* a_col;                    // im2col rows [B*np, kpad]
+  std::vector<bf16*> x;           // x[i]: residual stream entering block i; x[used] = tower output   [Mv, d]
+  std::vector<bf16*> qkv, attn_o, x_mid, fc1_pre;
+  std::vector<float*> mean1, rstd1, mean2, rstd2, lse;
+};
+struct LlmActs {
+  std::vector<bf16*> x;           // x[l]: residual stream entering layer l; x[layers] = final  [ML, h]
+  std::vector<bf16*> qkv, attn_o, x_mid, gu;
+  std::vector<float*> rstd1, rstd2, lse;
+};
+
+}  // namespace
+
+struct vla_engine {
+  vla_config cfg;
+  VitDims vit[2];
+  int np = 0, kpad = 0, grid = 0;
+  // weights
+  std::unordered_map<std::string, Slot> slots;
+  size_t weight_elems = 0;
+  bf16* warena = nullptr;
+  bool weights_resolved = false;
+  VitW vw[2];
+  const bf16 *pj_w[3], *pj_b[3], *pj_t[3];
+  const bf16 *embed, *final_norm, *lm_head, *lm_head_t;
+  std::vector<LlamaLayerW> lw;
+  // plan
+  int B = 0, T = 0, L = 0;
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  // batch state
+  int R = 0;
+  bool batch_set = false;
+  int n_place = 0;
+  // staging / activations
+  uint8_t* obs = nullptr;
+  int64_t* ids = nullptr;
+  int *kv_len = nullptr, *meta = nullptr, *sup_rows = nullptr;
+  int* xy = nullptr;
+  float* theta = nullptr;
+  float *rope_cos = nullptr, *rope_sin = nullptr;
+  bool rope_set = false;
+  bf16 *px = nullptr, *dpx = nullptr;
+  VitActs va[2];
+  bf16 *feats = nullptr, *p1_pre = nullptr, *p2_pre = nullptr;
+  LlmActs la;
+  bf16 *hs = nullptr, *hn = nullptr, *dlogits = nullptr;
+  float *rstd_f = nullptr, *logits = nullptr, *row_stats = nullptr, *delta = nullptr;
+  // transients
+  bf16 *t_norm = nullptr, *t_wide = nullptr, *t_wide2 = nullptr, *t_qkv = nullptr, *t_a = nullptr, *t_b = nullptr,
+       *t_c = nullptr, *t_d = nullptr;
+  FrontendNorm nrm;
+};
+
+namespace {
+
+constexpr int MAX_PLACEMENTS = 4096;
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+void add_slot(vla_engine* e, const std::string& name, int rows, int cols) {
+  Slot s;
+  s.off = e->weight_elems;
+  s.rows = rows;
+  s.cols = cols;
+  e->slots[name] = s;
+  e->weight_elems += align_up(static_cast<size_t>(rows) * cols, 128);   // 256-byte aligned slots
+}
+
+void add_matrix(vla_engine* e, const std::string& name, int out, int in) {
+  add_slot(e, name, out, in);
+  add_slot(e, name + "#T", in, out);
+}
+
+void build_slots(vla_engine* e) {
+  const vla_config& c = e->cfg;
+  for (int t = 0; t < 2; ++t) {
+    const VitDims& v = e->vit[t];
+    const std::string& p = v.prefix;
+    add_slot(e, p + "patch_embed.proj.weight", v.dim, e->kpad);
+    add_slot(e, p + "patch_embed.proj.weight#T", e->kpad, v.dim);
+    add_slot(e, p + "patch_embed.proj.bias", 1, v.dim);
+    add_slot(e, p + "pos_embed", e->np, v.dim);
+    if (v.npre) {
+      add_slot(e, p + "cls_token", 1, v.dim);
+      add_slot(e, p + "reg_token", v.npre - 1, v.dim);
+    }
+    for (int i = 0; i < v.used; ++i) {
+      const std::string b = p + "blocks." + std::to_string(i) + ".";
+      add_slot(e, b + "norm1.weight", 1, v.dim);
+      add_slot(e, b + "norm1.bias", 1, v.dim);
+      add_matrix(e, b + "attn.qkv.weight", 3 * v.dim, v.dim);
+      add_slot(e, b + "attn.qkv.bias", 1, 3 * v.dim);
+      add_matrix(e, b + "attn.proj.weight", v.dim, v.dim);
+      add_slot(e, b + "attn.proj.bias", 1, v.dim);
+      add_slot(e, b + "norm2.weight", 1, v.dim);
+      add_slot(e, b + "norm2.bias", 1, v.dim);
+      add_matrix(e, b + "mlp.fc1.weight", v.mlp, v.dim);
+      add_slot(e, b + "mlp.fc1.bias", 1, v.mlp);
+      add_matrix(e, b + "mlp.fc2.weight", v.dim, v.mlp);
+      add_slot(e, b + "mlp.fc2.bias", 1, v.dim);
+      if (v.layerscale) {
+        add_slot(e, b + "ls1.scale_factor", 1, v.dim);
+        add_slot(e, b + "ls2.scale_factor", 1, v.dim);
+      }
+    }
+  }
+  const int vd = c.dino_dim + c.sig_dim, ph = 4 * vd, h = c.llm_hidden, f = c.llm_ffn;
+  add_matrix(e, "projector.fc1.weight", ph, vd);
+  add_slot(e, "projector.fc1.bias", 1, ph);
+  add_matrix(e, "projector.fc2.weight", h, ph);
+  add_slot(e, "projector.fc2.bias", 1, h);
+  add_matrix(e, "projector.fc3.weight", h, h);
+  add_slot(e, "projector.fc3.bias", 1, h);
+  const std::string lm = "language_model.";
+  add_slot(e, lm + "model.embed_tokens.weight", c.vocab, h);
+  for (int l = 0; l < c.llm_layers; ++l) {
+    const std::string p = lm + "model.layers." + std::to_string(l) + ".";
+    add_slot(e, p + "input_layernorm.weight", 1, h);
+    add_slot(e, p + "post_attention_layernorm.weight", 1, h);
+    add_matrix(e, p + "self_attn.qkv_packed", 3 * h, h);     // filled from q_proj / k_proj / v_proj
+    add_matrix(e, p + "self_attn.o_proj.weight", h, h);
+    add_matrix(e, p + "mlp.gate_up_packed", 2 * f, h);       // filled from gate_proj / up_proj
+    add_matrix(e, p + "mlp.down_proj.weight", h, f);
+    e->slots[p + "self_attn.qkv_packed"].needed = 3;
+    e->slots[p + "mlp.gate_up_packed"].needed = 2;
+  }
+  add_slot(e, lm + "model.norm.weight", 1, h);
+  add_matrix(e, lm + "lm_head.weight", c.vocab, h);
+}
+
+const bf16* wptr(vla_engine* e, const std::string& name) {
+  auto it = e->slots.find(name);
+  return it == e->slots.end() ? nullptr : e->warena + it->second.off;
+}
+
+int resolve_weights(vla_engine* e) {
+  for (int t = 0; t < 2; ++t) {
+    const VitDims& v = e->vit[t];
+    const std::string& p = v.prefix;
+    VitW& w = e->vw[t];
+    w.pe_w = wptr(e, p + "patch_embed.proj.weight");
+    w.pe_t = wptr(e, p + "patch_embed.proj.weight#T");
+    w.pe_b = wptr(e, p + "patch_embed.proj.bias");
+    w.pos = wptr(e, p + "pos_embed");
+    w.cls = wptr(e, p + "cls_token");
+    w.reg = wptr(e, p + "reg_token");
+    w.blk.resize(v.used);
+    for (int i = 0; i < v.used; ++i) {
+      const std::string b = p + "blocks." + std::to_string(i) + ".";
+      VitBlockW& k = w.blk[i];
+      k.n1w = wptr(e, b + "norm1.weight");
+      k.n1b = wptr(e, b + "norm1.bias");
+      k.qkv_w = wptr(e, b + "attn.qkv.weight");
+      k.qkv_t = wptr(e, b + "attn.qkv.weight#T");
+      k.qkv_b = wptr(e, b + "attn.qkv.bias");
+      k.proj_w = wptr(e, b + "attn.proj.weight");
+      k.proj_t = wptr(e, b + "attn.proj.weight#T");
+      k.proj_b = wptr(e, b + "attn.proj.bias");
+      k.n2w = wptr(e, b + "norm2.weight");
+      k.n2b = wptr(e, b + "norm2.bias");
+      k.fc1_w = wptr(e, b + "mlp.fc1.weight");
+      k.fc1_t = wptr(e, b + "mlp.fc1.weight#T");
+      k.fc1_b = wptr(e, b + "mlp.fc1.bias");
+      k.fc2_w = wptr(e, b + "mlp.fc2.weight");
+      k.fc2_t = wptr(e, b + "mlp.fc2.weight#T");
+      k.fc2_b = wptr(e, b + "mlp.fc2.bias");
+      k.ls1 = wptr(e, b + "ls1.scale_factor");
+      k.ls2 = wptr(e, b + "ls2.scale_factor");
+    }
+  }
+  for (int i = 0; i < 3; ++i) {
+    const std::string n = "projector.fc" + std::to_string(i + 1);
+    e->pj_w[i] = wptr(e, n + ".weight");
+    e->pj_t[i] = wptr(e, n + ".weight#T");
+    e->pj_b[i] = wptr(e, n + ".bias");
+  }
+  const std::string lm = "language_model.";
+  e->embed = wptr(e, lm + "model.embed_tokens.weight");
+  e->final_norm = wptr(e, lm + "model.norm.weight");
+  e->lm_head = wptr(e, lm + "lm_head.weight");
+  e->lm_head_t = wptr(e, lm + "lm_head.weight#T");
+  e->lw.resize(e->cfg.llm_layers);
+  for (int l = 0; l < e->cfg.llm_layers; ++l) {
+    const std::string p = lm + "model.layers." + std::to_string(l) + ".";
+    LlamaLayerW& w = e->lw[l];
+    w.n1 = wptr(e, p + "input_layernorm.weight");
+    w.n2 = wptr(e, p + "post_attention_layernorm.weight");
+    w.qkv = wptr(e, p + "self_attn.qkv_packed");
+    w.qkv_t = wptr(e, p + "self_attn.qkv_packed#T");
+    w.o = wptr(e, p + "self_attn.o_proj.weight");
+    w.o_t = wptr(e, p + "self_attn.o_proj.weight#T");
+    w.gu = wptr(e, p + "mlp.gate_up_packed");
+    w.gu_t = wptr(e, p + "mlp.gate_up_packed#T");
+    w.down = wptr(e, p + "mlp.down_proj.weight");
+    w.down_t = wptr(e, p + "mlp.down_proj.weight#T");
+  }
+  e->weights_resolved = true;
+  return 0;
+}
+
+// ---- workspace plan ------------------------------------------------------------------------------------------
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+size_t plan(vla_engine* e, uint8_t* base, int B, int T) {
+  const vla_config& c = e->cfg;
+  Bump bp{base};
+  const int H = c.img, P = e->np, L = T + P;
+  const int64_t ML = static_cast<int64_t>(B) * L;
+  const int h = c.llm_hidden, f = c.llm_ffn, V = c.vocab;
+  const int Rmax = B * (T - 1);
+  e->obs = bp.take<uint8_t>(static_cast<size_t>(B) * H * H * 3);
+  e->ids = bp.take<int64_t>(static_cast<size_t>(B) * T);
+  e->kv_len = bp.take<int>(B);
+  e->meta = bp.take<int>(static_cast<size_t>(Rmax) * 3);
+  e->sup_rows = bp.take<int>(Rmax);
+  e->xy = bp.take<int>(static_cast<size_t>(MAX_PLACEMENTS) * 2);
+  e->theta = bp.take<float>(static_cast<size_t>(MAX_PLACEMENTS) * 6);
+  e->rope_cos = bp.take<float>(static_cast<size_t>(L) * (h / c.llm_heads / 2));
+  e->rope_sin = bp.take<float>(static_cast<size_t>(L) * (h / c.llm_heads / 2));
+  e->px = bp.take<bf16>(static_cast<size_t>(B) * 6 * H * H);
+  e->dpx = bp.take<bf16>(static_cast<size_t>(B) * 6 * H * H);
+  size_t max_md = 0, max_wide = 0, max_qkv = 0, max_lse = 0;
+  for (int t = 0; t < 2; ++t) {
+    const VitDims& v = e->vit[t];
+    VitActs& a = e->va[t];
+    const size_t Mv = static_cast<size_t>(B) * v.ntok;
+    a.a_col = bp.take<bf16>(static_cast<size_t>(B) * P * e->kpad);
+    a.x.assign(v.used + 1, nullptr);
+    a.qkv.assign(v.used, nullptr);
+    a.attn_o.assign(v.used, nullptr);
+    a.x_mid.assign(v.used, nullptr);
+    a.fc1_pre.assign(v.used, nullptr);
+    a.mean1.assign(v.used, nullptr);
+    a.rstd1.assign(v.used, nullptr);
+    a.mean2.assign(v.used, nullptr);
+    a.rstd2.assign(v.used, nullptr);
+    a.lse.assign(v.used, nullptr);
+    for (int i = 0; i <= v.used; ++i) a.x[i] = bp.take<bf16>(Mv * v.dim);
+    for (int i = 0; i < v.used; ++i) {
+      a.qkv[i] = bp.take<bf16>(Mv * 3 * v.dim);
+      a.attn_o[i] = bp.take<bf16>(Mv * v.dim);
+      a.x_mid[i] = bp.take<bf16>(Mv * v.dim);
+      a.fc1_pre[i] = bp.take<bf16>(Mv * v.mlp);
+      a.mean1[i] = bp.take<float>(Mv);
+      a.rstd1[i] = bp.take<float>(Mv);
+      a.mean2[i] = bp.take<float>(Mv);
+      a.rstd2[i] = bp.take<float>(Mv);
+      a.lse[i] = bp.take<float>(static_cast<size_t>(B) * v.heads * v.ntok);
+    }
+    max_md = std::max(max_md, Mv * v.dim);
+    max_wide = std::max(max_wide, Mv * v.mlp);
+    max_qkv = std::max(max_qkv, Mv * 3 * v.dim);
+    max_lse = std::max(max_lse, static_cast<size_t>(B) * v.heads * v.ntok);
+  }
+  const int vd = c.dino_dim + c.sig_dim, phd = 4 * vd;
+  const size_t MP = static_cast<size_t>(B) * P;
+  e->feats = bp.take<bf16>(MP * vd);
+  e->p1_pre = bp.take<bf16>(MP * phd);
+  e->p2_pre = bp.take<bf16>(MP * h);
+  max_wide = std::max(max_wide, MP * phd);
+  max_md = std::max(max_md, MP * static_cast<size_t>(std::max(h, vd)));
+  LlmActs& la = e->la;
+  const int NL = c.llm_layers;
+  la.x.assign(NL + 1, nullptr);
+  la.qkv.assign(NL, nullptr);
+  la.attn_o.assign(NL, nullptr);
+  la.x_mid.assign(NL, nullptr);
+  la.gu.assign(NL, nullptr);
+  la.rstd1.assign(NL, nullptr);
+  la.rstd2.assign(NL, nullptr);
+  la.lse.assign(NL, nullptr);
+  for (int l = 0; l <= NL; ++l) la.x[l] = bp.take<bf16>(ML * h);
+  for (int l = 0; l < NL; ++l) {
+    la.qkv[l] = bp.take<bf16>(ML * 3 * h);
+    la.attn_o[l] = bp.take<bf16>(ML * h);
+    la.x_mid[l] = bp.take<bf16>(ML * h);
+    la.gu[l] = bp.take<bf16>(ML * 2 * f);
+    la.rstd1[l] = bp.take<float>(ML);
+    la.rstd2[l] = bp.take<float>(ML);
+    la.lse[l] = bp.take<float>(static_cast<size_t>(B) * c.llm_heads * L);
+  }
+  max_md = std::max(max_md, static_cast<size_t>(ML) * h);
+  max_wide = std::max(max_wide, static_cast<size_t>(ML) * 2 * f);
+  max_qkv = std::max(max_qkv, static_cast<size_t>(ML) * 3 * h);
+  max_lse = std::max(max_lse, static_cast<size_t>(B) * c.llm_heads * L);
+  e->hs = bp.take<bf16>(static_cast<size_t>(Rmax) * h);
+  e->hn = bp.take<bf16>(static_cast<size_t>(Rmax) * h);
+  e->rstd_f = bp.take<float>(Rmax);
+  e->logits = bp.take<float>(static_cast<size_t>(Rmax) * V);
+  e->dlogits = bp.take<bf16>(static_cast<size_t>(Rmax) * V);
+  e->row_stats = bp.take<float>(loss_head_row_stats_floats(Rmax));
+  e->delta = bp.take<float>(max_lse);
+  e->t_norm = bp.take<bf16>(max_md);
+  e->t_wide = bp.take<bf16>(max_wide);
+  e->t_wide2 = bp.take<bf16>(max_wide);
+  e->t_qkv = bp.take<bf16>(max_qkv);
+  e->t_a = bp.take<bf16>(max_md);
+  e->t_b = bp.take<bf16>(max_md);
+  e->t_c = bp.take<bf16>(max_md);
+  e->t_d = bp.take<bf16>(max_md);
+  return align_up(bp.off, 256);
+}
+
+int G(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int64_t M, int N, int K,
+      const GemmEpilogue& ep, cudaStream_t s) {
+  return gemm_bf16_tn(A, lda, W, ldw, out, ldc, static_cast<int>(M), N, K, ep, s);
+}
+
+// ---- vision tower -----------------------------------------------------------------------------------------
+int vit_forward(vla_engine* e, int t, cudaStream_t s) {
+  const VitDims& v = e->vit[t];
+  const VitW& w = e->vw[t];
+  VitActs& a = e->va[t];
+  const int B = e->B, d = v.dim;
+  const int64_t Mv = static_cast<int64_t>(B) * v.ntok;
+  CK(write_prefix_tokens(w.cls, w.reg, a.x[0], B, v.ntok, v.npre, d, s));
+  {
+    GemmEpilogue ep;   // conv-as-GEMM + bias, + pos_embed (broadcast over batch), rows remapped past the prefix tokens
+    ep.bias = w.pe_b;
+    ep.resid = w.pos;
+    ep.ldr = d;
+    ep.resid_mod = e->np;
+    ep.out_group = e->np;
+    ep.out_stride = v.ntok;
+    ep.out_offset = v.npre;
+    CK(G(a.a_col, e->kpad, w.pe_w, e->kpad, a.x[0], d, static_cast<int64_t>(B) * e->np, d, e->kpad, ep, s));
+  }
+  for (int i = 0; i < v.used; ++i) {
+    const VitBlockW& k = w.blk[i];
+    CK(layernorm_fwd(a.x[i], k.n1w, k.n1b, e->t_norm, a.mean1[i], a.rstd1[i], Mv, d, e->cfg.vit_ln_eps, s));
+    {
+      GemmEpilogue ep;
+      ep.bias = k.qkv_b;
+      CK(G(e->t_norm, d, k.qkv_w, d, a.qkv[i], 3 * d, Mv, 3 * d, d, ep, s));
+    }
+    CK(attention_fwd(a.qkv[i], a.attn_o[i], a.lse[i], nullptr, B, v.ntok, v.heads, v.hd, 0, s));
+    {
+      GemmEpilogue ep;
+      ep.bias = k.proj_b;
+      ep.gamma = v.layerscale ? k.ls1 : nullptr;
+      ep.resid = a.x[i];
+      ep.ldr = d;
+      CK(G(a.attn_o[i], d, k.proj_w, d, a.x_mid[i], d, Mv, d, d, ep, s));
+    }
+    CK(layernorm_fwd(a.x_mid[i], k.n2w, k.n2b, e->t_norm, a.mean2[i], a.rstd2[i], Mv, d, e->cfg.vit_ln_eps, s));
+    {
+      GemmEpilogue ep;
+      ep.bias = k.fc1_b;
+      ep.act = 1;
+      ep.preact_out = a.fc1_pre[i];
+      CK(G(e->t_norm, d, k.fc1_w, d, e->t_wide, v.mlp, Mv, v.mlp, d, ep, s));
+    }
+    {
+      GemmEpilogue ep;
+      ep.bias = k.fc2_b;
+      ep.gamma = v.layerscale ? k.ls2 : nullptr;
+      ep.resid = a.x_mid[i];
+      ep.ldr = d;
+      CK(G(e->t_wide, v.mlp, k.fc2_w, v.mlp, a.x[i + 1], d, Mv, d, v.mlp, ep, s));
+    }
+  }
+  return 0;
+}
+
+// dx_in: gradient wrt the tower output in e->t_a ([Mv, d], prefix rows zero). Leaves d(im2col rows) in a.a_col.
+int vit_backward(vla_engine* e, int t, cudaStream_t s) {
+  const VitDims& v = e->vit[t];
+  const VitW& w = e->vw[t];
+  VitActs& a = e->va[t];
+  const int B = e->B, d = v.dim;
+  const int64_t Mv = static_cast<int64_t>(B) * v.ntok;
+  bf16* dx = e->t_a;       // gradient wrt x[i+1]
+  bf16* dxm = e->t_b;      // gradient wrt x_mid[i]
+  GemmEpilogue plain;
+  for (int i = v.used - 1; i >= 0; --i) {
+    const VitBlockW& k = w.blk[i];
+    const bf16* g = dx;
+    if (v.layerscale) {
+      CK(scale_cols(dx, k.ls2, e->t_c, Mv, d, s));
+      g = e->t_c;
+    }
+    CK(G(g, d, k.fc2_t, d, e->t_wide, v.mlp, Mv, v.mlp, d, plain, s));
+    CK(gelu_bwd(e->t_wide, a.fc1_pre[i], e->t_wide, Mv * v.mlp, s));
+    CK(G(e->t_wide, v.mlp, k.fc1_t, v.mlp, e->t_norm, d, Mv, d, v.mlp, plain, s));
+    CK(layernorm_bwd(e->t_norm, a.x_mid[i], k.n2w, a.mean2[i], a.rstd2[i], dx, dxm, Mv, d, s));
+    g = dxm;
+    if (v.layerscale) {
+      CK(scale_cols(dxm, k.ls1, e->t_c, Mv, d, s));
+      g = e->t_c;
+    }
+    CK(G(g, d, k.proj_t, d, e->t_d, d, Mv, d, d, plain, s));
+    CK(attention_bwd(a.qkv[i], a.attn_o[i], e->t_d, a.lse[i], e->delta, e->t_qkv, nullptr, B, v.ntok, v.heads, v.hd, 0, s));
+    CK(G(e->t_qkv, 3 * d, k.qkv_t, 3 * d, e->t_norm, d, Mv, d, 3 * d, plain, s));
+    CK(layernorm_bwd(e->t_norm, a.x[i], k.n1w, a.mean1[i], a.rstd1[i], dxm, dx, Mv, d, s));
+  }
+  // patch-token rows of d x[0] -> d conv output [B*np, d] -> d im2col rows [B*np, kpad]
+  CK(copy_rows(dx, d, v.ntok, v.npre, e->t_c, d, e->np, 0, B, e->np, d, s));
+  CK(G(e->t_c, d, w.pe_t, d, a.a_col, e->kpad, static_cast<int64_t>(B) * e->np, e->kpad, d, plain, s));
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+extern "C" int vla_engine_create(const vla_config* cfg, vla_engine** out) {
+  VLA_REQUIRE(cfg && out, "vla_engine_create: null argument");
+  VLA_REQUIRE(cfg->img % cfg->patch == 0, "image size %d is not a multiple of the ViT patch %d", cfg->img, cfg->patch);
+  VLA_REQUIRE(cfg->llm_hidden % cfg->llm_heads == 0 && cfg->dino_dim % cfg->dino_heads == 0 &&
+                  cfg->sig_dim % cfg->sig_heads == 0,
+              "hidden sizes must be divisible by head counts");
+  VLA_REQUIRE(cfg->vocab >= 32000, "vocabulary must contain the action ids 31744..31999");
+  vla_engine* e = new vla_engine();
+  e->cfg = *cfg;
+  e->grid = cfg->img / cfg->patch;
+  e->np = e->grid * e->grid;
+  e->kpad = static_cast<int>(align_up(3 * cfg->patch * cfg->patch, 64));
+  e->vit[0] = {cfg->dino_dim, cfg->dino_depth, cfg->dino_heads, cfg->dino_mlp, cfg->dino_prefix, cfg->dino_layerscale,
+               cfg->dino_depth - 1, e->np + cfg->dino_prefix, cfg->dino_dim / cfg->dino_heads,
+               "vision_backbone.featurizer."};
+  e->vit[1] = {cfg->sig_dim, cfg->sig_depth, cfg->sig_heads, cfg->sig_mlp, cfg->sig_prefix, cfg->sig_layerscale,
+               cfg->sig_depth - 1, e->np + cfg->sig_prefix, cfg->sig_dim / cfg->sig_heads,
+               "vision_backbone.fused_featurizer."};
+  for (int s = 0; s < 2; ++s)
+    for (int c = 0; c < 3; ++c) {
+      e->nrm.mean[s][c] = cfg->norm_mean[s][c];
+      e->nrm.std[s][c] = cfg->norm_std[s][c];
+    }
+  build_slots(e);
+  *out = e;
+  return 0;
+}
+
+extern "C" void vla_engine_destroy(vla_engine* e) { delete e; }
+
+extern "C" size_t vla_engine_weight_bytes(const vla_engine* e) { return e->weight_elems * sizeof(bf16); }
+
+extern "C" size_t vla_engine_workspace_bytes(vla_engine* e, int B, int T) {
+  vla_engine tmp = *e;   // plan() on a copy with a null base only measures
+  return plan(&tmp, nullptr, B, T);
+}
+
+extern "C" int vla_engine_set_buffers(vla_engine* e, void* weight_arena, size_t weight_bytes, void* workspace,
+                                      size_t workspace_bytes, int B, int T) {
+  VLA_REQUIRE(e && weight_arena && workspace, "vla_engine_set_buffers: null argument");
+  VLA_REQUIRE(B >= 1 && T >= 2, "vla_engine_set_buffers: need B >= 1 and T >= 2 (got %d, %d)", B, T);
+  VLA_REQUIRE(weight_bytes >= vla_engine_weight_bytes(e), "weight arena too small: %zu < %zu", weight_bytes,
+              vla_engine_weight_bytes(e));
+  const size_t need = vla_engine_workspace_bytes(e, B, T);
+  VLA_REQUIRE(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  VLA_REQUIRE((reinterpret_cast<uintptr_t>(weight_arena) & 255) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "arenas must be 256-byte aligned");
+  e->warena = static_cast<bf16*>(weight_arena);
+  e->ws = static_cast<uint8_t*>(workspace);
+  e->ws_bytes = workspace_bytes;
+  e->B = B;
+  e->T = T;
+  e->L = T + e->np;
+  plan(e, e->ws, B, T);
+  e->batch_set = false;
+  e->rope_set = false;
+  e->n_place = 0;
+  return resolve_weights(e);
+}
+
+// Copies one checkpoint tensor (bf16, device memory, HF name) into the arena, building the derived forms the kernels
+// use: K-padded conv weight, packed q|k|v and gate|up, and the transposed copy every input-gradient GEMM reads.
+extern "C" int vla_engine_load_weight(vla_engine* e, const char* name_c, const void* src_v, int64_t numel, void* stream) {
+  VLA_REQUIRE(e && e->warena, "vla_engine_load_weight: call vla_engine_set_buffers first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bf16* src = static_cast<const bf16*>(src_v);
+  std::string name(name_c);
+  const int h = e->cfg.llm_hidden, f = e->cfg.llm_ffn;
+  auto find = [&](const std::string& n) -> Slot* {
+    auto it = e->slots.find(n);
+    return it == e->slots.end() ? nullptr : &it->second;
+  };
+  // --- packed Llama projections ---
+  struct Pack { const char* suffix; const char* packed; int index; int rows; };
+  const Pack packs[] = {{"self_attn.q_proj.weight", "self_attn.qkv_packed", 0, h},
+                        {"self_attn.k_proj.weight", "self_attn.qkv_packed", 1, h},
+                        {"self_attn.v_proj.weight", "self_attn.qkv_packed", 2, h},
+                        {"mlp.gate_proj.weight", "mlp.gate_up_packed", 0, f},
+                        {"mlp.up_proj.weight", "mlp.gate_up_packed", 1, f}};
+  for (const Pack& pk : packs) {
+    const size_t sl = strlen(pk.suffix);
+    if (name.size() > sl && name.compare(name.size() - sl, sl, pk.suffix) == 0) {
+      const std::string pname = name.substr(0, name.size() - sl) + pk.packed;
+      Slot* sp = find(pname);
+      Slot* st = find(pname + "#T");
+      VLA_REQUIRE(sp && st, "unknown weight '%s'", name_c);
+      VLA_REQUIRE(numel == static_cast<int64_t>(pk.rows) * h, "weight '%s': expected %lld elements, got %lld", name_c,
+                  static_cast<long long>(pk.rows) * h, static_cast<long long>(numel));
+      bf16* dst = e->warena + sp->off + static_cast<size_t>(pk.index) * pk.rows * h;
+      VLA_CHECK_CUDA(cudaMemcpyAsync(dst, src, numel * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+      // transposed: [h, total_rows], this block occupies columns [index*rows, (index+1)*rows)
+      CK(transpose_bf16(src, h, e->warena + st->off + static_cast<size_t>(pk.index) * pk.rows, st->cols, pk.rows, h, s));
+      sp->loaded++;
+      st->loaded = sp->loaded;
+      return 0;
+    }
+  }
+  Slot* sp = find(name);
+  VLA_REQUIRE(sp, "unknown weight '%s' (not on the attack hot path)", name_c);
+  bf16* dst = e->warena + sp->off;
+  const std::string pe = "patch_embed.proj.weight";
+  if (name.size() > pe.size() && name.compare(name.size() - pe.size(), pe.size(), pe) == 0) {
+    const int kk = 3 * e->cfg.patch * e->cfg.patch;
+    VLA_REQUIRE(numel == static_cast<int64_t>(sp->rows) * kk, "weight '%s': expected %lld elements, got %lld", name_c,
+                static_cast<long long>(sp->rows) * kk, static_cast<long long>(numel));
+    VLA_CHECK_CUDA(cudaMemsetAsync(dst, 0, static_cast<size_t>(sp->rows) * sp->cols * sizeof(bf16), s));
+    VLA_CHECK_CUDA(cudaMemcpy2DAsync(dst, sp->cols * sizeof(bf16), src, kk * sizeof(bf16), kk * sizeof(bf16), sp->rows,
+                                     cudaMemcpyDeviceToDevice, s));
+  } else {
+    VLA_REQUIRE(numel == static_cast<int64_t>(sp->rows) * sp->cols, "weight '%s': expected %lld elements, got %lld", name_c,
+                static_cast<long long>(sp->rows) * sp->cols, static_cast<long long>(numel));
+    VLA_CHECK_CUDA(cudaMemcpyAsync(dst, src, numel * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+  }
+  sp->loaded++;
+  if (Slot* st = find(name + "#T")) {
+    CK(transpose_bf16(dst, sp->cols, e->warena + st->off, st->cols, sp->rows, sp->cols, s));
+    st->loaded = sp->loaded;
+  }
+  return 0;
+}
+
+extern "C" int vla_engine_weights_ready(vla_engine* e) {
+  int missing = 0;
+  std::string first;
+  for (auto& kv : e->slots)
+    if (kv.second.loaded < kv.second.needed) {
+      if (!missing) first = kv.first;
+      ++missing;
+    }
+  VLA_REQUIRE(missing == 0, "%d weight tensors not loaded (e.g. '%s')", missing, first.c_str());
+  return 0;
+}
+
+// cos / sin tables [L, head_dim/2] fp32 (host), computed by the caller exactly as HF LlamaRotaryEmbedding does
+// (fp32 outer product, cos/sin, cast to bf16) so that the engine and the oracle share them bit for bit.
+extern "C" int vla_engine_set_rope(vla_engine* e, const float* cos_host, const float* sin_host, int L, void* stream) {
+  VLA_REQUIRE(e && e->ws, "vla_engine_set_rope: call vla_engine_set_buffers first");
+  VLA_REQUIRE(L == e->L, "rope table length %d != planned sequence length %d", L, e->L);
+  const size_t n = static_cast<size_t>(L) * (e->cfg.llm_hidden / e->cfg.llm_heads / 2) * sizeof(float);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VLA_CHECK_CUDA(cudaMemcpyAsync(e->rope_cos, cos_host, n, cudaMemcpyHostToDevice, s));
+  VLA_CHECK_CUDA(cudaMemcpyAsync(e->rope_sin, sin_host, n, cudaMemcpyHostToDevice, s));
+  e->rope_set = true;
+  return 0;
+}
+
+// One outer iteration's batch (UADA.py:120-130): host tensors as the collator yields them (data_utils.py:183-217).
+// The clean observations stay on the device for all inner steps; supervised rows are located on the host once.
+extern "C" int vla_engine_set_batch(vla_engine* e, const uint8_t* obs, int obs_on_device, const int64_t* input_ids,
+                                    const uint8_t* attention_mask, const int64_t* labels, int B, int T, void* stream) {
+  VLA_REQUIRE(e && e->ws, "vla_engine_set_batch: call vla_engine_set_buffers first");
+  VLA_REQUIRE(B == e->B && T == e->T, "batch shape (%d, %d) != planned (%d, %d)", B, T, e->B, e->T);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int P = e->np, L = e->L;
+  std::vector<int> kv(B), meta, rows;
+  for (int b = 0; b < B; ++b) {
+    int n = 0;
+    bool ended = false;
+    for (int t = 0; t < T; ++t) {
+      if (attention_mask[b * T + t]) {
+        VLA_REQUIRE(!ended, "attention_mask of sample %d is not a right-padded prefix", b);
+        ++n;
+      } else {
+        ended = true;
+      }
+      const int64_t id = input_ids[b * T + t];
+      VLA_REQUIRE(id >= 0 && id < e->cfg.vocab, "input id %lld out of range", static_cast<long long>(id));
+    }
+    VLA_REQUIRE(n >= 1, "sample %d has an empty attention mask", b);
+    kv[b] = P + n;
+    int idx = 0;
+    for (int t = 1; t < T; ++t) {
+      const int64_t y = labels[b * T + t];
+      if (y == -100) continue;
+      VLA_REQUIRE(y >= 0 && y < e->cfg.vocab, "label %lld out of range", static_cast<long long>(y));
+      rows.push_back(b * L + P + t - 1);   // logits row that predicts text position t (shifted CE)
+      meta.push_back(static_cast<int>(y));
+      meta.push_back(b);
+      meta.push_back(idx++);
+    }
+  }
+  e->R = static_cast<int>(rows.size());
+  VLA_REQUIRE(e->R > 0, "no supervised tokens in the batch (all labels are -100)");
+  const size_t obs_bytes = static_cast<size_t>(B) * e->cfg.img * e->cfg.img * 3;
+  VLA_CHECK_CUDA(cudaMemcpyAsync(e->obs, obs, obs_bytes, obs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  VLA_CHECK_CUDA(cudaMemcpyAsync(e->ids, input_ids, sizeof(int64_t) * B * T, cudaMemcpyHostToDevice, s));
+  VLA_CHECK_CUDA(cudaMemcpyAsync(e->kv_len, kv.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+  VLA_CHECK_CUDA(cudaMemcpyAsync(e->meta, meta.data(), sizeof(int) * meta.size(), cudaMemcpyHostToDevice, s));
+  VLA_CHECK_CUDA(cudaMemcpyAsync(e->sup_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice, s));
+  VLA_CHECK_CUDA(cudaStreamSynchronize(s));   // the std::vectors above are pageable staging
+  e->batch_set = true;
+  return 0;
+}
+
+// Placements for the next `nsteps` inner iterations, drawn by the host RNG protocol (appply_random_transform.py:123-129)
+// in one go: xy int32 [nsteps, B, 2], theta float32 [nsteps, B, 2, 3].
+extern "C" int vla_engine_set_placements(vla_engine* e, const int* xy_host, const float* theta_host, int nsteps, void* stream) {
+  VLA_REQUIRE(e && e->ws, "vla_engine_set_placements: call vla_engine_set_buffers first");
+  VLA_REQUIRE(nsteps >= 1 && nsteps * e->B <= MAX_PLACEMENTS, "too many placements: %d steps x %d images > %d", nsteps, e->B,
+              MAX_PLACEMENTS);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VLA_CHECK_CUDA(cudaMemcpyAsync(e->xy, xy_host, sizeof(int) * 2 * nsteps * e->B, cudaMemcpyHostToDevice, s));
+  VLA_CHECK_CUDA(cudaMemcpyAsync(e->theta, theta_host, sizeof(float) * 6 * nsteps * e->B, cudaMemcpyHostToDevice, s));
+  VLA_CHECK_CUDA(cudaStreamSynchronize(s));
+  e->n_place = nsteps;
+  return 0;
+}
+
+extern "C" int vla_engine_num_supervised(const vla_engine* e) { return e->R; }
+
+extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, int step_idx, int fe_mode,
+                           const vla_loss_params* lp_c, float* dpatch, float* scalars, int* pred_ids, int flags,
+                           void* stream) {
+  VLA_REQUIRE(e && e->weights_resolved, "vla_fwd_bwd: engine not initialised");
+  VLA_REQUIRE(e->batch_set, "vla_fwd_bwd: call vla_engine_set_batch first");
+  VLA_REQUIRE(e->rope_set, "vla_fwd_bwd: call vla_engine_set_rope first");
+  VLA_REQUIRE(fe_mode == FE_MODE_NONE || (step_idx >= 0 && step_idx < e->n_place),
+              "vla_fwd_bwd: placement %d not uploaded (have %d)", step_idx, e->n_place);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const vla_config& c = e->cfg;
+  const int B = e->B, T = e->T, L = e->L, P = e->np, H = c.img;
+  const int h = c.llm_hidden, f = c.llm_ffn, V = c.vocab, NH = c.llm_heads, hd = h / NH;
+  const int64_t ML = static_cast<int64_t>(B) * L;
+  const int64_t MP = static_cast<int64_t>(B) * P;
+  const int vd = c.dino_dim + c.sig_dim, phd = 4 * vd;
+  const int* xy = e->xy + static_cast<size_t>(step_idx < 0 ? 0 : step_idx) * B * 2;
+  const float* th = e->theta + static_cast<size_t>(step_idx < 0 ? 0 : step_idx) * B * 6;
+  LossParams lp{lp_c->kind, lp_c->mse_weight, lp_c->alpha, lp_c->belta, lp_c->ce_scale};
+  GemmEpilogue plain;
+
+  // ---------------- forward ----------------
+  CK(patch_frontend_fwd(e->obs, patch, xy, th, e->px, B, H, H, ph, pw, fe_mode, e->nrm, s));
+  CK(im2col_patches(e->px, e->va[0].a_col, e->va[1].a_col, B, H, H, c.patch, e->kpad, s));
+  int col_off = 0;
+  for (int t = 0; t < 2; ++t) {
+    CK(vit_forward(e, t, s));
+    const VitDims& v = e->vit[t];
+    CK(copy_rows(e->va[t].x[v.used], v.dim, v.ntok, v.npre, e->feats + col_off, vd, P, 0, B, P, v.dim, s));
+    col_off += v.dim;
+  }
+  {
+    GemmEpilogue ep;
+    ep.bias = e->pj_b[0];
+    ep.act = 1;
+    ep.preact_out = e->p1_pre;
+    CK(G(e->feats, vd, e->pj_w[0], vd, e->t_wide, phd, MP, phd, vd, ep, s));
+    GemmEpilogue ep2;
+    ep2.bias = e->pj_b[1];
+    ep2.act = 1;
+    ep2.preact_out = e->p2_pre;
+    CK(G(e->t_wide, phd, e->pj_w[1], phd, e->t_a, h, MP, h, phd, ep2, s));
+    GemmEpilogue ep3;   // fc3 writes straight into rows 1..P of each sample's multimodal sequence
+    ep3.bias = e->pj_b[2];
+    ep3.out_group = P;
+    ep3.out_stride = L;
+    ep3.out_offset = 1;
+    CK(G(e->t_a, h, e->pj_w[2], h, e->la.x[0], h, MP, h, h, ep3, s));
+  }
+  CK(embed_tokens_splice(e->ids, e->embed, e->la.x[0], B, T, P, h, s));
+  LlmActs& la = e->la;
+  for (int l = 0; l < c.llm_layers; ++l) {
+    const LlamaLayerW& w = e->lw[l];
+    CK(rmsnorm_fwd(la.x[l], w.n1, e->t_norm, la.rstd1[l], ML, h, c.rms_eps, s));
+    CK(G(e->t_norm, h, w.qkv, h, la.qkv[l], 3 * h, ML, 3 * h, h, plain, s));
+    CK(rope_inplace(la.qkv[l], e->rope_cos, e->rope_sin, ML, L, NH, hd, +1, s));
+    CK(attention_fwd(la.qkv[l], la.attn_o[l], la.lse[l], e->kv_len, B, L, NH, hd, 1, s));
+    {
+      GemmEpilogue ep;
+      ep.resid = la.x[l];
+      ep.ldr = h;
+      CK(G(la.attn_o[l], h, w.o, h, la.x_mid[l], h, ML, h, h, ep, s));
+    }
+    CK(rmsnorm_fwd(la.x_mid[l], w.n2, e->t_norm, la.rstd2[l], ML, h, c.rms_eps, s));
+    CK(G(e->t_norm, h, w.gu, h, la.gu[l], 2 * f, ML, 2 * f, h, plain, s));
+    CK(swiglu_fwd(la.gu[l], e->t_wide, ML, f, s));
+    {
+      GemmEpilogue ep;
+      ep.resid = la.x_mid[l];
+      ep.ldr = h;
+      CK(G(e->t_wide, f, w.down, f, la.x[l + 1], h, ML, h, f, ep, s));
+    }
+  }
+  const int R = e->R;
+  CK(gather_rows(la.x[c.llm_layers], e->sup_rows, e->hs, R, h, s));
+  CK(rmsnorm_fwd(e->hs, e->final_norm, e->hn, e->rstd_f, R, h, c.rms_eps, s));
+  {
+    GemmEpilogue ep;
+    ep.out_f32 = 1;
+    CK(G(e->hn, h, e->lm_head, h, e->logits, V, R, V, h, ep, s));
+  }
+  CK(loss_head_fwd_bwd(e->logits, e->meta, R, V, B, lp, e->row_stats, e->dlogits, scalars, pred_ids, s));
+  if (flags & VLA_FLAG_FORWARD_ONLY) return 0;
+
+  // ---------------- backward (input gradients only) ----------------
+  CK(G(e->dlogits, V, e->lm_head_t, V, e->t_norm, h, R, h, V, plain, s));
+  CK(rmsnorm_bwd(e->t_norm, e->hs, e->final_norm, e->rstd_f, nullptr, e->hn, R, h, s));
+  bf16* dx = e->t_a;
+  bf16* dxm = e->t_b;
+  VLA_CHECK_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(ML) * h * sizeof(bf16), s));
+  CK(scatter_rows(e->hn, e->sup_rows, dx, R, h, s));
+  for (int l = c.llm_layers - 1; l >= 0; --l) {
+    const LlamaLayerW& w = e->lw[l];
+    CK(G(dx, h, w.down_t, h, e->t_wide, f, ML, f, h, plain, s));
+    CK(swiglu_bwd(e->t_wide, la.gu[l], e->t_wide2, ML, f, s));
+    CK(G(e->t_wide2, 2 * f, w.gu_t, 2 * f, e->t_norm, h, ML, h, 2 * f, plain, s));
+    CK(rmsnorm_bwd(e->t_norm, la.x_mid[l], w.n2, la.rstd2[l], dx, dxm, ML, h, s));
+    CK(G(dxm, h, w.o_t, h, e->t_d, h, ML, h, h, plain, s));
+    CK(attention_bwd(la.qkv[l], la.attn_o[l], e->t_d, la.lse[l], e->delta, e->t_qkv, e->kv_len, B, L, NH, hd, 1, s));
+    CK(rope_inplace(e->t_qkv, e->rope_cos, e->rope_sin, ML, L, NH, hd, -1, s));
+    CK(G(e->t_qkv, 3 * h, w.qkv_t, 3 * h, e->t_norm, h, ML, h, 3 * h, plain, s));
+    CK(rmsnorm_bwd(e->t_norm, la.x[l], w.n1, la.rstd1[l], dxm, dx, ML, h, s));
+  }
+  // d X0 rows 1..P -> projector backward
+  CK(copy_rows(dx, h, L, 1, e->t_c, h, P, 0, B, P, h, s));
+  CK(G(e->t_c, h, e->pj_t[2], h, e->t_d, h, MP, h, h, plain, s));
+  CK(gelu_bwd(e->t_d, e->p2_pre, e->t_d, MP * h, s));
+  CK(G(e->t_d, h, e->pj_t[1], h, e->t_wide, phd, MP, phd, h, plain, s));
+  CK(gelu_bwd(e->t_wide, e->p1_pre, e->t_wide, MP * phd, s));
+  CK(G(e->t_wide, phd, e->pj_t[0], phd, e->feats, vd, MP, vd, phd, plain, s));
+  col_off = 0;
+  for (int t = 0; t < 2; ++t) {
+    const VitDims& v = e->vit[t];
+    const int64_t Mv = static_cast<int64_t>(B) * v.ntok;
+    VLA_CHECK_CUDA(cudaMemsetAsync(e->t_a, 0, static_cast<size_t>(Mv) * v.dim * sizeof(bf16), s));
+    CK(copy_rows(e->feats + col_off, vd, P, 0, e->t_a, v.dim, v.ntok, v.npre, B, P, v.dim, s));
+    CK(vit_backward(e, t, s));
+    col_off += v.dim;
+  }
+  CK(col2im_patches(e->va[0].a_col, e->va[1].a_col, e->dpx, B, H, H, c.patch, e->kpad, s));
+  CK(patch_frontend_bwd(e->dpx, patch, xy, th, dpatch, B, H, H, ph, pw, fe_mode, e->nrm, s));
+  return 0;
+}
+
+// Debug / test taps: copy an internal activation to a caller buffer (device). Returns the element count.
+extern "C" int64_t vla_engine_debug_tap(vla_engine* e, const char* what_c, void* dst, int64_t max_bytes, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::string what(what_c);
+  const void* src = nullptr;
+  int64_t bytes = 0, elems = 0;
+  const vla_config& c = e->cfg;
+  auto set = [&](const void* p, int64_t n, int esz) { src = p; elems = n; bytes = n * esz; };
+  const int64_t ML = static_cast<int64_t>(e->B) * e->L;
+  if (what == "px") set(e->px, static_cast<int64_t>(e->B) * 6 * c.img * c.img, 2);
+  else if (what == "dpx") set(e->dpx, static_cast<int64_t>(e->B) * 6 * c.img * c.img, 2);
+  else if (what == "dino_out") set(e->va[0].x[e->vit[0].used], static_cast<int64_t>(e->B) * e->vit[0].ntok * e->vit[0].dim, 2);
+  else if (what == "siglip_out") set(e->va[1].x[e->vit[1].used], static_cast<int64_t>(e->B) * e->vit[1].ntok * e->vit[1].dim, 2);
+  else if (what == "dino_x0") set(e->va[0].x[0], static_cast<int64_t>(e->B) * e->vit[0].ntok * e->vit[0].dim, 2);
+  else if (what == "dino_x1") set(e->va[0].x[1], static_cast<int64_t>(e->B) * e->vit[0].ntok * e->vit[0].dim, 2);
+  else if (what == "llm_x0") set(e->la.x[0], ML * c.llm_hidden, 2);
+  else if (what == "llm_x1") set(e->la.x[1], ML * c.llm_hidden, 2);
+  else if (what == "llm_out") set(e->la.x[c.llm_layers], ML * c.llm_hidden, 2);
+  else if (what == "logits") set(e->logits, static_cast<int64_t>(e->R) * c.vocab, 4);
+  else if (what == "dlogits") set(e->dlogits, static_cast<int64_t>(e->R) * c.vocab, 2);
+  else if (what == "d_llm_x0") set(e->t_a, ML * c.llm_hidden, 2);
+  else {
+    vla_set_error("unknown tap '%s'", what_c);
+    return -1;
+  }
+  if (bytes > max_bytes) {
+    vla_set_error("tap '%s' needs %lld bytes, buffer has %lld", what_c, (long long)bytes, (long long)max_bytes);
+    return -1;
+  }
+  if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+    vla_set_error("tap copy failed");
+    return -1;
+  }
+  return elems;
+}

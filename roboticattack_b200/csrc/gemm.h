@@ -20,6 +20,11 @@ struct GemmEpilogue {
   int act = 0;
   bf16* preact_out = nullptr;  // same ld as out
   int out_f32 = 0;
+  // output row remap: row r -> (r / out_group) * out_stride + out_offset + r % out_group  (0 = identity); lets the
+  // patch-embed / projector GEMMs write straight into the token buffers ([cls,reg | patches], [BOS | patches | text])
+  int out_group = 0, out_stride = 0, out_offset = 0;
+  // resid row = r % resid_mod when > 0 (position embedding broadcast over the batch), else the output row
+  int resid_mod = 0;
 };
 
 // Returns 0 on success. No allocation, no synchronisation; launches on `stream`.

@@ -67,8 +67,10 @@ struct GemmCfg {
 };
 
 // One row x 32 columns of the accumulator -> global, with the fused epilogue.
-__device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const uint32_t (&acc)[32], int row, int col0) {
+__device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const uint32_t (&acc)[32], int row_in, int col0) {
   const GemmEpilogue& e = g.epi;
+  const int row = e.out_group ? (row_in / e.out_group) * e.out_stride + e.out_offset + row_in % e.out_group : row_in;
+  const int rrow = e.resid_mod ? row_in % e.resid_mod : row;
   const bool full = (col0 + 32 <= g.N);
   float x[32];
 #pragma unroll
@@ -92,7 +94,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = rbf(x[j]);
     if (e.preact_out) {
-      uint4* pp = reinterpret_cast<uint4*>(e.preact_out + static_cast<int64_t>(row) * g.ldc + col0);
+      uint4* pp = reinterpret_cast<uint4*>(e.preact_out + static_cast<int64_t>(row_in) * g.ldc + col0);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         pp[q] = make_uint4(pack_bf16x2(x[q * 8], x[q * 8 + 1]), pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]),
@@ -117,7 +119,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
       }
     }
     if (e.resid) {
-      const uint4* rp = reinterpret_cast<const uint4*>(e.resid + static_cast<int64_t>(row) * e.ldr + col0);
+      const uint4* rp = reinterpret_cast<const uint4*>(e.resid + static_cast<int64_t>(rrow) * e.ldr + col0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint4 u = rp[q];
@@ -150,10 +152,10 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
       float v = x[j];
       if (e.bias) v += b2f(e.bias[n]);
       v = rbf(v);
-      if (e.preact_out) e.preact_out[static_cast<int64_t>(row) * g.ldc + n] = f2b(v);
+      if (e.preact_out) e.preact_out[static_cast<int64_t>(row_in) * g.ldc + n] = f2b(v);
       if (e.act == 1) v = rbf(gelu_erf(v));
       if (e.gamma) v = rbf(v * b2f(e.gamma[n]));
-      if (e.resid) v = rbf(b2f(e.resid[static_cast<int64_t>(row) * e.ldr + n]) + v);
+      if (e.resid) v = rbf(b2f(e.resid[static_cast<int64_t>(rrow) * e.ldr + n]) + v);
       if (e.out_f32)
         static_cast<float*>(g.out)[static_cast<int64_t>(row) * g.ldc + n] = v;
       else

@@ -1,0 +1,86 @@
+// Host-side launchers of the non-GEMM kernels. All: no allocation, no synchronisation, return 0 on success.
+#pragma once
+#include "common.cuh"
+#include "gemm.h"
+
+// ---- front end (frontend.cu) ----------------------------------------------------------------------------
+enum { FE_MODE_WARP = 0, FE_MODE_PASTE20 = 1, FE_MODE_FIX = 2, FE_MODE_NONE = 3 };
+struct FrontendNorm {
+  float mean[2][3];
+  float std[2][3];
+};
+int patch_frontend_fwd(const uint8_t* obs, const float* patch, const int* xy, const float* theta, bf16* out, int B,
+                       int H, int W, int ph, int pw, int mode, const FrontendNorm& nrm, cudaStream_t stream);
+int patch_frontend_bwd(const bf16* dout, const float* patch, const int* xy, const float* theta, float* dpatch, int B,
+                       int H, int W, int ph, int pw, int mode, const FrontendNorm& nrm, cudaStream_t stream);
+
+// ---- layout / elementwise (elementwise.cu) --------------------------------------------------------------
+// px [B,6,H,W] -> per-tower im2col rows [B*np, kpad] (k = c*P*P + ky*P + kx, zero padded to kpad)
+int im2col_patches(const bf16* px, bf16* a_dino, bf16* a_sig, int B, int H, int W, int P, int kpad, cudaStream_t s);
+// inverse scatter of the two im2col-layout gradients back to dpx [B,6,H,W]
+int col2im_patches(const bf16* da_dino, const bf16* da_sig, bf16* dpx, int B, int H, int W, int P, int kpad,
+                   cudaStream_t s);
+// x[b, 0:npre] = prefix tokens (cls, reg...) ; rows npre.. are written by the patch-embed GEMM epilogue
+int write_prefix_tokens(const bf16* cls, const bf16* reg, bf16* x, int B, int ntok, int npre, int d, cudaStream_t s);
+// dst[b*rows_dst + dst_off + r, 0:cols] = src[b*rows_src + src_off + r, 0:cols]  for r < rows, b < B
+int copy_rows(const bf16* src, int64_t lds, int rows_src, int src_off, bf16* dst, int64_t ldd, int rows_dst,
+              int dst_off, int B, int rows, int cols, cudaStream_t s);
+int embed_tokens_splice(const int64_t* ids, const bf16* table, bf16* x, int B, int T, int P, int d, cudaStream_t s);
+int gelu_bwd(const bf16* dy, const bf16* pre, bf16* dx, int64_t n, cudaStream_t s);
+int scale_cols(const bf16* x, const bf16* gamma, bf16* y, int64_t rows, int cols, cudaStream_t s);
+// gu [M, 2F] = [gate | up] -> act [M, F] = bf16(bf16(silu(gate)) * up)
+int swiglu_fwd(const bf16* gu, bf16* act, int64_t M, int F, cudaStream_t s);
+int swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int64_t M, int F, cudaStream_t s);
+// rotary embedding applied in place to the q and k thirds of qkv [M, 3*H*hd]; pos = row % L. dir=+1 fwd, -1 bwd
+int rope_inplace(bf16* qkv, const float* cos_tab, const float* sin_tab, int64_t M, int L, int H, int hd, int dir,
+                 cudaStream_t s);
+// out[r] = a[r] + b[r] (bf16 rounding)
+int add_bf16(const bf16* a, const bf16* b, bf16* out, int64_t n, cudaStream_t s);
+// W [rows, cols] (row stride ldi) -> Wt [cols, rows] (row stride ldo)
+int transpose_bf16(const bf16* w, int64_t ldi, bf16* wt, int64_t ldo, int rows, int cols, cudaStream_t s);
+int gather_rows(const bf16* src, const int* rows, bf16* dst, int R, int d, cudaStream_t s);
+int scatter_rows(const bf16* src, const int* rows, bf16* dst, int R, int d, cudaStream_t s);
+
+// ---- norms (norm.cu) -------------------------------------------------------------------------------------
+int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* mean, float* rstd, int64_t M, int d,
+                  float eps, cudaStream_t s);
+// dx_out = bf16(dres + bf16(layernorm_bwd(dy)))   (dres may be null)
+int layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* mean, const float* rstd, const bf16* dres,
+                  bf16* dx, int64_t M, int d, cudaStream_t s);
+int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int64_t M, int d, float eps, cudaStream_t s);
+int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx, int64_t M,
+                int d, cudaStream_t s);
+
+// ---- attention (attention.cu) ----------------------------------------------------------------------------
+// qkv [B*N, 3*H*hd] (q | k | v, heads contiguous inside each third); o [B*N, H*hd]; lse [B, H, N] fp32.
+// causal != 0: key j visible to query i iff j <= i; kv_len (nullable) [B]: keys >= kv_len[b] are masked.
+int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
+                  cudaStream_t s);
+// dqkv [B*N, 3*H*hd]; delta scratch [B, H, N] fp32
+int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
+                  const int* kv_len, int B, int N, int H, int hd, int causal, cudaStream_t s);
+
+// ---- loss head (loss_head.cu) ----------------------------------------------------------------------------
+enum { LOSS_UADA = 0, LOSS_UADA_DDP = 1, LOSS_UPA = 2, LOSS_CE = 3, LOSS_NEG_CE = 4 };
+struct LossParams {
+  int kind;
+  float mse_weight;   // UADA: 5 (UADA.py:396) / MSE_weights (UADA_ddp.py:114)
+  float alpha, belta; // UPA (UPA.py:386)
+  float ce_scale;     // TMA: 1/accumulate_steps (TMA.py:148)
+};
+// Scalars written by the loss head (device float[LOSS_NUM_SCALARS])
+enum { LS_LOSS = 0, LS_CE = 1, LS_AUX0 = 2, LS_AUX1 = 3, LS_UAD = 4, LS_NTOK = 5, LS_NACT = 6, LS_GRAD_MEAN = 7,
+       LOSS_NUM_SCALARS = 8 };
+// logits fp32 [R, V] (bf16-rounded values) of the R supervised rows, sorted by (sample, position);
+// meta int [R][3] = {label of the row, sample index, index of the row among its sample's supervised rows}.
+// Writes dlogits bf16 [R, V], scalars, per-row argmax action id (pred_ids int [R]; -1 for non-action rows).
+int loss_head_fwd_bwd(const float* logits, const int* meta, int R, int V, int B, const LossParams& lp, float* row_stats,
+                      bf16* dlogits, float* scalars, int* pred_ids, cudaStream_t s);
+size_t loss_head_row_stats_floats(int R);
+
+// ---- patch update (patch_update.cu) ----------------------------------------------------------------------
+enum { OPT_ADAMW = 0, OPT_PGD = 1 };
+// grad is scaled by grad_scale (1/world after an all-reduce(sum)) first; clip_l1 > 0 applies
+// clip_grad_norm_(max_norm=clip_l1, norm_type=1) (UPA.py:157); then the update and clamp(0,1).
+int patch_update(float* patch, const float* grad, float* m, float* v, int n, int step, float lr, float beta1,
+                 float beta2, float eps, int kind, float grad_scale, float clip_l1, float* scalars, cudaStream_t s);

@@ -1,0 +1,166 @@
+"""Python host side of the attack-iteration engine: owns the device arenas (torch tensors), loads weights and
+drives ``vla_fwd_bwd`` / ``vla_patch_update`` through the C ABI.  PyTorch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_void_p
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import NORM_MEAN, NORM_STD, OpenVLAConfig
+
+
+@dataclass
+class LossSpec:
+    """Which loss head the engine applies (reference call sites in include/vla_b200.h)."""
+    kind: int = _lib.LOSS_UADA
+    mse_weight: float = 5.0
+    alpha: float = 0.8
+    belta: float = 0.2
+    ce_scale: float = 1.0
+
+    def to_c(self) -> _lib.LossParams:
+        return _lib.LossParams(self.kind, self.mse_weight, self.alpha, self.belta, self.ce_scale)
+
+
+def rope_tables(L: int, head_dim: int, theta: float):
+    """cos / sin exactly as HF ``LlamaRotaryEmbedding`` produces them for bf16 activations (fp32 maths, bf16 rounding)."""
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+    freqs = torch.outer(torch.arange(L, dtype=torch.float32), inv_freq)
+    cos = freqs.cos().to(torch.bfloat16).float().contiguous()
+    sin = freqs.sin().to(torch.bfloat16).float().contiguous()
+    return cos, sin
+
+
+def _c_config(cfg: OpenVLAConfig) -> _lib.Config:
+    c = _lib.Config()
+    c.img, c.patch = cfg.dino.img, cfg.dino.patch
+    d, s, l = cfg.dino, cfg.siglip, cfg.llm
+    assert d.img == s.img and d.patch == s.patch
+    c.dino_dim, c.dino_depth, c.dino_heads, c.dino_mlp = d.dim, d.depth, d.heads, d.mlp_hidden
+    c.dino_prefix, c.dino_layerscale = d.num_prefix, int(d.layerscale)
+    c.sig_dim, c.sig_depth, c.sig_heads, c.sig_mlp = s.dim, s.depth, s.heads, s.mlp_hidden
+    c.sig_prefix, c.sig_layerscale = s.num_prefix, int(s.layerscale)
+    c.vit_ln_eps = d.ln_eps
+    c.llm_hidden, c.llm_layers, c.llm_heads, c.llm_ffn, c.vocab = l.hidden, l.layers, l.heads, l.ffn, l.vocab
+    c.rms_eps = l.rms_eps
+    for i in range(2):
+        for j in range(3):
+            c.norm_mean[i][j] = NORM_MEAN[i][j]
+            c.norm_std[i][j] = NORM_STD[i][j]
+    return c
+
+
+class VLAEngine:
+    """One engine per process / GPU.  ``batch`` is the per-GPU batch, ``text_len`` the padded text length T."""
+
+    def __init__(self, cfg: OpenVLAConfig, batch: int, text_len: int, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise _lib.VLAError("VLAEngine needs a CUDA device (sm_100a); there is no CPU path")
+        self.cfg, self.B, self.T = cfg, batch, text_len
+        self.L = text_len + cfg.num_patches
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self._lib = _lib.lib()
+        self._h = c_void_p()
+        ccfg = _c_config(cfg)
+        _lib.check(self._lib.vla_engine_create(byref(ccfg), byref(self._h)), "vla_engine_create")
+        wbytes = self._lib.vla_engine_weight_bytes(self._h)
+        sbytes = self._lib.vla_engine_workspace_bytes(self._h, batch, text_len)
+        self.weight_arena = torch.empty(wbytes, dtype=torch.uint8, device=self.device)
+        self.workspace = torch.empty(sbytes, dtype=torch.uint8, device=self.device)
+        _lib.check(self._lib.vla_engine_set_buffers(self._h, _lib.ptr(self.weight_arena), wbytes,
+                                                    _lib.ptr(self.workspace), sbytes, batch, text_len),
+                   "vla_engine_set_buffers")
+        cos, sin = rope_tables(self.L, cfg.llm.head_dim, cfg.llm.rope_theta)
+        _lib.check(self._lib.vla_engine_set_rope(self._h, _lib.ptr(cos), _lib.ptr(sin), self.L, _lib.cur_stream()),
+                   "vla_engine_set_rope")
+        self.num_supervised = 0
+        self._weights_ok = False
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.vla_engine_destroy(h)
+            self._h = None
+
+    # ---- weights -------------------------------------------------------------------------------------------
+    def load_state_dict(self, sd, strict=True):
+        """Copy HF-named tensors into the engine arena (any device / float dtype; converted to bf16 on the GPU).
+        Entries that are not on the attack hot path are skipped unless ``strict``."""
+        stream = _lib.cur_stream()
+        for name, t in sd.items():
+            g = t.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+            rc = self._lib.vla_engine_load_weight(self._h, name.encode(), _lib.ptr(g), g.numel(), stream)
+            if rc != 0:
+                msg = self._lib.vla_last_error().decode()
+                if strict or "unknown weight" not in msg:
+                    raise _lib.VLAError(f"load_weight({name}): {msg}")
+            del g
+        torch.cuda.synchronize(self.device)
+        _lib.check(self._lib.vla_engine_weights_ready(self._h), "vla_engine_weights_ready")
+        self._weights_ok = True
+
+    def load_random_weights(self, seed=0, init="reference"):
+        """Random-init weights generated on the GPU one tensor at a time (no checkpoint is available offline)."""
+        from .weights import param_shapes
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        from .weights import random_tensor
+        stream = _lib.cur_stream()
+        for name, shape in param_shapes(self.cfg).items():
+            t = random_tensor(name, shape, g, self.device, init).to(torch.bfloat16).contiguous()
+            _lib.check(self._lib.vla_engine_load_weight(self._h, name.encode(), _lib.ptr(t), t.numel(), stream),
+                       f"load_weight({name})")
+            del t
+        torch.cuda.synchronize(self.device)
+        _lib.check(self._lib.vla_engine_weights_ready(self._h), "vla_engine_weights_ready")
+        self._weights_ok = True
+
+    # ---- per outer iteration -------------------------------------------------------------------------------
+    def set_batch(self, obs_u8, input_ids, attention_mask, labels):
+        """obs_u8 [B,H,W,3] uint8 (host, ideally pinned, or device); ids / mask / labels [B,T] host tensors."""
+        B, T = input_ids.shape
+        ids = input_ids.to(torch.int64).contiguous().cpu()
+        mask = attention_mask.to(torch.uint8).contiguous().cpu()
+        lab = labels.to(torch.int64).contiguous().cpu()
+        obs = obs_u8.contiguous()
+        assert obs.dtype == torch.uint8 and tuple(obs.shape) == (B, self.cfg.img, self.cfg.img, 3), obs.shape
+        _lib.check(self._lib.vla_engine_set_batch(self._h, _lib.ptr(obs), int(obs.is_cuda), _lib.ptr(ids), _lib.ptr(mask),
+                                                  _lib.ptr(lab), B, T, _lib.cur_stream()), "vla_engine_set_batch")
+        self.num_supervised = self._lib.vla_engine_num_supervised(self._h)
+        return self.num_supervised
+
+    def set_placements(self, xy, theta):
+        """xy int32 [steps,B,2], theta float32 [steps,B,2,3] (numpy or torch, host)."""
+        xy = np.ascontiguousarray(np.asarray(xy), dtype=np.int32)
+        theta = np.ascontiguousarray(np.asarray(theta), dtype=np.float32)
+        steps = xy.shape[0]
+        assert xy.shape == (steps, self.B, 2) and theta.shape == (steps, self.B, 2, 3), (xy.shape, theta.shape)
+        _lib.check(self._lib.vla_engine_set_placements(self._h, xy.ctypes.data_as(c_void_p), theta.ctypes.data_as(c_void_p),
+                                                       steps, _lib.cur_stream()), "vla_engine_set_placements")
+
+    # ---- per inner iteration -------------------------------------------------------------------------------
+    def fwd_bwd(self, patch, step_idx, fe_mode, loss: LossSpec, dpatch, scalars, pred_ids, forward_only=False):
+        """patch / dpatch f32 [3,ph,pw] (device); scalars f32 [8] (device); pred_ids i32 [>= num_supervised]."""
+        assert self._weights_ok, "weights not loaded"
+        lp = loss.to_c()
+        _lib.check(self._lib.vla_fwd_bwd(self._h, _lib.ptr(patch), patch.shape[1], patch.shape[2], step_idx, fe_mode,
+                                         byref(lp), _lib.ptr(dpatch), _lib.ptr(scalars), _lib.ptr(pred_ids),
+                                         _lib.FLAG_FORWARD_ONLY if forward_only else 0, _lib.cur_stream()), "vla_fwd_bwd")
+
+    def patch_update(self, patch, grad, m, v, step, lr, kind=_lib.OPT_ADAMW, grad_scale=1.0, clip_l1=0.0, scalars=None,
+                     betas=(0.9, 0.999), eps=1e-6):
+        _lib.check(self._lib.vla_patch_update(_lib.ptr(patch), _lib.ptr(grad), _lib.ptr(m), _lib.ptr(v), patch.numel(),
+                                              step, lr, betas[0], betas[1], eps, kind, grad_scale, clip_l1,
+                                              _lib.ptr(scalars), _lib.cur_stream()), "vla_patch_update")
+
+    def tap(self, what: str, dtype=torch.bfloat16, max_elems=1 << 28):
+        buf = torch.empty(max_elems, dtype=dtype, device=self.device)
+        n = self._lib.vla_engine_debug_tap(self._h, what.encode(), _lib.ptr(buf), buf.numel() * buf.element_size(),
+                                           _lib.cur_stream())
+        if n < 0:
+            raise _lib.VLAError(self._lib.vla_last_error().decode())
+        return buf[:n].clone()

@@ -68,6 +68,32 @@ def param_shapes(cfg: OpenVLAConfig) -> dict:
 
 
 
+def random_tensor(name, shape, g, device, init="reference"):
+    """One synthetic parameter in fp32 (see ``random_state_dict``)."""
+    leaf = name.rsplit(".", 1)[-1]
+    is_norm = ("norm" in name.rsplit(".", 2)[-2]) if name.count(".") >= 2 else False
+    if init == "reference":
+        if "scale_factor" in name:
+            return torch.full(shape, 1e-5, device=device)
+        if is_norm and leaf == "weight":
+            return torch.ones(shape, device=device)
+        if leaf == "bias":
+            return torch.zeros(shape, device=device)
+        return torch.randn(shape, generator=g, device=device) * 0.02
+    if "scale_factor" in name:
+        return torch.randn(shape, generator=g, device=device) * 0.3
+    if is_norm and leaf == "weight":
+        return 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
+    if leaf == "bias":
+        return 0.05 * torch.randn(shape, generator=g, device=device)
+    if name.endswith("embed_tokens.weight") or leaf in ("pos_embed", "cls_token", "reg_token"):
+        return torch.randn(shape, generator=g, device=device) * 0.5
+    fan_in = 1
+    for s in shape[1:]:
+        fan_in *= s
+    return torch.randn(shape, generator=g, device=device) * (1.0 / fan_in ** 0.5)
+
+
 def random_state_dict(cfg: OpenVLAConfig, seed: int = 0, device="cpu", dtype=torch.bfloat16, init: str = "reference"):
     """Random-init weights of the right shapes (no checkpoint is available offline).
 
@@ -77,32 +103,4 @@ def random_state_dict(cfg: OpenVLAConfig, seed: int = 0, device="cpu", dtype=tor
     branch carries signal and gradient in the parity tests.
     """
     g = torch.Generator(device=device).manual_seed(seed)
-    sd = {}
-    for name, shape in param_shapes(cfg).items():
-        leaf = name.rsplit(".", 1)[-1]
-        is_norm = ("norm" in name.rsplit(".", 2)[-2]) if name.count(".") >= 2 else False
-        if init == "reference":
-            if "scale_factor" in name:
-                t = torch.full(shape, 1e-5, device=device)
-            elif is_norm and leaf == "weight":
-                t = torch.ones(shape, device=device)
-            elif leaf == "bias":
-                t = torch.zeros(shape, device=device)
-            else:
-                t = torch.randn(shape, generator=g, device=device) * 0.02
-        else:
-            if "scale_factor" in name:
-                t = torch.randn(shape, generator=g, device=device) * 0.3
-            elif is_norm and leaf == "weight":
-                t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
-            elif leaf == "bias":
-                t = 0.05 * torch.randn(shape, generator=g, device=device)
-            elif name.endswith("embed_tokens.weight") or leaf in ("pos_embed", "cls_token", "reg_token"):
-                t = torch.randn(shape, generator=g, device=device) * 0.5
-            else:
-                fan_in = 1
-                for s in shape[1:]:
-                    fan_in *= s
-                t = torch.randn(shape, generator=g, device=device) * (1.0 / fan_in ** 0.5)
-        sd[name] = t.to(dtype)
-    return sd
+    return {name: random_tensor(name, shape, g, device, init).to(dtype) for name, shape in param_shapes(cfg).items()}

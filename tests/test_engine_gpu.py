@@ -1,0 +1,177 @@
+"""End-to-end parity of the CUDA engine (through the C ABI) against the oracle on reduced-depth models.
+
+The engine computes in bf16 with fp32 accumulation, like the reference's eager path.  Two bf16 implementations of
+a deep network differ by accumulated rounding noise, so parity is stated against an fp32 run of the oracle on the
+SAME bf16-valued weights ("truth"): the engine must be as close to truth as the oracle's own bf16 run is
+(within a factor), and the loss scalars must agree to bf16-level tolerance.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from roboticattack_b200 import _lib  # noqa: E402
+from roboticattack_b200.config import NORM_MEAN, NORM_STD, tiny  # noqa: E402
+from roboticattack_b200.engine import LossSpec, VLAEngine  # noqa: E402
+from roboticattack_b200.synthetic import synthetic_batch  # noqa: E402
+from roboticattack_b200.weights import random_state_dict  # noqa: E402
+
+
+def oracle_step(sd, cfg, batch, patch, xy, theta, mode, loss_kind, dtype, maskidx):
+    """One attack iteration of the reference path (front end -> model -> loss -> backward) in `dtype`."""
+    from oracle import frontend as ofe, losses as ol, model as om
+    sdd = {k: v.to(dtype) for k, v in sd.items()}
+    p = patch.clone().requires_grad_(True)
+    px = ofe.apply_patch_batch(batch["obs"], p, xy, theta, mode, NORM_MEAN, NORM_STD)
+    out = om.forward(sdd, cfg, batch["input_ids"], batch["attention_mask"], px.to(dtype), batch["labels"])
+    logits = out.logits.float()
+    if loss_kind == "uada":
+        mse, uad = ol.weighted_loss_uada(logits, batch["labels"], 5)
+        loss = mse + 1 / out.loss
+    elif loss_kind == "ddp":
+        loss, uad = ol.weighted_loss_uada(logits, batch["labels"], 5)
+    elif loss_kind == "upa":
+        loss, _, _ = ol.weighted_loss_upa(logits, batch["labels"], 0.8, 0.2, cfg.num_patches)
+    elif loss_kind == "ce":
+        loss = out.loss
+    loss.backward()
+    return {"loss": loss.item(), "ce": out.loss.item(), "grad": p.grad.clone(), "px": px.detach(), "logits": logits.detach()}
+
+
+def rel(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+SPECS = {"uada": LossSpec(_lib.LOSS_UADA, 5.0), "ddp": LossSpec(_lib.LOSS_UADA_DDP, 5.0),
+         "upa": LossSpec(_lib.LOSS_UPA, 0, 0.8, 0.2), "ce": LossSpec(_lib.LOSS_CE, ce_scale=1.0)}
+
+
+@pytest.fixture(scope="module")
+def tiny_setup():
+    cfg = tiny(img=56, llm_layers=2, vit_depth=3)
+    sd = random_state_dict(cfg, seed=0, dtype=torch.bfloat16, init="test")
+    B, T = 3, 16
+    eng = VLAEngine(cfg, B, T)
+    eng.load_state_dict(sd)
+    return cfg, sd, eng, B, T
+
+
+@pytest.mark.parametrize("loss_kind,mode,ragged", [("uada", _lib.FE_WARP, False), ("ddp", _lib.FE_WARP, True),
+                                                   ("upa", _lib.FE_PASTE20, False), ("ce", _lib.FE_FIX, True)])
+def test_engine_step_vs_oracle(tiny_setup, loss_kind, mode, ragged):
+    from oracle import frontend as ofe, losses as ol
+    cfg, sd, eng, B, T = tiny_setup
+    batch = synthetic_batch(cfg, B, T, seed=1234, ragged=ragged)
+    maskidx = [0, 1, 2]
+    if loss_kind in ("uada", "ddp"):
+        batch["labels"] = ol.mask_labels_uada(batch["labels"].clone(), maskidx)
+    torch.manual_seed(42)
+    p = 12
+    patch = torch.rand(3, p, p)
+    random.seed(42)
+    np.random.seed(42)
+    xy, theta = ofe.draw_placements(B, (cfg.img, cfg.img), (p, p), mode == _lib.FE_WARP)
+    truth = oracle_step(sd, cfg, batch, patch, xy, theta, mode, loss_kind, torch.float32, maskidx)
+    orc = oracle_step(sd, cfg, batch, patch, xy, theta, mode, loss_kind, torch.bfloat16, maskidx)
+
+    eng.set_batch(batch["obs"], batch["input_ids"], batch["attention_mask"], batch["labels"])
+    eng.set_placements(xy[None], theta[None])
+    pd = patch.cuda()
+    dp = torch.zeros_like(pd)
+    sc = torch.zeros(_lib.NUM_SCALARS, device="cuda")
+    pred = torch.zeros(eng.num_supervised, dtype=torch.int32, device="cuda")
+    eng.fwd_bwd(pd, 0, mode, SPECS[loss_kind], dp, sc, pred)
+    torch.cuda.synchronize()
+    sc = sc.cpu()
+    g = dp.cpu()
+    assert torch.isfinite(g).all() and g.abs().sum() > 0
+    e_or, e_en = rel(orc["grad"], truth["grad"]), rel(g, truth["grad"])
+    l_or, l_en = abs(orc["loss"] - truth["loss"]), abs(sc[_lib.S_LOSS].item() - truth["loss"])
+    print(f"[{loss_kind}] loss truth {truth['loss']:.6f} oracle-bf16 {orc['loss']:.6f} engine {sc[_lib.S_LOSS].item():.6f}; "
+          f"grad rel-err vs fp32 truth: oracle-bf16 {e_or:.4f} engine {e_en:.4f}; cos(engine, truth) "
+          f"{torch.nn.functional.cosine_similarity(g.flatten(), truth['grad'].flatten(), dim=0).item():.5f}")
+    assert l_en <= max(3 * l_or, 2e-2 * abs(truth["loss"])), (l_en, l_or)
+    assert abs(sc[_lib.S_CE].item() - truth["ce"]) <= max(3 * abs(orc["ce"] - truth["ce"]), 2e-2 * truth["ce"])
+    assert e_en <= max(2.5 * e_or, 0.08), f"engine gradient error {e_en:.4f} vs oracle-bf16 {e_or:.4f}"
+
+
+def test_engine_forward_taps(tiny_setup):
+    """Stage-by-stage forward parity: front end, both towers, multimodal embedding, final hidden, logits."""
+    from oracle import frontend as ofe, model as om
+    cfg, sd, eng, B, T = tiny_setup
+    batch = synthetic_batch(cfg, B, T, seed=7, ragged=True)
+    torch.manual_seed(1)
+    p = 10
+    patch = torch.rand(3, p, p)
+    random.seed(1)
+    np.random.seed(1)
+    xy, theta = ofe.draw_placements(B, (cfg.img, cfg.img), (p, p), True)
+    px = ofe.apply_patch_batch(batch["obs"], patch, xy, theta, ofe.MODE_WARP, NORM_MEAN, NORM_STD).bfloat16()
+    sdf = {k: v.float() for k, v in sd.items()}
+    feats = om.vision_backbone(sdf, cfg, px.float())
+    proj = om.projector(sdf, feats)
+    x0, m, y = om.splice(sdf, cfg, proj, batch["input_ids"], batch["attention_mask"], batch["labels"])
+    eng.set_batch(batch["obs"], batch["input_ids"], batch["attention_mask"], batch["labels"])
+    eng.set_placements(xy[None], theta[None])
+    pd = patch.cuda()
+    dp = torch.zeros_like(pd)
+    sc = torch.zeros(_lib.NUM_SCALARS, device="cuda")
+    pred = torch.zeros(eng.num_supervised, dtype=torch.int32, device="cuda")
+    eng.fwd_bwd(pd, 0, _lib.FE_WARP, SPECS["ce"], dp, sc, pred, forward_only=True)
+    got_px = eng.tap("px").view(B, 6, cfg.img, cfg.img).float().cpu()
+    assert ((got_px - px.float()).abs() > 0).float().mean() < 2e-3
+    d_out = eng.tap("dino_out").view(B, cfg.dino.tokens, cfg.dino.dim)[:, cfg.dino.num_prefix:].float().cpu()
+    s_out = eng.tap("siglip_out").view(B, cfg.siglip.tokens, cfg.siglip.dim).float().cpu()
+    assert rel(d_out, feats[..., :cfg.dino.dim]) < 0.03, rel(d_out, feats[..., :cfg.dino.dim])
+    assert rel(s_out, feats[..., cfg.dino.dim:]) < 0.03, rel(s_out, feats[..., cfg.dino.dim:])
+    got_x0 = eng.tap("llm_x0").view(B, eng.L, cfg.llm.hidden).float().cpu()
+    assert rel(got_x0, x0) < 0.03, rel(got_x0, x0)
+
+
+def test_engine_attack_trajectory(tiny_setup):
+    """Ten AdamW steps engine vs oracle-bf16 from the same state: per-step loss tracks and the patch stays close.
+    (Adam's first steps move every pixel by ~lr regardless of |g|, so a gradient SIGN flip from bf16 noise moves a
+    pixel by 2*lr; the test reports the fraction of pixels within lr/2 and bounds the mean deviation.)"""
+    from oracle import frontend as ofe, losses as ol, optim as oo
+    cfg, sd, eng, B, T = tiny_setup
+    batch = synthetic_batch(cfg, B, T, seed=99, ragged=False)
+    batch["labels"] = ol.mask_labels_uada(batch["labels"].clone(), [0, 1, 2])
+    steps, lr, p = 10, 2e-3, 12
+    torch.manual_seed(42)
+    patch0 = torch.rand(3, p, p)
+    random.seed(42)
+    np.random.seed(42)
+    draws = [ofe.draw_placements(B, (cfg.img, cfg.img), (p, p), True) for _ in range(steps)]
+    xy = np.stack([d[0] for d in draws])
+    theta = np.stack([d[1] for d in draws])
+    # oracle trajectory
+    po = patch0.clone()
+    opt = oo.HFAdamW(po.shape, lr)
+    o_losses = []
+    for s in range(steps):
+        r = oracle_step(sd, cfg, batch, po, xy[s], theta[s], ofe.MODE_WARP, "ddp", torch.bfloat16, None)
+        o_losses.append(r["loss"])
+        opt.step(po, r["grad"])
+        po.clamp_(0, 1)
+    # engine trajectory
+    eng.set_batch(batch["obs"], batch["input_ids"], batch["attention_mask"], batch["labels"])
+    eng.set_placements(xy, theta)
+    pe = patch0.cuda()
+    m, v, dp = torch.zeros_like(pe), torch.zeros_like(pe), torch.zeros_like(pe)
+    sc = torch.zeros(steps, _lib.NUM_SCALARS, device="cuda")
+    pred = torch.zeros(eng.num_supervised, dtype=torch.int32, device="cuda")
+    for s in range(steps):
+        eng.fwd_bwd(pe, s, _lib.FE_WARP, SPECS["ddp"], dp, sc[s], pred)
+        eng.patch_update(pe, dp, m, v, s + 1, lr, scalars=sc[s])
+    torch.cuda.synchronize()
+    e_losses = sc[:, _lib.S_LOSS].cpu().tolist()
+    dev_ = (pe.cpu() - po).abs()
+    print("oracle losses", [f"{x:.4f}" for x in o_losses])
+    print("engine losses", [f"{x:.4f}" for x in e_losses])
+    print(f"patch Linf {dev_.max().item():.4g} mean {dev_.mean().item():.4g} frac within lr/2: {(dev_ < lr / 2).float().mean().item():.3f}")
+    assert abs(e_losses[0] - o_losses[0]) <= 2e-2 * abs(o_losses[0]) + 1e-3
+    assert dev_.mean().item() < 2 * lr
+    assert ((pe.cpu() - patch0).abs().max().item()) > 0

@@ -1,0 +1,366 @@
+"""GPU parity tests of the individual CUDA kernels, called through the C ABI, against the oracle / fp32 torch maths.
+
+Tolerances: kernels emit bf16 (8 mantissa bits, ulp = 2^-8 relative = 3.9e-3); a kernel that mirrors the eager
+path's rounding points may still differ from a reference by one rounding per op, so elementwise checks allow
+~2 ulp of the tensor scale, and reductions (GEMM K=4096, attention) are compared against an fp32 reference with the
+same bound applied to the OUTPUT rounding only.  fp32 outputs (loss scalars, patch update) use 1e-5 relative.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from roboticattack_b200 import _lib  # noqa: E402
+from roboticattack_b200.config import NORM_MEAN, NORM_STD  # noqa: E402
+
+BF16_ULP = 2.0 ** -8
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+def close(got, ref, ulps=2.0, what=""):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    scale = ref.abs().max().item() + 1e-12
+    err = (got - ref).abs().max().item()
+    assert err <= ulps * BF16_ULP * scale, f"{what}: max err {err:.4g} vs scale {scale:.4g} ({err / scale / BF16_ULP:.2f} ulp)"
+
+
+L = None
+
+
+def setup_module(module):
+    global L
+    L = _lib.lib()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (100, 200, 136), (300, 432, 144), (2312, 4096, 4096), (2048, 4304, 1152)])
+def test_gemm_plain(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(L.vla_gemm_bf16_tn(_lib.ptr(A), K, _lib.ptr(W), K, _lib.ptr(out), N, M, N, K, None, None, None, 0, 0, None, 0,
+                                  _lib.cur_stream()))
+    ref = (A.float() @ W.float().t())
+    close(out, ref.bfloat16(), 1.01, f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_epilogues():
+    M, N, K = 520, 1024, 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = (torch.randn(N, device="cuda", generator=g) * 0.2).bfloat16()
+    gm = torch.randn(N, device="cuda", generator=g).bfloat16()
+    r = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _lib.check(L.vla_gemm_bf16_tn(_lib.ptr(A), K, _lib.ptr(W), K, _lib.ptr(out), N, M, N, K, _lib.ptr(b), _lib.ptr(gm), _lib.ptr(r),
+                                  N, 1, _lib.ptr(pre), 0, _lib.cur_stream()))
+    lin = (A.float() @ W.float().t() + b.float()).bfloat16()
+    close(pre, lin, 1.01, "preact")
+    # the remaining steps are exact functions of the (already compared) bf16 pre-activation
+    x = torch.nn.functional.gelu(pre.float()).bfloat16()
+    x = (x.float() * gm.float()).bfloat16()
+    x = (r.float() + x.float()).bfloat16()
+    close(out, x, 1.01, "gelu*gamma+resid")
+    of = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    _lib.check(L.vla_gemm_bf16_tn(_lib.ptr(A), K, _lib.ptr(W), K, _lib.ptr(of), N, M, N, K, None, None, None, 0, 0, None, 1,
+                                  _lib.cur_stream()))
+    assert torch.equal(of, of.bfloat16().float()), "fp32 logits must hold bf16-rounded values (HF: lm_head(...).float())"
+    close(of, (A.float() @ W.float().t()).bfloat16(), 1.01, "f32 out")
+
+
+# ------------------------------------------------------------------------------------------------ front end
+@pytest.mark.parametrize("mode", [_lib.FE_WARP, _lib.FE_PASTE20, _lib.FE_FIX, _lib.FE_NONE])
+@pytest.mark.parametrize("S,p,B", [(224, 50, 8), (56, 12, 3)])
+def test_frontend_vs_oracle(mode, S, p, B):
+    from oracle import frontend as ofe
+    rng = np.random.default_rng(1234)
+    obs = torch.from_numpy(rng.integers(0, 256, size=(B, S, S, 3), dtype=np.uint8))
+    torch.manual_seed(42)
+    patch = torch.rand(3, p, p)
+    random.seed(42)
+    np.random.seed(42)
+    xy, theta = ofe.draw_placements(B, (S, S), (p, p), mode == _lib.FE_WARP)
+    pr = patch.clone().requires_grad_(True)
+    ref = ofe.apply_patch_batch(obs, pr, xy, theta, mode, NORM_MEAN, NORM_STD)
+    gw = torch.from_numpy(np.random.default_rng(7).standard_normal(tuple(ref.shape)).astype(np.float32)).bfloat16()
+    ref_b = ref.to(torch.bfloat16)          # UADA.py:142
+    (ref_b.float() * gw.float()).sum().backward()
+    out = torch.empty(B, 6, S, S, device="cuda", dtype=torch.bfloat16)
+    nrm = _lib.norm_array(NORM_MEAN, NORM_STD)
+    xy_d, th_d = dev(torch.from_numpy(xy)), dev(torch.from_numpy(theta))
+    _lib.check(L.vla_patch_frontend_fwd(_lib.ptr(dev(obs)), _lib.ptr(dev(patch)), _lib.ptr(xy_d), _lib.ptr(th_d), _lib.ptr(out),
+                                        B, S, S, p, p, mode, nrm, _lib.cur_stream()))
+    got = out.float().cpu()
+    # identical up to one bf16 rounding flip where the fp32 value sits on a rounding boundary (coordinate maths
+    # differs from ATen's affine_grid by ~1 fp32 ulp); composite decisions must agree except on such boundaries
+    diff = (got - ref_b.float()).abs()
+    frac_bad = (diff > 0).float().mean().item()
+    assert frac_bad < 2e-3, f"{frac_bad:.2e} of pixels differ"
+    assert (diff <= BF16_ULP * ref_b.float().abs().clamp_min(1.0) * 1.01).float().mean().item() > 1 - 1e-5
+    if mode == _lib.FE_NONE:
+        return
+    dp = torch.empty(3, p, p, device="cuda")
+    _lib.check(L.vla_patch_frontend_bwd(_lib.ptr(dev(gw)), _lib.ptr(dev(patch)), _lib.ptr(xy_d), _lib.ptr(th_d), _lib.ptr(dp),
+                                        B, S, S, p, p, mode, nrm, _lib.cur_stream()))
+    torch.testing.assert_close(dp.cpu(), pr.grad, rtol=2e-4, atol=2e-4 * pr.grad.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("M,d", [(37, 128), (300, 1152), (2312, 4096), (50, 144)])
+def test_layernorm(M, d):
+    g = torch.Generator(device="cuda").manual_seed(d)
+    x = (torch.randn(M, d, device="cuda", generator=g) * 2 + 0.3).bfloat16()
+    w = (1 + 0.1 * torch.randn(d, device="cuda", generator=g)).bfloat16()
+    b = (0.1 * torch.randn(d, device="cuda", generator=g)).bfloat16()
+    dy = torch.randn(M, d, device="cuda", generator=g).bfloat16()
+    dres = torch.randn(M, d, device="cuda", generator=g).bfloat16()
+    y = torch.empty_like(x)
+    mean = torch.empty(M, device="cuda")
+    rstd = torch.empty(M, device="cuda")
+    _lib.check(L.vla_layernorm_fwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd), M, d, 1e-6,
+                                   _lib.cur_stream()))
+    xr = x.float().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (d,), w.float(), b.float(), 1e-6)
+    close(y, ref.detach().bfloat16(), 1.01, "ln fwd")
+    ref.backward(dy.float())
+    dx = torch.empty_like(x)
+    _lib.check(L.vla_layernorm_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(w), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(dres), _lib.ptr(dx),
+                                   M, d, _lib.cur_stream()))
+    expect = (dres.float() + xr.grad.bfloat16().float()).bfloat16()
+    close(dx, expect, 1.5, "ln bwd")
+
+
+@pytest.mark.parametrize("M,d", [(64, 256), (2312, 4096)])
+def test_rmsnorm(M, d):
+    from oracle.llama import rms_norm
+    g = torch.Generator(device="cuda").manual_seed(d)
+    x = (torch.randn(M, d, device="cuda", generator=g) * 1.5).bfloat16()
+    w = (1 + 0.1 * torch.randn(d, device="cuda", generator=g)).bfloat16()
+    dy = torch.randn(M, d, device="cuda", generator=g).bfloat16()
+    dres = torch.randn(M, d, device="cuda", generator=g).bfloat16()
+    y = torch.empty_like(x)
+    rstd = torch.empty(M, device="cuda")
+    _lib.check(L.vla_rmsnorm_fwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), _lib.ptr(rstd), M, d, 1e-6, _lib.cur_stream()))
+    xr = x.clone().requires_grad_(True)
+    ref = rms_norm(xr, w, 1e-6)
+    close(y, ref.detach(), 1.01, "rms fwd")
+    ref.backward(dy)
+    dx = torch.empty_like(x)
+    _lib.check(L.vla_rmsnorm_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(w), _lib.ptr(rstd), _lib.ptr(dres), _lib.ptr(dx), M, d,
+                                 _lib.cur_stream()))
+    expect = (dres.float() + xr.grad.float()).bfloat16()
+    close(dx, expect, 1.5, "rms bwd")
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,N,H,hd,causal,ragged", [(2, 261, 4, 64, 0, False), (2, 256, 3, 72, 0, False),
+                                                    (3, 289, 4, 128, 1, True), (1, 21, 2, 64, 0, False),
+                                                    (2, 40, 2, 128, 1, True), (8, 289, 32, 128, 1, False)])
+def test_attention(B, N, H, hd, causal, ragged):
+    g = torch.Generator(device="cuda").manual_seed(N * hd + H)
+    D = H * hd
+    qkv = torch.randn(B * N, 3 * D, device="cuda", generator=g).bfloat16()
+    dout = torch.randn(B * N, D, device="cuda", generator=g).bfloat16()
+    kv_len = None
+    if ragged:
+        kv_len = torch.tensor([N - 3 * b for b in range(B)], dtype=torch.int32, device="cuda")
+    o = torch.zeros(B * N, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device="cuda")
+    _lib.check(L.vla_attention_fwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(lse), _lib.ptr(kv_len), B, N, H, hd, causal, _lib.cur_stream()))
+    x = qkv.float().view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
+    q, k, v = x[0], x[1], x[2]
+    allowed = torch.ones(B, 1, N, N, dtype=torch.bool, device="cuda")
+    if causal:
+        allowed &= torch.ones(N, N, dtype=torch.bool, device="cuda").tril()[None, None]
+    if kv_len is not None:
+        allowed &= (torch.arange(N, device="cuda")[None, :] < kv_len[:, None])[:, None, None, :]
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    s = s.masked_fill(~allowed, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    ref = (p @ v).transpose(1, 2).reshape(B * N, D)
+    valid_q = torch.ones(B, N, dtype=torch.bool, device="cuda")
+    close(o, ref.detach().bfloat16(), 3.0, "attn fwd")
+    ref_lse = torch.logsumexp(s, dim=-1)
+    torch.testing.assert_close(lse, ref_lse.detach(), rtol=1e-3, atol=2e-3)
+    ref.backward(dout.float())
+    dqkv = torch.zeros(B * N, 3 * D, device="cuda", dtype=torch.bfloat16)
+    delta = torch.empty(B, H, N, device="cuda")
+    _lib.check(L.vla_attention_bwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(dout), _lib.ptr(lse), _lib.ptr(delta), _lib.ptr(dqkv),
+                                   _lib.ptr(kv_len), B, N, H, hd, causal, _lib.cur_stream()))
+    gref = x.grad.permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D)
+    for i, nm in enumerate("qkv"):
+        close(dqkv[:, i * D:(i + 1) * D], gref[:, i * D:(i + 1) * D], 6.0, f"attn d{nm}")
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def test_rope_swiglu_gelu():
+    from oracle.llama import rotate_half
+    from roboticattack_b200.engine import rope_tables
+    B, Ls, H, hd = 2, 37, 3, 128
+    g = torch.Generator(device="cuda").manual_seed(1)
+    qkv = torch.randn(B * Ls, 3 * H * hd, device="cuda", generator=g).bfloat16()
+    cos, sin = rope_tables(Ls, hd, 10000.0)
+    ref = qkv.clone().view(B, Ls, 3, H, hd)
+    c = torch.cat([cos, cos], -1).bfloat16().cuda()[None, :, None, :]
+    s = torch.cat([sin, sin], -1).bfloat16().cuda()[None, :, None, :]
+    for i in range(2):
+        t = ref[:, :, i]
+        ref[:, :, i] = (t * c) + (rotate_half(t) * s)
+    x = qkv.clone()
+    _lib.check(L.vla_rope_inplace(_lib.ptr(x), _lib.ptr(dev(cos)), _lib.ptr(dev(sin)), B * Ls, Ls, H, hd, 1, _lib.cur_stream()))
+    assert torch.equal(x.view(B, Ls, 3, H, hd)[:, :, 2], qkv.view(B, Ls, 3, H, hd)[:, :, 2]), "v must be untouched"
+    close(x, ref.reshape(B * Ls, -1), 1.01, "rope")
+    M, F = 70, 688
+    gu = torch.randn(M, 2 * F, device="cuda", generator=g).bfloat16()
+    dact = torch.randn(M, F, device="cuda", generator=g).bfloat16()
+    act = torch.empty(M, F, device="cuda", dtype=torch.bfloat16)
+    _lib.check(L.vla_swiglu_fwd(_lib.ptr(gu), _lib.ptr(act), M, F, _lib.cur_stream()))
+    gr = gu.clone().requires_grad_(True)
+    refa = torch.nn.functional.silu(gr[:, :F]) * gr[:, F:]
+    close(act, refa.detach(), 1.01, "swiglu fwd")
+    refa.backward(dact)
+    dgu = torch.empty_like(gu)
+    _lib.check(L.vla_swiglu_bwd(_lib.ptr(dact), _lib.ptr(gu), _lib.ptr(dgu), M, F, _lib.cur_stream()))
+    close(dgu, gr.grad, 1.5, "swiglu bwd")
+    pre = torch.randn(M, F, device="cuda", generator=g).bfloat16()
+    pr = pre.clone().requires_grad_(True)
+    torch.nn.functional.gelu(pr).backward(dact)
+    dx = torch.empty_like(pre)
+    _lib.check(L.vla_gelu_bwd(_lib.ptr(dact), _lib.ptr(pre), _lib.ptr(dx), M * F, _lib.cur_stream()))
+    close(dx, pr.grad, 1.5, "gelu bwd")
+
+
+# ------------------------------------------------------------------------------------------------ loss heads
+def _loss_case(B=4, T=14, ragged=True, seed=3):
+    rng = np.random.default_rng(seed)
+    V, P = 32064, 16
+    labels = torch.full((B, T), -100, dtype=torch.int64)
+    lens = [T - (b % 3 if ragged else 0) for b in range(B)]
+    for b, n in enumerate(lens):
+        labels[b, n - 8:n - 1] = torch.from_numpy(rng.integers(31744, 32000, size=7))
+        labels[b, n - 1] = 2
+    Lm = P + T
+    logits = torch.from_numpy((rng.standard_normal((B, Lm, V)) * 2).astype(np.float32)).bfloat16().float()
+    return labels, logits, P, V
+
+
+def _gather(labels, logits, P):
+    B, T = labels.shape
+    Lm = logits.shape[1]
+    rows, meta = [], []
+    for b in range(B):
+        idx = 0
+        for t in range(1, T):
+            if labels[b, t] != -100:
+                rows.append(b * Lm + P + t - 1)
+                meta.append([int(labels[b, t]), b, idx])
+                idx += 1
+    z = logits.reshape(B * Lm, -1)[rows].contiguous()
+    return z, torch.tensor(meta, dtype=torch.int32), rows
+
+
+@pytest.mark.parametrize("kind", ["uada", "ddp", "upa", "ce", "negce"])
+@pytest.mark.parametrize("maskidx", [[0], [0, 1, 2], [0, 1, 2, 3, 4, 5, 6]])
+def test_loss_head_vs_oracle(kind, maskidx):
+    from oracle import losses as ol
+    from oracle.llama import causal_lm_loss
+    labels, logits, P, V = _loss_case()
+    B, T = labels.shape
+    if kind in ("uada", "ddp", "negce"):
+        labels = ol.mask_labels_uada(labels.clone(), maskidx) if kind != "negce" else ol.mask_labels_upa(labels.clone(), maskidx)
+    mm_labels = torch.cat([labels[:, :1], torch.full((B, P), -100), labels[:, 1:]], dim=1)
+    lg = logits.clone().requires_grad_(True)
+    ce = causal_lm_loss(lg, mm_labels)
+    aux = {}
+    if kind == "uada":
+        mse, uad = ol.weighted_loss_uada(lg, labels, 5)
+        loss = mse + 1 / ce
+        spec = _lib.LossParams(_lib.LOSS_UADA, 5.0, 0, 0, 1.0)
+        aux = {"mse": mse.item(), "uad": float(uad)}
+    elif kind == "ddp":
+        mse, uad = ol.weighted_loss_uada(lg, labels, 3)
+        loss = mse
+        spec = _lib.LossParams(_lib.LOSS_UADA_DDP, 3.0, 0, 0, 1.0)
+        aux = {"mse": mse.item(), "uad": float(uad)}
+    elif kind == "upa":
+        loss, ang, dist = ol.weighted_loss_upa(lg, labels, 0.8, 0.2, P)
+        spec = _lib.LossParams(_lib.LOSS_UPA, 0, 0.8, 0.2, 1.0)
+        aux = {"ang": ang.item(), "dist": dist.item()}
+    elif kind == "ce":
+        loss = ce / 2
+        spec = _lib.LossParams(_lib.LOSS_CE, 0, 0, 0, 0.5)
+    else:
+        loss = -ce
+        spec = _lib.LossParams(_lib.LOSS_NEG_CE, 0, 0, 0, 1.0)
+    loss.backward()
+    z, meta, rows = _gather(labels, logits, P)
+    R = z.shape[0]
+    zd, md = dev(z), dev(meta)
+    stats = torch.empty(8 * R, device="cuda")
+    dl = torch.empty(R, V, device="cuda", dtype=torch.bfloat16)
+    sc = torch.zeros(8, device="cuda")
+    pred = torch.empty(R, dtype=torch.int32, device="cuda")
+    import ctypes
+    _lib.check(L.vla_loss_head(_lib.ptr(zd), _lib.ptr(md), R, V, B, ctypes.byref(spec), _lib.ptr(stats), _lib.ptr(dl), _lib.ptr(sc),
+                               _lib.ptr(pred), _lib.cur_stream()))
+    sc = sc.cpu()
+    np.testing.assert_allclose(sc[_lib.S_LOSS].item(), loss.item(), rtol=2e-5)
+    np.testing.assert_allclose(sc[_lib.S_CE].item(), ce.item(), rtol=2e-5)
+    if "mse" in aux:
+        np.testing.assert_allclose(sc[_lib.S_AUX0].item(), aux["mse"], rtol=2e-5)
+        np.testing.assert_allclose(sc[_lib.S_UAD].item(), aux["uad"], rtol=1e-5)
+    if "ang" in aux:
+        np.testing.assert_allclose(sc[_lib.S_AUX0].item(), aux["ang"], rtol=2e-5)
+        np.testing.assert_allclose(sc[_lib.S_AUX1].item(), aux["dist"], rtol=2e-5)
+    gref = lg.grad.reshape(-1, V)[rows]
+    other = lg.grad.reshape(-1, V).clone()
+    other[rows] = 0
+    assert other.abs().max().item() == 0.0, "oracle gradient reaches unsupervised rows?"
+    got = dl.float().cpu()
+    scale = gref.abs().max().item()
+    assert (got - gref).abs().max().item() <= 1.01 * BF16_ULP * scale + 1e-12, "dlogits"
+    # argmax ids
+    zz = z[:, 31744:32000]
+    exp_pred = torch.where(meta[:, 0] > 2, zz.argmax(-1).int() + 31744, torch.full((R,), -1, dtype=torch.int32))
+    assert torch.equal(pred.cpu(), exp_pred)
+
+
+# ------------------------------------------------------------------------------------------------ patch update
+@pytest.mark.parametrize("kind,clip", [("adamw", 0.0), ("adamw", 1e-3), ("pgd", 0.0)])
+def test_patch_update_vs_oracle(kind, clip):
+    from oracle import optim as oo
+    torch.manual_seed(0)
+    p = torch.rand(3, 50, 50)
+    opt = oo.HFAdamW(p.shape, lr=2e-3)
+    pd, md, vd = dev(p), torch.zeros(3, 50, 50, device="cuda"), torch.zeros(3, 50, 50, device="cuda")
+    sc = torch.zeros(8, device="cuda")
+    for step in range(1, 6):
+        g = torch.randn(3, 50, 50) * 10 ** (-step)
+        gs = g * 4.0          # pretend all-reduce(sum) over 4 ranks
+        gref = g.clone()
+        if clip > 0:
+            oo.clip_grad_l1_(gref, clip)
+        if kind == "adamw":
+            opt.step(p, gref, lr=2e-3 * step)
+            p.clamp_(0, 1)
+        else:
+            p = oo.pgd_step(p, gref, 2e-3 * step)
+        _lib.check(L.vla_patch_update(_lib.ptr(pd), _lib.ptr(dev(gs)), _lib.ptr(md), _lib.ptr(vd), p.numel(), step, 2e-3 * step, 0.9, 0.999,
+                                      1e-6, _lib.OPT_ADAMW if kind == "adamw" else _lib.OPT_PGD, 0.25, clip, _lib.ptr(sc),
+                                      _lib.cur_stream()))
+        torch.testing.assert_close(pd.cpu(), p, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(sc[_lib.S_GRAD_MEAN].item(), g.mean().item(), rtol=1e-3, atol=1e-9)
+    if kind == "adamw":
+        torch.testing.assert_close(md.cpu(), opt.m, rtol=1e-5, atol=1e-12)
+        torch.testing.assert_close(vd.cpu(), opt.v, rtol=1e-5, atol=1e-14)
