@@ -25,6 +25,12 @@ int vla_abi_version(void);
 /* number of kernel launches issued by this library since process start */
 long long vla_launch_count(void);
 
+/* Measurement hook (bench.py roofline leg): while enabled, every tcgen05 GEMM launch is bracketed by CUDA events on
+ * its launch stream; _end synchronises the device and returns the summed kernel time, the summed algorithmic FLOPs
+ * (2*M*N*K with the true, unpadded dims) and the launch count. */
+int vla_profile_gemm_begin(void);
+int vla_profile_gemm_end(double* total_ms, double* total_flops, int* launches);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Front end.  Replaces RandomPatchTransform.apply_random_patch_batch (VLAAttacker/white_patch/
  * appply_random_transform.py:104-136), .paste_patch_fix (:160-188) / .random_paste_patch (:138-158), .im_process

@@ -1,0 +1,432 @@
+"""``OpenVLAAttacker`` for UADA / UPA / TMA / UADA-DDP with the reference's constructor and
+``patchattack_unconstrained`` / ``attack`` signatures, driving the CUDA engine instead of PyTorch autograd.
+
+Reference: VLAAttacker/white_patch/UADA.py:33-418, UPA.py:30-390, TMA.py:28-482, UADA_ddp.py:36-344.
+What stays Python (as in the reference): the outer loop over batches, label masking, the LR schedule, logging,
+validation cadence and checkpoint files.  What moved into the engine: everything inside the inner loop.
+Differences from the reference that are deliberate and documented in DESIGN.md: the model weights are frozen in
+every variant (UADA.py never freezes them and so also computes 7.5 B unused weight gradients); per-step scalars are
+read back once per outer iteration instead of four ``.item()`` syncs per inner step; clean observations are uploaded
+once per outer iteration instead of once per inner step.
+"""
+from __future__ import annotations
+
+import math
+import os
+import pickle
+from typing import Iterable, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, labels as lab
+from .config import NORM_MEAN, NORM_STD, OpenVLAConfig, openvla_7b
+from .engine import LossSpec, VLAEngine
+from .frontend import RandomPatchTransform
+from .synthetic import draw_placements
+
+IGNORE_INDEX = -100
+
+
+def cosine_with_warmup(step: int, warmup: int, total: int, num_cycles: float = 0.5) -> float:
+    """``transformers.get_cosine_schedule_with_warmup`` multiplier after ``step`` scheduler steps."""
+    if step < warmup:
+        return float(step) / float(max(1, warmup))
+    progress = float(step - warmup) / float(max(1, total - warmup))
+    return max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress)))
+
+
+def observations_to_uint8(pixel_values, img: int) -> torch.Tensor:
+    """The collator's ``pixel_values`` (list of PIL images, data_utils.py:203-204) -> pinned uint8 [B,H,W,3]."""
+    if isinstance(pixel_values, torch.Tensor):
+        t = pixel_values
+    else:
+        t = torch.from_numpy(np.stack([np.asarray(im.convert("RGB") if hasattr(im, "convert") else im, dtype=np.uint8)
+                                       for im in pixel_values]))
+    assert t.dtype == torch.uint8 and t.shape[1:] == (img, img, 3), f"expected uint8 [B,{img},{img},3], got {t.shape}"
+    if not t.is_cuda and torch.cuda.is_available() and not t.is_pinned():
+        t = t.pin_memory()
+    return t
+
+
+class AttackEngineHost:
+    """Shared machinery: engine creation from ``vla`` (an HF-style module, a state dict, or a loaded VLAEngine),
+    patch / optimiser state, one outer iteration = set_batch + placements + ``innerLoop`` engine steps."""
+
+    def __init__(self, vla, cfg: Optional[OpenVLAConfig] = None, device="cuda:0", max_text_len: int = 64):
+        self.cfg = cfg or getattr(vla, "cfg", None) or openvla_7b()
+        self.device = torch.device(device)
+        self._vla = vla
+        self.engine: Optional[VLAEngine] = vla if isinstance(vla, VLAEngine) else None
+        self.max_text_len = max_text_len
+        self.patch = self.m = self.v = self.grad = None
+        self.opt_step = 0
+        self.world_size, self.rank = 1, 0
+
+    # -- engine ---------------------------------------------------------------------------------------------
+    def ensure_engine(self, B: int, T: int):
+        if self.engine is None:
+            self.engine = VLAEngine(self.cfg, B, max(T, 11), device=self.device)
+            src = self._vla
+            if src is None:
+                raise _lib.VLAError("no weights: pass an HF model, a state dict or a loaded VLAEngine")
+            sd = src if isinstance(src, dict) else src.state_dict()
+            self.engine.load_state_dict(sd, strict=False)
+        self.engine.ensure_plan(B, T)
+        return self.engine
+
+    # -- patch / optimiser state -----------------------------------------------------------------------------
+    def init_patch(self, patch_size, patch: Optional[torch.Tensor] = None):
+        """``patch = torch.rand(patch_size)`` (UADA.py:104); DDP: rank 0's value is broadcast (UADA_ddp.py:140-144)."""
+        if patch is None:
+            patch = torch.rand(list(patch_size))
+        self.patch = patch.to(self.device, torch.float32).contiguous()
+        if self.world_size > 1:
+            torch.distributed.broadcast(self.patch, src=0)
+        self.m = torch.zeros_like(self.patch)
+        self.v = torch.zeros_like(self.patch)
+        self.grad = torch.zeros_like(self.patch)
+        self.opt_step = 0
+
+    def run_inner_loop(self, batch, n_inner, fe_mode, loss: LossSpec, lr, opt_kind, clip_l1=0.0, do_step=True,
+                       accumulate=None):
+        """One outer iteration. Returns (scalars [n_inner, 8] on the host, pred_ids [R] of the last inner step)."""
+        obs = observations_to_uint8(batch["pixel_values"], self.cfg.img)
+        B, T = batch["input_ids"].shape
+        eng = self.ensure_engine(B, T)
+        R = eng.set_batch(obs, batch["input_ids"], batch["attention_mask"], batch["labels"])
+        geometry = fe_mode == _lib.FE_WARP
+        xy, theta = draw_placements(B, (self.cfg.img, self.cfg.img), tuple(self.patch.shape[1:]), geometry, steps=n_inner)
+        eng.set_placements(xy, theta)
+        scalars = torch.zeros(n_inner, _lib.NUM_SCALARS, device=self.device)
+        pred = torch.full((R,), -1, dtype=torch.int32, device=self.device)
+        for s in range(n_inner):
+            eng.fwd_bwd(self.patch, s, fe_mode, loss, self.grad, scalars[s], pred)
+            g = self.grad
+            if accumulate is not None:        # TMA / UPA with accumulate_steps > 1: grads pile up until a stepping iteration
+                accumulate.add_(self.grad)
+                g = accumulate
+            if self.world_size > 1:           # DDP reducer: all-reduce of patch.grad on every backward (UADA_ddp.py:206)
+                torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM)
+            if do_step:
+                self.opt_step += 1
+                eng.patch_update(self.patch, g, self.m, self.v, self.opt_step, lr, kind=opt_kind,
+                                 grad_scale=1.0 / self.world_size, clip_l1=clip_l1, scalars=scalars[s])
+                if accumulate is not None:
+                    accumulate.zero_()
+        return scalars.cpu(), pred.cpu()
+
+    def evaluate(self, batch, fe_mode, loss: LossSpec):
+        """Forward-only pass (validation): scalars [8] and pred_ids [R] on the host."""
+        obs = observations_to_uint8(batch["pixel_values"], self.cfg.img)
+        B, T = batch["input_ids"].shape
+        eng = self.ensure_engine(B, T)
+        R = eng.set_batch(obs, batch["input_ids"], batch["attention_mask"], batch["labels"])
+        xy, theta = draw_placements(B, (self.cfg.img, self.cfg.img), tuple(self.patch.shape[1:]), fe_mode == _lib.FE_WARP, 1)
+        eng.set_placements(xy, theta)
+        scalars = torch.zeros(_lib.NUM_SCALARS, device=self.device)
+        pred = torch.full((R,), -1, dtype=torch.int32, device=self.device)
+        eng.fwd_bwd(self.patch, 0, fe_mode, loss, self.grad, scalars, pred, forward_only=True)
+        return scalars.cpu(), pred.cpu()
+
+
+def _decoded_pairs(pred_ids: torch.Tensor, labels: torch.Tensor):
+    """(pred, gt) continuous actions of the supervised ACTION tokens, in (sample, position) order."""
+    sup = labels[:, 1:][labels[:, 1:] != IGNORE_INDEX]
+    act = sup > lab.ACTION_TOKEN_BEGIN_IDX
+    gt = torch.tensor(lab.decode_token_ids_to_actions(sup[act].numpy()))
+    pr = torch.tensor(lab.decode_token_ids_to_actions(pred_ids.long()[act].numpy()))
+    return pr, gt
+
+
+class _AttackerBase(object):
+    KIND = "UADA"
+
+    def __init__(self, vla, processor=None, save_dir="", optimizer="pgd", resize_patch=False, cfg=None, device="cuda:0"):
+        self.vla = vla
+        self.processor = processor
+        self.save_dir = save_dir
+        self.optimizer = optimizer
+        if resize_patch:
+            raise NotImplementedError("resize_patch=True is dead code in the reference (appply_random_transform.py:113-118)")
+        self.host = AttackEngineHost(vla, cfg=cfg, device=device)
+        self.mean = [torch.tensor(NORM_MEAN[0]), torch.tensor(NORM_MEAN[1])]
+        self.std = [torch.tensor(NORM_STD[0]), torch.tensor(NORM_STD[1])]
+        self.randomPatchTransform = RandomPatchTransform(device, resize_patch)
+        self.loss_buffer = []
+        self.val_every = 100
+        self.val_batches = 1000
+
+    # reference helpers kept under their names
+    def mask_labels(self, labels, maskidx):
+        return lab.mask_labels_uada(labels, maskidx)
+
+    def _save_patch(self, patch, sub):
+        d = os.path.join(self.save_dir, sub)
+        os.makedirs(d, exist_ok=True)
+        torch.save(patch.detach().cpu(), os.path.join(d, "patch.pt"))     # fp32 [3,h,w] CPU tensor, as the reference
+        return d
+
+    def _dump(self, **lists):
+        os.makedirs(self.save_dir, exist_ok=True)
+        for name, values in lists.items():
+            with open(os.path.join(self.save_dir, f"{name}.pkl"), "wb") as f:
+                pickle.dump(values, f)
+
+    @staticmethod
+    def _log(args, data, step):
+        if args is not None and getattr(args, "wandb_project", "false") != "false":
+            try:
+                import wandb
+                wandb.log(data, step=step)
+            except ImportError:
+                pass
+
+    @staticmethod
+    def _next(iterator, loader):
+        try:
+            return next(iterator), iterator
+        except StopIteration:
+            iterator = iter(loader)
+            return next(iterator), iterator
+
+
+class UADAAttacker(_AttackerBase):
+    """Untargeted action-discrepancy attack (UADA.py).  loss = mean((5e - 5t)^2) + 1/CE."""
+    KIND = "UADA"
+
+    def patchattack_unconstrained(self, train_dataloader, val_dataloader, num_iter=5000, target_action=np.zeros(7),
+                                  patch_size=[3, 50, 50], lr=1 / 255, accumulate_steps=1, maskidx=[], warmup=20,
+                                  filterGripTrainTo1=False, geometry=False, innerLoop=1, args=None):
+        h = self.host
+        self.val_CE_loss, self.val_MSE_Distance, self.val_UAD = [], [], []
+        self.train_CE_loss, self.train_MSE_distance_loss, self.train_UAD = [], [], []
+        self.MSE_Distance_best = 10000
+        h.init_patch(patch_size)
+        loss = LossSpec(_lib.LOSS_UADA, mse_weight=5.0)
+        fe_mode = _lib.FE_WARP if geometry else _lib.FE_PASTE20
+        opt_kind = _lib.OPT_ADAMW if self.optimizer == "adamW" else _lib.OPT_PGD
+        total = int(num_iter / accumulate_steps)
+        sched_step = 0
+        train_it, val_it = iter(train_dataloader), iter(val_dataloader)
+        for i in range(num_iter):
+            data, train_it = self._next(train_it, train_dataloader)
+            data = dict(data)
+            data["labels"] = self.mask_labels(data["labels"].clone(), maskidx)
+            cur_lr = lr * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else lr
+            scalars, pred = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind)
+            self.train_CE_loss += scalars[:, _lib.S_CE].tolist()
+            self.train_MSE_distance_loss += scalars[:, _lib.S_LOSS].tolist()
+            self.train_UAD += scalars[:, _lib.S_UAD].tolist()
+            if self.optimizer == "adamW" and ((i + 1) % accumulate_steps == 0):
+                sched_step += 1
+            pr, gt = _decoded_pairs(pred, data["labels"])
+            rd = lab.relative_distance(pr, gt).view(-1, max(1, len(maskidx)))
+            log = {"TRAIN_attack_loss(CE)": scalars[-1, _lib.S_CE].item(),
+                   "TRAIN_patch_gradient": scalars[-1, _lib.S_GRAD_MEAN].item(),
+                   "TRAIN_LR": cur_lr,
+                   "TRAIN_attack_loss (MSE_Distance)": scalars[-1, _lib.S_LOSS].item(),
+                   "TRAIN_UAD": scalars[-1, _lib.S_UAD].item()}
+            for k, idx in enumerate(maskidx):
+                log[f"train_rd_{idx}"] = rd[:, k].mean().item()
+            self.loss_buffer.append(log["TRAIN_attack_loss (MSE_Distance)"])
+            self._log(args, log, i)
+            if i % self.val_every == 0:
+                val_it = self._validate(i, val_it, val_dataloader, maskidx, fe_mode, loss, args)
+        return h.patch.detach().cpu()
+
+    def _validate(self, i, val_it, val_dataloader, maskidx, fe_mode, loss, args):
+        h = self.host
+        n, s_mse, s_uad, s_ce = 0, 0.0, 0.0, 0.0
+        rds = []
+        for _ in range(self.val_batches):
+            data, val_it = self._next(val_it, val_dataloader)
+            data = dict(data)
+            data["labels"] = self.mask_labels(data["labels"].clone(), maskidx)
+            n += data["labels"].shape[0]
+            sc, pred = h.evaluate(data, fe_mode, loss)
+            s_mse += sc[_lib.S_AUX0].item()
+            s_uad += sc[_lib.S_UAD].item()
+            s_ce += sc[_lib.S_CE].item()
+            pr, gt = _decoded_pairs(pred, data["labels"])
+            rds.append(lab.relative_distance(pr, gt).view(-1, max(1, len(maskidx))))
+        avg_mse, avg_uad, avg_ce = s_mse / n, s_uad / n, s_ce / n     # the reference divides by the sample count
+        log = {"VAL_MSE_Distance": avg_mse, "VAL_UAD": avg_uad}
+        rd = torch.cat(rds)
+        for k, idx in enumerate(maskidx):
+            log[f"val_rd_{idx}"] = rd[:, k].mean().item()
+        self._log(args, log, i)
+        if avg_mse < self.MSE_Distance_best:
+            self.MSE_Distance_best = avg_mse
+            self._save_patch(h.patch, str(i))
+        self._save_patch(h.patch, "last")
+        self.val_CE_loss.append(avg_ce)
+        self.val_MSE_Distance.append(avg_mse)
+        self.val_UAD.append(avg_uad)
+        self._dump(train_CE_loss=self.train_CE_loss, train_MSE_distance_loss=self.train_MSE_distance_loss,
+                   train_UAD=self.train_UAD, val_CE_loss=self.val_CE_loss, val_MSE_Distance=self.val_MSE_Distance,
+                   val_UAD=self.val_UAD)
+        return val_it
+
+
+class UPAAttacker(_AttackerBase):
+    """Untargeted position-aware attack (UPA.py)."""
+    KIND = "UPA"
+
+    def __init__(self, vla, processor=None, save_dir="", optimizer="pgd", resize_patch=False, alpha=0.5, belta=0.5, **kw):
+        super().__init__(vla, processor, save_dir, optimizer, resize_patch, **kw)
+        self.alpha, self.belta = alpha, belta
+        self.val_batches = 100
+
+    def mask_labels(self, labels, maskidx):
+        return lab.mask_labels_upa(labels, maskidx)
+
+    def patchattack_unconstrained(self, train_dataloader, val_dataloader, num_iter=5000, target_action=np.zeros(7),
+                                  patch_size=[3, 50, 50], lr=1 / 255, accumulate_steps=1, maskidx=[], warmup=20,
+                                  filterGripTrainTo1=False, geometry=False, guide=False, innerLoop=1,
+                                  reverse_direction=True, args=None):
+        h = self.host
+        self.train_CE_loss, self.val_CE_loss = [], []
+        h.init_patch(patch_size)
+        if guide:
+            loss = LossSpec(_lib.LOSS_CE, ce_scale=1.0)
+        elif reverse_direction:
+            loss = LossSpec(_lib.LOSS_UPA, alpha=self.alpha, belta=self.belta)
+        else:
+            loss = LossSpec(_lib.LOSS_NEG_CE)
+        fe_mode = _lib.FE_WARP if geometry else _lib.FE_PASTE20
+        opt_kind = _lib.OPT_ADAMW if self.optimizer == "adamW" else _lib.OPT_PGD
+        total = int(num_iter / accumulate_steps)
+        sched_step = 0
+        acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
+        train_it = iter(train_dataloader)
+        for i in range(num_iter):
+            data, train_it = self._next(train_it, train_dataloader)
+            data = dict(data)
+            labels = data["labels"].clone()
+            if not reverse_direction:
+                labels = self.mask_labels(labels, maskidx)
+            if guide:
+                labels = lab.change_target(labels)
+            data["labels"] = labels
+            stepping = (i + 1) % accumulate_steps == 0
+            cur_lr = lr * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else lr
+            scalars, _ = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind,
+                                          clip_l1=1e-3 if self.optimizer == "adamW" else 0.0, do_step=stepping, accumulate=acc)
+            if self.optimizer == "adamW" and stepping:
+                sched_step += 1
+            log = {"TRAIN_attack_loss(CE)": scalars[-1, _lib.S_LOSS].item(),
+                   "TRAIN_patch_gradient": scalars[-1, _lib.S_GRAD_MEAN].item(), "TRAIN_LR": cur_lr,
+                   "TRAIN_ANGLE_LOSS": scalars[-1, _lib.S_AUX0].item(), "TRAIN_DISTANCE_LOSS": scalars[-1, _lib.S_AUX1].item()}
+            self.train_CE_loss.append(log["TRAIN_attack_loss(CE)"])
+            self.loss_buffer.append(log["TRAIN_attack_loss(CE)"])
+            self._log(args, log, i)
+            if i % self.val_every == 0:
+                self._save_patch(h.patch, "last")
+                self._dump(train_CE_loss=self.train_CE_loss)
+        return h.patch.detach().cpu()
+
+
+class TMAAttacker(_AttackerBase):
+    """Targeted manipulation attack (TMA.py): CE towards a target action on the DoF in ``maskidx``."""
+    KIND = "TMA"
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.val_batches = 100
+
+    def patchattack_unconstrained(self, train_dataloader, val_dataloader, num_iter=5000, target_action=np.zeros(7),
+                                  patch_size=[3, 50, 50], alpha=1 / 255, accumulate_steps=1, maskidx=[], warmup=20,
+                                  filterGripTrainTo1=False, geometry=False, colorjitter=False, innerLoop=1, args=None):
+        h = self.host
+        self.train_CE_loss, self.train_inner_avg_loss, self.train_inner_relatived_distance = [], [], []
+        h.init_patch(patch_size)
+        target = lab.tma_target(target_action, maskidx)
+        loss = LossSpec(_lib.LOSS_CE, ce_scale=1.0 / accumulate_steps)
+        fe_mode = _lib.FE_WARP if geometry else _lib.FE_FIX          # paste_patch_fix when no geometry (TMA.py:133-135)
+        opt_kind = _lib.OPT_ADAMW if self.optimizer == "adamW" else _lib.OPT_PGD
+        total = int(num_iter / accumulate_steps)
+        sched_step = 0
+        acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
+        train_it = iter(train_dataloader)
+        for i in range(num_iter):
+            data, train_it = self._next(train_it, train_dataloader)
+            data = dict(data)
+            data["labels"] = lab.tma_labels(data["labels"], target)
+            stepping = (i + 1) % accumulate_steps == 0
+            cur_lr = alpha * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else alpha
+            scalars, pred = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind, do_step=stepping, accumulate=acc)
+            if self.optimizer == "adamW" and stepping:
+                sched_step += 1
+            pr, gt = _decoded_pairs(pred, data["labels"])
+            rd = lab.relative_distance(pr, gt).mean().item() if pr.numel() else 0.0
+            log = {"TRAIN_attack_loss(CE)": scalars[-1, _lib.S_LOSS].item(),
+                   "TRAIN_patch_gradient": scalars[-1, _lib.S_GRAD_MEAN].item(), "TRAIN_LR": cur_lr,
+                   "TRAIN_inner_avg_loss": scalars[:, _lib.S_LOSS].mean().item(), "TRAIN_inner_relatived_distance": rd}
+            self.train_CE_loss.append(log["TRAIN_attack_loss(CE)"])
+            self.train_inner_avg_loss.append(log["TRAIN_inner_avg_loss"])
+            self.train_inner_relatived_distance.append(rd)
+            self.loss_buffer.append(log["TRAIN_attack_loss(CE)"])
+            self._log(args, log, i)
+            if i % self.val_every == 0:
+                self._save_patch(h.patch, "last")
+                self._dump(train_CE_loss=self.train_CE_loss, train_inner_avg_loss=self.train_inner_avg_loss)
+        return h.patch.detach().cpu()
+
+
+class UADADDPAttacker(_AttackerBase):
+    """UADA with the batch sharded over ranks (UADA_ddp.py): one process per GPU, each rank runs the engine on its
+    shard, the patch gradient is all-reduced (mean) every inner step, the replicated update keeps patches identical.
+    Constructor mirrors UADA_ddp.py:37 except that the model / dataset are passed in instead of loaded by path."""
+    KIND = "UADA_DDP"
+
+    def __init__(self, vla, dataloaders=None, save_dir="", resize_patch=False, patch_size=[3, 50, 50], lr=0.01, bs=1,
+                 warmup=20, num_iter=10000, maskidx=[], innerLoop=1, geometry=True, use_wandb=False, MSE_weights=1,
+                 cfg=None, device=None):
+        rank = int(os.environ.get("LOCAL_RANK", 0))
+        device = device or f"cuda:{rank}"
+        super().__init__(vla, None, save_dir, "adamW", resize_patch, cfg=cfg, device=device)
+        self.dataloaders = dataloaders
+        self.patch_size, self.lr, self.bs, self.warmup, self.num_iter = patch_size, lr, bs, warmup, num_iter
+        self.maskidx, self.innerLoop, self.geometry, self.use_wandb, self.MSE_weights = maskidx, innerLoop, geometry, use_wandb, MSE_weights
+        self.val_every, self.val_batches = 200, 100
+        self.val_CE_loss, self.val_MSE_Distance, self.val_UAD = [], [], []
+
+    def setup(self, rank, world_size):
+        import torch.distributed as dist
+        if world_size > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", rank=rank, world_size=world_size)
+        torch.cuda.set_device(self.host.device)
+        self.host.rank, self.host.world_size = rank, world_size
+
+    def attack(self, rank, world_size, train_dataloader=None, val_dataloader=None):
+        import torch.distributed as dist
+        self.setup(rank, world_size)
+        h = self.host
+        train_dataloader = train_dataloader or self.dataloaders[0]
+        h.init_patch(self.patch_size)
+        loss = LossSpec(_lib.LOSS_UADA_DDP, mse_weight=float(self.MSE_weights))
+        fe_mode = _lib.FE_WARP if self.geometry else _lib.FE_PASTE20
+        logs = []
+        for i, data in enumerate(train_dataloader):
+            if i == self.num_iter:
+                break
+            data = dict(data)
+            data["labels"] = self.mask_labels(data["labels"].clone(), self.maskidx)
+            cur_lr = self.lr * cosine_with_warmup(i, self.warmup, int(self.num_iter))
+            scalars, _ = h.run_inner_loop(data, self.innerLoop, fe_mode, loss, cur_lr, _lib.OPT_ADAMW)
+            # four scalar all-reduces of the reference (UADA_ddp.py:214-221) packed into one
+            last = scalars[-1]
+            pack = torch.tensor([last[_lib.S_CE], last[_lib.S_LOSS], last[_lib.S_UAD], last[_lib.S_GRAD_MEAN]], device=h.device)
+            if world_size > 1:
+                gathered = [torch.zeros_like(pack) for _ in range(world_size)]
+                dist.all_gather(gathered, pack)
+                g = torch.stack(gathered)
+                pack = torch.stack([g[:, 0].mean(), g[:, 1].mean(), g[:, 2].mean(), g[:, 3].max()])
+            log = {"TRAIN_attack_loss(CE)": pack[0].item(), "TRAIN_attack_loss (MSE_Distance)": pack[1].item(),
+                   "TRAIN_UAD": pack[2].item(), "TRAIN_patch_gradient": pack[3].item(), "TRAIN_LR": cur_lr}
+            logs.append(log)
+            if rank == 0 and i % self.val_every == 0 and self.save_dir:
+                self._save_patch(h.patch, "last")
+        self.train_logs = logs
+        return h.patch.detach().cpu()

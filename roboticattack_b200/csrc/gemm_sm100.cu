@@ -15,10 +15,46 @@
 //                              store bf16 (or fp32) rows
 // Two TMEM accumulator stages (2 x BLOCK_N columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <unordered_map>
+#include <vector>
 
 #include "gemm.h"
 
 long long g_vla_launch_count = 0;
+
+// Optional per-launch timing of the GEMM kernel (bench.py's roofline leg): CUDA events recorded on the launch
+// stream around every GEMM launch while enabled; summed after a synchronise.
+namespace {
+struct GemmProf {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop)
+  std::vector<double> flops;
+  size_t used = 0;
+} g_prof;
+}  // namespace
+
+extern "C" int vla_profile_gemm_begin(void) {
+  g_prof.on = true;
+  g_prof.used = 0;
+  g_prof.flops.clear();
+  return 0;
+}
+
+// total_ms: sum of GEMM kernel durations; total_flops: sum of 2*M*N*K (true, unpadded dims); launches: count
+extern "C" int vla_profile_gemm_end(double* total_ms, double* total_flops, int* launches) {
+  g_prof.on = false;
+  VLA_CHECK_CUDA(cudaDeviceSynchronize());
+  double ms = 0.0, fl = 0.0;
+  for (size_t i = 0; i < g_prof.flops.size(); ++i) {
+    float t = 0.f;
+    VLA_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+    ms += t;
+    fl += g_prof.flops[i];
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = static_cast<int>(g_prof.flops.size());
+  return 0;
+}
 
 namespace {
 
@@ -380,8 +416,24 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g,
   }
   const int tiles = g.num_m_blocks * g.num_n_blocks;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof.on) {
+    while (g_prof.ev.size() < g_prof.used + 2) {
+      cudaEvent_t ev;
+      VLA_CHECK_CUDA(cudaEventCreate(&ev));
+      g_prof.ev.push_back(ev);
+    }
+    e0 = g_prof.ev[g_prof.used];
+    e1 = g_prof.ev[g_prof.used + 1];
+    g_prof.used += 2;
+    VLA_CHECK_CUDA(cudaEventRecord(e0, stream));
+  }
   gemm_bf16_tn_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, g);
   VLA_LAUNCH_CHECK();
+  if (e1) {
+    VLA_CHECK_CUDA(cudaEventRecord(e1, stream));
+    g_prof.flops.push_back(2.0 * g.M * g.N * g.K);
+  }
   ++g_vla_launch_count;
   return 0;
 }

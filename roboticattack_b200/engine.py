@@ -72,14 +72,30 @@ class VLAEngine:
         sbytes = self._lib.vla_engine_workspace_bytes(self._h, batch, text_len)
         self.weight_arena = torch.empty(wbytes, dtype=torch.uint8, device=self.device)
         self.workspace = torch.empty(sbytes, dtype=torch.uint8, device=self.device)
-        _lib.check(self._lib.vla_engine_set_buffers(self._h, _lib.ptr(self.weight_arena), wbytes,
-                                                    _lib.ptr(self.workspace), sbytes, batch, text_len),
-                   "vla_engine_set_buffers")
-        cos, sin = rope_tables(self.L, cfg.llm.head_dim, cfg.llm.rope_theta)
-        _lib.check(self._lib.vla_engine_set_rope(self._h, _lib.ptr(cos), _lib.ptr(sin), self.L, _lib.cur_stream()),
-                   "vla_engine_set_rope")
         self.num_supervised = 0
         self._weights_ok = False
+        self._bind(batch, text_len)
+
+    def _bind(self, batch, text_len):
+        self.B, self.T, self.L = batch, text_len, text_len + self.cfg.num_patches
+        _lib.check(self._lib.vla_engine_set_buffers(self._h, _lib.ptr(self.weight_arena), self.weight_arena.numel(),
+                                                    _lib.ptr(self.workspace), self.workspace.numel(), batch, text_len),
+                   "vla_engine_set_buffers")
+        cos, sin = rope_tables(self.L, self.cfg.llm.head_dim, self.cfg.llm.rope_theta)
+        _lib.check(self._lib.vla_engine_set_rope(self._h, _lib.ptr(cos), _lib.ptr(sin), self.L, _lib.cur_stream()),
+                   "vla_engine_set_rope")
+        torch.cuda.synchronize(self.device)
+
+    def ensure_plan(self, batch, text_len):
+        """Re-plan the activation arena when the collator hands over a different (B, T); weights stay in place."""
+        if (batch, text_len) == (self.B, self.T):
+            return
+        need = self._lib.vla_engine_workspace_bytes(self._h, batch, text_len)
+        if need > self.workspace.numel():
+            torch.cuda.synchronize(self.device)
+            self.workspace = None
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._bind(batch, text_len)
 
     def __del__(self):
         h = getattr(self, "_h", None)

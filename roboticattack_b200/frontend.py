@@ -1,0 +1,92 @@
+"""``RandomPatchTransform`` with the reference's method names, backed by the fused CUDA front end.
+
+Reference: VLAAttacker/white_patch/appply_random_transform.py:8-197.  Differences: images may be a list of PIL images
+(as the collator yields), a uint8 array/tensor [B,H,W,3]; the result is the bf16 tensor the model consumes
+(the reference returns fp32 and callers immediately cast with ``.to(torch.bfloat16)``, UADA.py:142); gradients
+flow to ``patch`` through a ``torch.autograd.Function`` that calls ``vla_patch_frontend_bwd``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import NORM_MEAN, NORM_STD
+from .synthetic import draw_placements
+
+
+def _as_uint8_batch(images, device):
+    if isinstance(images, torch.Tensor):
+        t = images
+    else:
+        t = torch.from_numpy(np.stack([np.asarray(im, dtype=np.uint8) for im in images]))
+    assert t.dtype == torch.uint8 and t.dim() == 4 and t.shape[-1] == 3, "images must be uint8 [B,H,W,3]"
+    return t.to(device).contiguous()
+
+
+class _FrontendFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, patch, obs, xy, theta, mode, norm):
+        B, H, W, _ = obs.shape
+        out = torch.empty(B, 6, H, W, device=obs.device, dtype=torch.bfloat16)
+        p = patch.detach().to(torch.float32).contiguous()
+        _lib.check(_lib.lib().vla_patch_frontend_fwd(_lib.ptr(obs), _lib.ptr(p), _lib.ptr(xy), _lib.ptr(theta), _lib.ptr(out),
+                                                     B, H, W, p.shape[1], p.shape[2], mode, norm, _lib.cur_stream()),
+                   "vla_patch_frontend_fwd")
+        ctx.save_for_backward(p, xy, theta)
+        ctx.meta = (B, H, W, mode, norm)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        p, xy, theta = ctx.saved_tensors
+        B, H, W, mode, norm = ctx.meta
+        dp = torch.empty_like(p)
+        g = dout.to(torch.bfloat16).contiguous()
+        _lib.check(_lib.lib().vla_patch_frontend_bwd(_lib.ptr(g), _lib.ptr(p), _lib.ptr(xy), _lib.ptr(theta), _lib.ptr(dp),
+                                                     B, H, W, p.shape[1], p.shape[2], mode, norm, _lib.cur_stream()),
+                   "vla_patch_frontend_bwd")
+        return dp, None, None, None, None, None
+
+
+class RandomPatchTransform:
+    def __init__(self, device, resize_patch=False):
+        self.device = torch.device(device)
+        self.angle, self.shx, self.shy = 30, 0.2, 0.2
+        if resize_patch:
+            raise NotImplementedError("resize_patch=True is dead code in the reference (uses a variable before assignment)")
+        self.resize_patch = resize_patch
+
+    def normalize(self, images, mean, std):
+        return (images - mean[None, :, None, None]) / std[None, :, None, None]
+
+    def denormalize(self, images, mean, std):
+        return images * std[None, :, None, None] + mean[None, :, None, None]
+
+    def _run(self, images, patch, mean, std, mode, geometry):
+        obs = _as_uint8_batch(images, self.device)
+        B, H, W, _ = obs.shape
+        mean = NORM_MEAN if mean is None else [[float(v) for v in m] for m in mean]
+        std = NORM_STD if std is None else [[float(v) for v in s] for s in std]
+        norm = _lib.norm_array(mean, std)
+        if mode == _lib.FE_NONE:
+            xy = torch.zeros(B, 2, dtype=torch.int32, device=self.device)
+            theta = torch.zeros(B, 2, 3, device=self.device)
+            patch = torch.zeros(3, 1, 1, device=self.device)
+        else:
+            xy_np, th_np = draw_placements(B, (H, W), tuple(patch.shape[1:]), geometry, steps=1)
+            xy = torch.from_numpy(xy_np[0]).to(self.device)
+            theta = torch.from_numpy(th_np[0]).to(self.device)
+        return _FrontendFn.apply(patch.to(self.device), obs, xy, theta, mode, norm)
+
+    def apply_random_patch_batch(self, images, patch, mean=None, std=None, geometry=False):
+        return self._run(images, patch, mean, std, _lib.FE_WARP if geometry else _lib.FE_PASTE20, geometry)
+
+    def random_paste_patch(self, images, patch, mean=None, std=None):
+        return self._run(images, patch, mean, std, _lib.FE_FIX, False)
+
+    def paste_patch_fix(self, images, patch, mean=None, std=None, inference=False):
+        return self._run(images, patch, mean, std, _lib.FE_FIX, False)
+
+    def im_process(self, images, mean=None, std=None):
+        return self._run(images, None, mean, std, _lib.FE_NONE, False)
