@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--text-len", type=int, default=33)
     ap.add_argument("--model", default="openvla-7b", choices=["openvla-7b", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="profiling aid: bracket ONE steady-state step with cudaProfilerStart/Stop and exit (no JSON line)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -252,6 +254,12 @@ def engine_arm(args):
     for s in range(W):
         step(s)
     sync()
+    if args.ncu_step:
+        torch.cuda.profiler.start()
+        step(W)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return 0
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lib.vla_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -303,8 +311,10 @@ def engine_arm(args):
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every GEMM launch of one more step
     roof = None
+    eng.set_placements(xy, theta)
     if rank == 0:
         import ctypes
+        eng.set_placements(xy, theta)
         lib.vla_profile_gemm_begin()
         step(W)
         tm, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()

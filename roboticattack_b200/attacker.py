@@ -53,8 +53,10 @@ class AttackEngineHost:
     """Shared machinery: engine creation from ``vla`` (an HF-style module, a state dict, or a loaded VLAEngine),
     patch / optimiser state, one outer iteration = set_batch + placements + ``innerLoop`` engine steps."""
 
-    def __init__(self, vla, cfg: Optional[OpenVLAConfig] = None, device="cuda:0", max_text_len: int = 64):
+    def __init__(self, vla, cfg: Optional[OpenVLAConfig] = None, device="cuda:0", max_text_len: int = 64,
+                 engine_factory=None):
         self.cfg = cfg or getattr(vla, "cfg", None) or openvla_7b()
+        self.engine_factory = engine_factory or VLAEngine
         self.device = torch.device(device)
         self._vla = vla
         self.engine: Optional[VLAEngine] = vla if isinstance(vla, VLAEngine) else None
@@ -66,7 +68,7 @@ class AttackEngineHost:
     # -- engine ---------------------------------------------------------------------------------------------
     def ensure_engine(self, B: int, T: int):
         if self.engine is None:
-            self.engine = VLAEngine(self.cfg, B, max(T, 11), device=self.device)
+            self.engine = self.engine_factory(self.cfg, B, T, device=self.device)
             src = self._vla
             if src is None:
                 raise _lib.VLAError("no weights: pass an HF model, a state dict or a loaded VLAEngine")
@@ -142,17 +144,18 @@ def _decoded_pairs(pred_ids: torch.Tensor, labels: torch.Tensor):
 class _AttackerBase(object):
     KIND = "UADA"
 
-    def __init__(self, vla, processor=None, save_dir="", optimizer="pgd", resize_patch=False, cfg=None, device="cuda:0"):
+    def __init__(self, vla, processor=None, save_dir="", optimizer="pgd", resize_patch=False, cfg=None, device="cuda:0",
+                 engine_factory=None):
         self.vla = vla
         self.processor = processor
         self.save_dir = save_dir
         self.optimizer = optimizer
         if resize_patch:
             raise NotImplementedError("resize_patch=True is dead code in the reference (appply_random_transform.py:113-118)")
-        self.host = AttackEngineHost(vla, cfg=cfg, device=device)
+        self.host = AttackEngineHost(vla, cfg=cfg, device=device, engine_factory=engine_factory)
         self.mean = [torch.tensor(NORM_MEAN[0]), torch.tensor(NORM_MEAN[1])]
         self.std = [torch.tensor(NORM_STD[0]), torch.tensor(NORM_STD[1])]
-        self.randomPatchTransform = RandomPatchTransform(device, resize_patch)
+        self.randomPatchTransform = RandomPatchTransform(device, resize_patch)   # reference attribute; used by eval scripts
         self.loss_buffer = []
         self.val_every = 100
         self.val_batches = 1000
@@ -382,10 +385,11 @@ class UADADDPAttacker(_AttackerBase):
 
     def __init__(self, vla, dataloaders=None, save_dir="", resize_patch=False, patch_size=[3, 50, 50], lr=0.01, bs=1,
                  warmup=20, num_iter=10000, maskidx=[], innerLoop=1, geometry=True, use_wandb=False, MSE_weights=1,
-                 cfg=None, device=None):
+                 cfg=None, device=None, engine_factory=None, backend="nccl"):
         rank = int(os.environ.get("LOCAL_RANK", 0))
         device = device or f"cuda:{rank}"
-        super().__init__(vla, None, save_dir, "adamW", resize_patch, cfg=cfg, device=device)
+        super().__init__(vla, None, save_dir, "adamW", resize_patch, cfg=cfg, device=device, engine_factory=engine_factory)
+        self.backend = backend
         self.dataloaders = dataloaders
         self.patch_size, self.lr, self.bs, self.warmup, self.num_iter = patch_size, lr, bs, warmup, num_iter
         self.maskidx, self.innerLoop, self.geometry, self.use_wandb, self.MSE_weights = maskidx, innerLoop, geometry, use_wandb, MSE_weights
@@ -395,8 +399,9 @@ class UADADDPAttacker(_AttackerBase):
     def setup(self, rank, world_size):
         import torch.distributed as dist
         if world_size > 1 and not dist.is_initialized():
-            dist.init_process_group("nccl", rank=rank, world_size=world_size)
-        torch.cuda.set_device(self.host.device)
+            dist.init_process_group(self.backend, rank=rank, world_size=world_size)
+        if self.host.device.type == "cuda":
+            torch.cuda.set_device(self.host.device)
         self.host.rank, self.host.world_size = rank, world_size
 
     def attack(self, rank, world_size, train_dataloader=None, val_dataloader=None):

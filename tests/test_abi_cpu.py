@@ -1,0 +1,78 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol include/vla_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from roboticattack_b200.build import build_extension
+    return build_extension()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "vla_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vla_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(built):
+    lib = ctypes.CDLL(str(built))
+    names = declared_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in vla_b200.h but not exported: {missing}"
+
+
+def test_binding_covers_header(built):
+    from roboticattack_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    h = _lib.lib()
+    assert h.vla_abi_version() == 1
+    assert h.vla_launch_count() >= 0
+
+
+def test_errors_are_reported_not_swallowed(built):
+    """Host-side validation works without a GPU: bad arguments -> non-zero rc + message (no compute call is made)."""
+    from roboticattack_b200 import _lib
+    h = _lib.lib()
+    cfg = _lib.Config()
+    cfg.img, cfg.patch = 225, 14            # not a multiple of the ViT patch
+    out = ctypes.c_void_p()
+    rc = h.vla_engine_create(ctypes.byref(cfg), ctypes.byref(out))
+    assert rc != 0 and b"multiple" in h.vla_last_error()
+    with pytest.raises(_lib.VLAError):
+        _lib.check(rc, "vla_engine_create")
+    rc = h.vla_patch_update(None, None, None, None, 0, 0, 0.0, 0.9, 0.999, 1e-6, 0, 1.0, 0.0, None, None)
+    assert rc != 0
+
+
+def test_engine_planning_without_gpu(built):
+    """Arena sizes are pure host arithmetic: OpenVLA-7B at bs=8 needs ~30 GB of weights and ~10 GB of activations."""
+    from roboticattack_b200 import _lib
+    from roboticattack_b200.config import openvla_7b
+    from roboticattack_b200.engine import _c_config
+    h = _lib.lib()
+    c = _c_config(openvla_7b())
+    e = ctypes.c_void_p()
+    _lib.check(h.vla_engine_create(ctypes.byref(c), ctypes.byref(e)))
+    wb = h.vla_engine_weight_bytes(e)
+    sb = h.vla_engine_workspace_bytes(e, 8, 33)
+    h.vla_engine_destroy(e)
+    assert 29e9 < wb < 32e9, wb
+    assert 8e9 < sb < 16e9, sb
+
+
+def test_engine_refuses_cpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from roboticattack_b200 import _lib
+    from roboticattack_b200.config import tiny
+    from roboticattack_b200.engine import VLAEngine
+    with pytest.raises(_lib.VLAError):
+        VLAEngine(tiny(), 1, 16)
