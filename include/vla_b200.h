@@ -29,6 +29,12 @@ long long vla_launch_count(void);
  * its launch stream; _end synchronises the device and returns the summed kernel time, the summed algorithmic FLOPs
  * (2*M*N*K with the true, unpadded dims) and the launch count. */
 int vla_profile_gemm_begin(void);
+/* pin one GEMM kernel variant: ctas in {1,2} (2 = tcgen05.mma.cta_group::2 CTA pairs), block_n in {128,256};
+ * (0,0) restores the automatic per-shape choice.  For A/B measurements and the variant parity tests. */
+int vla_gemm_set_mode(int ctas, int block_n);
+/* autotune (default on): the FIRST call with a new (M,N,K) times every kernel variant on the real operands and keeps
+ * the fastest for later calls; that first call synchronises the stream (warm-up only; never while capturing). */
+int vla_gemm_set_autotune(int on);
 int vla_profile_gemm_end(double* total_ms, double* total_flops, int* launches);
 
 /* ------------------------------------------------------------------------------------------------------------

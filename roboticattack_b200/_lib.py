@@ -45,6 +45,8 @@ SIGNATURES = {
     "vla_abi_version": (c_int, []),
     "vla_launch_count": (c_longlong, []),
     "vla_profile_gemm_begin": (c_int, []),
+    "vla_gemm_set_mode": (c_int, [c_int, c_int]),
+    "vla_gemm_set_autotune": (c_int, [c_int]),
     "vla_profile_gemm_end": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int)]),
     "vla_patch_frontend_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_int, POINTER(c_float), c_void_p]),

@@ -63,13 +63,13 @@ __global__ void copy_rows_kernel(const bf16* __restrict__ src, int64_t lds, int 
   *reinterpret_cast<uint4*>(dst + (static_cast<int64_t>(b) * rows_dst + dst_off + r) * ldd + c * 8) = v;
 }
 
-__global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ table,
+__global__ void embed_splice_kernel(const int64_t* __restrict__ ids, int ld_ids, const bf16* __restrict__ table,
                                     bf16* __restrict__ x, int B, int T, int P, int d8) {
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<int64_t>(B) * T * d8) return;
   const int c = static_cast<int>(idx % d8), t = static_cast<int>((idx / d8) % T);
   const int b = static_cast<int>(idx / (static_cast<int64_t>(d8) * T));
-  const int64_t id = ids[b * T + t];
+  const int64_t id = ids[b * ld_ids + t];
   const int pos = (t == 0) ? 0 : P + t;   // [BOS | P patch rows | rest of the text]
   const int64_t d = static_cast<int64_t>(d8) * 8;
   *reinterpret_cast<uint4*>(x + (static_cast<int64_t>(b) * (T + P) + pos) * d + c * 8) =
@@ -158,22 +158,43 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __r
   *reinterpret_cast<uint4*>(dgu + m * 2 * F + F + c * 8) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
 }
 
-// one thread per (row, q|k, head, pair i < hd/2)
+// one thread per (row, q|k, head, 8 consecutive rotation pairs): two 16-byte loads, two 16-byte stores
 __global__ void rope_kernel(bf16* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
                             int64_t M, int L, int H, int hd, float sgn) {
-  const int half = hd / 2;
+  const int half = hd / 2, oct = half / 8;
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (idx >= M * 2 * H * half) return;
-  const int i = static_cast<int>(idx % half);
-  const int h = static_cast<int>((idx / half) % H);
-  const int which = static_cast<int>((idx / (static_cast<int64_t>(half) * H)) % 2);
-  const int64_t m = idx / (static_cast<int64_t>(half) * H * 2);
+  if (idx >= M * 2 * H * oct) return;
+  const int o = static_cast<int>(idx % oct);
+  const int h = static_cast<int>((idx / oct) % H);
+  const int which = static_cast<int>((idx / (static_cast<int64_t>(oct) * H)) % 2);
+  const int64_t m = idx / (static_cast<int64_t>(oct) * H * 2);
   const int pos = static_cast<int>(m % L);
-  bf16* p = qkv + m * 3 * H * hd + static_cast<int64_t>(which) * H * hd + h * hd;
-  const float c = cos_tab[pos * half + i], s = sgn * sin_tab[pos * half + i];
-  const float x1 = b2f(p[i]), x2 = b2f(p[i + half]);
-  p[i] = f2b(rbf(x1 * c) + rbf(-x2 * s));
-  p[i + half] = f2b(rbf(x2 * c) + rbf(x1 * s));
+  bf16* p = qkv + m * 3 * H * hd + static_cast<int64_t>(which) * H * hd + h * hd + o * 8;
+  const uint4 lo = *reinterpret_cast<const uint4*>(p), hi = *reinterpret_cast<const uint4*>(p + half);
+  const float4 c0 = *reinterpret_cast<const float4*>(cos_tab + pos * half + o * 8);
+  const float4 c1 = *reinterpret_cast<const float4*>(cos_tab + pos * half + o * 8 + 4);
+  const float4 s0 = *reinterpret_cast<const float4*>(sin_tab + pos * half + o * 8);
+  const float4 s1 = *reinterpret_cast<const float4*>(sin_tab + pos * half + o * 8 + 4);
+  const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+  const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w}, hw[4] = {hi.x, hi.y, hi.z, hi.w};
+  uint32_t ol[4], oh[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 a = unpack_bf16x2(lw[t]), b = unpack_bf16x2(hw[t]);
+    const float x1[2] = {a.x, a.y}, x2[2] = {b.x, b.y};
+    float r1[2], r2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float cc = c[2 * t + e], ss = sgn * sn[2 * t + e];
+      r1[e] = rbf(x1[e] * cc) + rbf(-x2[e] * ss);   // q*cos + rotate_half(q)*sin, each product a bf16 tensor in HF
+      r2[e] = rbf(x2[e] * cc) + rbf(x1[e] * ss);
+    }
+    ol[t] = pack_bf16x2(r1[0], r1[1]);
+    oh[t] = pack_bf16x2(r2[0], r2[1]);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  *reinterpret_cast<uint4*>(p + half) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
 }
 
 __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, int64_t n8) {
@@ -247,9 +268,10 @@ int copy_rows(const bf16* src, int64_t lds, int rows_src, int src_off, bf16* dst
       src, lds, rows_src, src_off, dst, ldd, rows_dst, dst_off, B, rows, cols / 8);
   EW_DONE();
 }
-int embed_tokens_splice(const int64_t* ids, const bf16* table, bf16* x, int B, int T, int P, int d, cudaStream_t s) {
+int embed_tokens_splice(const int64_t* ids, int ld_ids, const bf16* table, bf16* x, int B, int T, int P, int d,
+                        cudaStream_t s) {
   VLA_REQUIRE(d % 8 == 0, "embed: hidden must be a multiple of 8");
-  embed_splice_kernel<<<blocks_for(static_cast<int64_t>(B) * T * (d / 8)), EW_THREADS, 0, s>>>(ids, table, x, B, T, P, d / 8);
+  embed_splice_kernel<<<blocks_for(static_cast<int64_t>(B) * T * (d / 8)), EW_THREADS, 0, s>>>(ids, ld_ids, table, x, B, T, P, d / 8);
   EW_DONE();
 }
 int gelu_bwd(const bf16* dy, const bf16* pre, bf16* dx, int64_t n, cudaStream_t s) {
@@ -274,7 +296,8 @@ int swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int64_t M, int F, cu
 }
 int rope_inplace(bf16* qkv, const float* cos_tab, const float* sin_tab, int64_t M, int L, int H, int hd, int dir,
                  cudaStream_t s) {
-  rope_kernel<<<blocks_for(M * 2 * H * (hd / 2)), EW_THREADS, 0, s>>>(qkv, cos_tab, sin_tab, M, L, H, hd, dir >= 0 ? 1.f : -1.f);
+  VLA_REQUIRE(hd % 16 == 0, "rope: head dim must be a multiple of 16");
+  rope_kernel<<<blocks_for(M * 2 * H * (hd / 16)), EW_THREADS, 0, s>>>(qkv, cos_tab, sin_tab, M, L, H, hd, dir >= 0 ? 1.f : -1.f);
   EW_DONE();
 }
 int add_bf16(const bf16* a, const bf16* b, bf16* out, int64_t n, cudaStream_t s) {

@@ -263,7 +263,7 @@ struct Bump {
 size_t plan(vla_engine* e, uint8_t* base, int B, int T) {
   const vla_config& c = e->cfg;
   Bump bp{base};
-  const int H = c.img, P = e->np, L = T + P;
+  const int H = c.img, P = e->np, L = T + P - 1;   // the last text position is never a useful query or key (see set_buffers)
   const int64_t ML = static_cast<int64_t>(B) * L;
   const int h = c.llm_hidden, f = c.llm_ffn, V = c.vocab;
   const int Rmax = B * (T - 1);
@@ -515,7 +515,10 @@ extern "C" int vla_engine_set_buffers(vla_engine* e, void* weight_arena, size_t 
   e->ws_bytes = workspace_bytes;
   e->B = B;
   e->T = T;
-  e->L = T + e->np;
+  // Sequence run through the LLM: [BOS | np patch rows | text 1..T-2].  The last text position T-1 is dropped: under
+  // the causal mask no other position attends to it and the logits row it would produce predicts nothing (the shifted
+  // CE pairs logits[:, :-1] with labels[:, 1:]), so the loss and every gradient are unchanged.
+  e->L = T + e->np - 1;
   plan(e, e->ws, B, T);
   e->batch_set = false;
   e->rope_set = false;
@@ -632,7 +635,7 @@ extern "C" int vla_engine_set_batch(vla_engine* e, const uint8_t* obs, int obs_o
       VLA_REQUIRE(id >= 0 && id < e->cfg.vocab, "input id %lld out of range", static_cast<long long>(id));
     }
     VLA_REQUIRE(n >= 1, "sample %d has an empty attention mask", b);
-    kv[b] = P + n;
+    kv[b] = std::min(P + n, L);
     int idx = 0;
     for (int t = 1; t < T; ++t) {
       const int64_t y = labels[b * T + t];
@@ -721,7 +724,7 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
     ep3.out_offset = 1;
     CK(G(e->t_a, h, e->pj_w[2], h, e->la.x[0], h, MP, h, h, ep3, s));
   }
-  CK(embed_tokens_splice(e->ids, e->embed, e->la.x[0], B, T, P, h, s));
+  CK(embed_tokens_splice(e->ids, T, e->embed, e->la.x[0], B, T - 1, P, h, s));
   LlmActs& la = e->la;
   for (int l = 0; l < c.llm_layers; ++l) {
     const LlamaLayerW& w = e->lw[l];

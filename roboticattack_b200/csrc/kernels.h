@@ -25,7 +25,9 @@ int write_prefix_tokens(const bf16* cls, const bf16* reg, bf16* x, int B, int nt
 // dst[b*rows_dst + dst_off + r, 0:cols] = src[b*rows_src + src_off + r, 0:cols]  for r < rows, b < B
 int copy_rows(const bf16* src, int64_t lds, int rows_src, int src_off, bf16* dst, int64_t ldd, int rows_dst,
               int dst_off, int B, int rows, int cols, cudaStream_t s);
-int embed_tokens_splice(const int64_t* ids, const bf16* table, bf16* x, int B, int T, int P, int d, cudaStream_t s);
+// x[b] = [table[ids[b,0]] | P rows left for the projector | table[ids[b,1..T-1]]]; ids row stride ld_ids (>= T)
+int embed_tokens_splice(const int64_t* ids, int ld_ids, const bf16* table, bf16* x, int B, int T, int P, int d,
+                        cudaStream_t s);
 int gelu_bwd(const bf16* dy, const bf16* pre, bf16* dx, int64_t n, cudaStream_t s);
 int scale_cols(const bf16* x, const bf16* gamma, bf16* y, int64_t rows, int cols, cudaStream_t s);
 // gu [M, 2F] = [gate | up] -> act [M, F] = bf16(bf16(silu(gate)) * up)

@@ -61,7 +61,7 @@ class VLAEngine:
         if not torch.cuda.is_available():
             raise _lib.VLAError("VLAEngine needs a CUDA device (sm_100a); there is no CPU path")
         self.cfg, self.B, self.T = cfg, batch, text_len
-        self.L = text_len + cfg.num_patches
+        self.L = text_len + cfg.num_patches - 1
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self._lib = _lib.lib()
@@ -77,7 +77,8 @@ class VLAEngine:
         self._bind(batch, text_len)
 
     def _bind(self, batch, text_len):
-        self.B, self.T, self.L = batch, text_len, text_len + self.cfg.num_patches
+        # the engine drops the last text position (dead under the causal mask + shifted CE): L = T + P - 1
+        self.B, self.T, self.L = batch, text_len, text_len + self.cfg.num_patches - 1
         _lib.check(self._lib.vla_engine_set_buffers(self._h, _lib.ptr(self.weight_arena), self.weight_arena.numel(),
                                                     _lib.ptr(self.workspace), self.workspace.numel(), batch, text_len),
                    "vla_engine_set_buffers")

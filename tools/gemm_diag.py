@@ -60,18 +60,25 @@ def bench(M, N, K, iters=20):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    ok = True
-    ok &= run(128, 128, 64)
-    ok &= run(128, 256, 64)
-    ok &= run(128, 256, 256)
-    ok &= run(256, 512, 1024)
-    ok &= run(100, 200, 136)            # ragged everything
-    ok &= run(2312, 4096, 4096, bias=True)
-    ok &= run(2088, 4096, 1024, bias=True, act=1)
-    ok &= run(2088, 1024, 4096, bias=True, gamma=True, resid=True)
-    ok &= run(64, 32064, 4096, f32=True)
-    ok &= run(2048, 1152, 640, bias=True)
-    print("ALL OK" if ok else "FAILURES")
-    if ok or os.environ.get("BENCH_ANYWAY"):
-        for shp in [(2312, 4096, 4096), (2312, 12288, 4096), (2312, 22016, 4096), (2312, 4096, 11008), (2088, 4096, 1024), (2048, 4304, 1152), (8192, 8192, 8192)]:
-            bench(*shp)
+    L = _lib.lib()
+    allok = True
+    for mode in [(1, 256), (1, 128), (2, 256), (2, 128), (0, 0)]:
+        _lib.check(L.vla_gemm_set_mode(*mode))
+        print("=== variant (ctas, block_n) =", mode)
+        ok = True
+        ok &= run(128, 128, 64)
+        ok &= run(256, 256, 256)
+        ok &= run(300, 432, 144)
+        ok &= run(100, 200, 136)            # ragged everything
+        ok &= run(2304, 4096, 4096, bias=True)
+        ok &= run(2088, 4096, 1024, bias=True, act=1)
+        ok &= run(2088, 1024, 4096, bias=True, gamma=True, resid=True)
+        ok &= run(64, 32064, 4096, f32=True)
+        ok &= run(2048, 1152, 640, bias=True)
+        print("variant OK" if ok else "variant FAILED")
+        allok &= ok
+        if ok:
+            for shp in [(2304, 4096, 4096), (2304, 12288, 4096), (2304, 22016, 4096), (2304, 4096, 11008), (2088, 3072, 1024),
+                        (2088, 1024, 4096), (2048, 4304, 1152), (8192, 8192, 8192)]:
+                bench(*shp)
+    print("ALL OK" if allok else "FAILURES")
