@@ -439,9 +439,13 @@ int launch_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* ls
 
 }  // namespace
 
+int g_attn_impl = 1;
+
 int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                   cudaStream_t s) {
   VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
+  if (g_attn_impl && attention_tc_supported(N, hd))
+    return attention_fwd_tc(qkv, o, lse, kv_len, B, N, H, hd, causal, 1.f / sqrtf(static_cast<float>(hd)), s);
   if (hd <= 64) return launch_fwd<64>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   if (hd <= 80) return launch_fwd<80>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   return launch_fwd<128>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);

@@ -96,6 +96,11 @@ int vla_attention_bwd(const void* qkv, const void* o, const void* dout, const fl
                       const int32_t* kv_len, int B, int N, int H, int hd, int causal, void* stream) {
   return attention_bwd(CBF(qkv), CBF(o), CBF(dout), lse, delta, BF(dqkv), kv_len, B, N, H, hd, causal, S(stream));
 }
+int vla_attention_set_impl(int impl) {
+  VLA_REQUIRE(impl == 0 || impl == 1, "vla_attention_set_impl: 0 = legacy mma.sync, 1 = tcgen05 where supported");
+  g_attn_impl = impl;
+  return 0;
+}
 int vla_rope_inplace(void* qkv, const float* cos_tab, const float* sin_tab, int64_t M, int L, int H, int hd, int dir,
                      void* stream) {
   return rope_inplace(BF(qkv), cos_tab, sin_tab, M, L, H, hd, dir, S(stream));

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "gemm.h"
+#include "tma_desc.h"
 
 long long g_vla_launch_count = 0;
 
@@ -376,65 +377,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_tmapEncodeTiled get_encode_fn() {
-  static PFN_tmapEncodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
-  }
-  return fn;
-}
-
-struct TmapKey {
-  const void* ptr;
-  int64_t ld;
-  int rows, cols, box_rows;
-  bool operator==(const TmapKey& o) const {
-    return ptr == o.ptr && ld == o.ld && rows == o.rows && cols == o.cols && box_rows == o.box_rows;
-  }
-};
-struct TmapKeyHash {
-  size_t operator()(const TmapKey& k) const {
-    size_t h = reinterpret_cast<size_t>(k.ptr);
-    h ^= static_cast<size_t>(k.ld) * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-    h ^= (static_cast<size_t>(k.rows) << 32 | static_cast<uint32_t>(k.cols)) + (h << 6) + (h >> 2);
-    h ^= static_cast<size_t>(k.box_rows) * 0xC2B2AE3D27D4EB4Full;
-    return h;
-  }
-};
-
-// 2-D bf16 row-major [rows, cols] (ld elements between rows) -> tensor map with a (box_rows x 64) box,
-// 128B swizzle, zero fill out of bounds.
+// 2-D bf16 row-major [rows, cols] (ld elements between rows) -> tensor map with a (box_rows x 64) box, 128B swizzle
 int get_tmap(const bf16* ptr, int64_t ld, int rows, int cols, int box_rows, CUtensorMap* out) {
-  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{ptr, ld, rows, cols, box_rows};
-  auto it = cache.find(key);
-  if (it != cache.end()) {
-    *out = it->second;
-    return 0;
-  }
-  PFN_tmapEncodeTiled enc = get_encode_fn();
-  VLA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {BLOCK_K, static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  VLA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: CUresult %d (ptr %p ld %lld rows %d cols %d)", (int)r,
-              (const void*)ptr, (long long)ld, rows, cols);
-  if (cache.size() > 8192) cache.clear();
-  cache.emplace(key, *out);
-  return 0;
+  return make_tmap_bf16(ptr, cols, rows, 1, ld, 0, BLOCK_K, box_rows, out);
 }
 
 int g_num_sms = 0;

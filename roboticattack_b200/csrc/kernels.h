@@ -58,6 +58,12 @@ int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd,
 // causal != 0: key j visible to query i iff j <= i; kv_len (nullable) [B]: keys >= kv_len[b] are masked.
 int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                   cudaStream_t s);
+// tcgen05 implementations (attention_tc.cu): head dim 64 / 128, N <= 320.  attention_fwd / attention_bwd dispatch to them
+// when g_attn_impl != 0 and the shape is supported, else to the legacy mma.sync kernels.
+bool attention_tc_supported(int N, int hd);
+int attention_fwd_tc(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
+                     float scale, cudaStream_t s);
+extern int g_attn_impl;   // 0 = legacy mma.sync kernels only, 1 = tcgen05 where supported (default)
 // dqkv [B*N, 3*H*hd]; delta scratch [B, H, N] fp32
 int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                   const int* kv_len, int B, int N, int H, int hd, int causal, cudaStream_t s);

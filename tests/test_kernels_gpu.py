@@ -171,10 +171,21 @@ def test_rmsnorm(M, d):
 
 
 # ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("B,N,H,hd,causal,ragged", [(2, 261, 4, 64, 0, False), (2, 256, 3, 72, 0, False),
                                                     (3, 289, 4, 128, 1, True), (1, 21, 2, 64, 0, False),
-                                                    (2, 40, 2, 128, 1, True), (8, 289, 32, 128, 1, False)])
-def test_attention(B, N, H, hd, causal, ragged):
+                                                    (2, 40, 2, 128, 1, True), (8, 288, 32, 128, 1, False),
+                                                    (2, 320, 2, 128, 0, False), (2, 130, 2, 64, 1, True)])
+def test_attention(B, N, H, hd, causal, ragged, impl):
+    """impl 0 = legacy mma.sync kernels, 1 = tcgen05 kernels where supported (hd 64 / 128)."""
+    _lib.check(L.vla_attention_set_impl(impl))
+    try:
+        _attention_case(B, N, H, hd, causal, ragged)
+    finally:
+        _lib.check(L.vla_attention_set_impl(1))
+
+
+def _attention_case(B, N, H, hd, causal, ragged):
     g = torch.Generator(device="cuda").manual_seed(N * hd + H)
     D = H * hd
     qkv = torch.randn(B * N, 3 * D, device="cuda", generator=g).bfloat16()
