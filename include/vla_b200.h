@@ -106,7 +106,8 @@ int vla_attention_fwd(const void* qkv, void* o, float* lse, const int32_t* kv_le
                       int causal, void* stream);
 int vla_attention_bwd(const void* qkv, const void* o, const void* dout, const float* lse, float* delta_scratch,
                       void* dqkv, const int32_t* kv_len, int B, int N, int H, int hd, int causal, void* stream);
-/* 0 = legacy mma.sync attention kernels only; 1 (default) = tcgen05 kernels where the shape is supported (hd 64/128, N <= 320) */
+/* 0 (default) = pipelined mma.sync attention kernels; 1 = tcgen05 forward kernel where the shape is supported
+ * (hd 64/128, 64 <= N <= 320) */
 int vla_attention_set_impl(int impl);
 int vla_rope_inplace(void* qkv, const float* cos_tab, const float* sin_tab, int64_t M, int L, int H, int hd, int dir,
                      void* stream);

@@ -38,6 +38,25 @@ __device__ __forceinline__ void load_tile(bf16* __restrict__ s, const bf16* __re
   }
 }
 
+// Same tile copy with cp.async (16-byte, L2-only): issued for tile j+1 while tile j is being multiplied.
+template <int HDP>
+__device__ __forceinline__ void load_tile_async(bf16* __restrict__ s, const bf16* __restrict__ g, int64_t ldg, int r0,
+                                                int nrows, int hd) {
+  constexpr int LD = HDP + 8;
+  constexpr int CH = HDP / 8;
+  for (int idx = threadIdx.x; idx < 64 * CH; idx += ATT_THREADS) {
+    const int r = idx / CH, c = idx % CH;
+    const bool ok = (r0 + r < nrows) && (c * 8 < hd);
+    const bf16* src = ok ? g + static_cast<int64_t>(r0 + r) * ldg + c * 8 : g;
+    const uint32_t dst = smem_u32(s + r * LD + c * 8);
+    const int bytes = ok ? 16 : 0;   // src-size 0 -> the 16 destination bytes are zero filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // acc[NT][4] (16 x NT*8, fp32) += A(16 x K16*16) * B.
 //   A: registers a[K16][4] (mma A-fragment order) when A_REG, else smem rows a_row0.. (row stride lda), cols k.
 //   B_TRANS == false: Bs is [n][k] (contraction along smem columns), n range starts at b_row0.
@@ -96,8 +115,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
   using L = SmemLayout<HDP>;
   extern __shared__ __align__(16) uint8_t smem_att[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_att);
-  bf16* sK = sQ + L::TILE;
-  bf16* sV = sK + L::TILE;
+  bf16* sKb = sQ + L::TILE;            // K stage 0, K stage 1
+  bf16* sVb = sKb + 2 * L::TILE;       // V stage 0, V stage 1
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -106,8 +125,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
   const bf16* base = qkv + static_cast<int64_t>(b) * N * ld + h * hd;
   const int klen = kv_len ? min(kv_len[b], N) : N;
   const float sl2 = scale * LOG2E;
+  const int kv_end = causal ? min(klen, q0 + BM) : klen;
 
-  load_tile<HDP>(sQ, base, ld, q0, N, hd);
+  load_tile_async<HDP>(sQ, base, ld, q0, N, hd);
+  load_tile_async<HDP>(sKb, base + D, ld, 0, N, hd);
+  load_tile_async<HDP>(sVb, base + 2 * D, ld, 0, N, hd);
+  cp_async_commit();
 
   float acc_o[HDP / 8][4];
 #pragma unroll
@@ -116,11 +139,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
     for (int k = 0; k < 4; ++k) acc_o[i][k] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
 
-  const int kv_end = causal ? min(klen, q0 + BM) : klen;
-  for (int j0 = 0; j0 < kv_end; j0 += BN) {
-    __syncthreads();   // previous iteration's reads of sK/sV are done (also orders the sQ fill)
-    load_tile<HDP>(sK, base + D, ld, j0, N, hd);
-    load_tile<HDP>(sV, base + 2 * D, ld, j0, N, hd);
+  for (int j0 = 0, it = 0; j0 < kv_end; j0 += BN, ++it) {
+    const bf16* sK = sKb + (it & 1) * L::TILE;
+    const bf16* sV = sVb + (it & 1) * L::TILE;
+    if (j0 + BN < kv_end) {   // prefetch the next K/V tile into the other stage (freed by the barrier ending iteration it-1)
+      load_tile_async<HDP>(sKb + ((it + 1) & 1) * L::TILE, base + D, ld, j0 + BN, N, hd);
+      load_tile_async<HDP>(sVb + ((it + 1) & 1) * L::TILE, base + 2 * D, ld, j0 + BN, N, hd);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
 
     float s[8][4];
@@ -178,6 +207,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
     uint32_t pa[4][4];
     acc_to_afrag(s, pa);
     warp_gemm<HDP / 8, 4, true, true>(acc_o, pa, nullptr, 0, 0, sV, L::LD, 0);
+    __syncthreads();   // every warp is done with this stage before the next prefetch overwrites it
   }
 
   // epilogue: O / l, LSE (natural log)
@@ -235,8 +265,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
   extern __shared__ __align__(16) uint8_t smem_att[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_att);
   bf16* sdO = sQ + L::TILE;
-  bf16* sK = sdO + L::TILE;
-  bf16* sV = sK + L::TILE;
+  bf16* sKb = sdO + L::TILE;           // K stage 0, K stage 1
+  bf16* sVb = sKb + 2 * L::TILE;       // V stage 0, V stage 1
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -245,9 +275,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
   const bf16* base = qkv + static_cast<int64_t>(b) * N * ld + h * hd;
   const int klen = kv_len ? min(kv_len[b], N) : N;
   const float sl2 = scale * LOG2E;
+  const int kv_end = causal ? min(klen, q0 + BM) : klen;
 
-  load_tile<HDP>(sQ, base, ld, q0, N, hd);
-  load_tile<HDP>(sdO, dout + static_cast<int64_t>(b) * N * D + h * hd, D, q0, N, hd);
+  load_tile_async<HDP>(sQ, base, ld, q0, N, hd);
+  load_tile_async<HDP>(sdO, dout + static_cast<int64_t>(b) * N * D + h * hd, D, q0, N, hd);
+  load_tile_async<HDP>(sKb, base + D, ld, 0, N, hd);
+  load_tile_async<HDP>(sVb, base + 2 * D, ld, 0, N, hd);
+  cp_async_commit();
 
   float lse2[2], dl[2];
 #pragma unroll
@@ -265,11 +299,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc_dq[i][k] = 0.f;
 
-  const int kv_end = causal ? min(klen, q0 + BM) : klen;
-  for (int j0 = 0; j0 < kv_end; j0 += BN) {
-    __syncthreads();
-    load_tile<HDP>(sK, base + D, ld, j0, N, hd);
-    load_tile<HDP>(sV, base + 2 * D, ld, j0, N, hd);
+  for (int j0 = 0, it = 0; j0 < kv_end; j0 += BN, ++it) {
+    const bf16* sK = sKb + (it & 1) * L::TILE;
+    const bf16* sV = sVb + (it & 1) * L::TILE;
+    if (j0 + BN < kv_end) {
+      load_tile_async<HDP>(sKb + ((it + 1) & 1) * L::TILE, base + D, ld, j0 + BN, N, hd);
+      load_tile_async<HDP>(sVb + ((it + 1) & 1) * L::TILE, base + 2 * D, ld, j0 + BN, N, hd);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
 
     float s[8][4], dp[8][4];
@@ -292,6 +332,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
     uint32_t dsa[4][4];
     acc_to_afrag(s, dsa);
     warp_gemm<HDP / 8, 4, true, true>(acc_dq, dsa, nullptr, 0, 0, sK, L::LD, 0);
+    __syncthreads();
   }
 
 #pragma unroll
@@ -318,21 +359,39 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
   extern __shared__ __align__(16) uint8_t smem_att[];
   bf16* sK = reinterpret_cast<bf16*>(smem_att);
   bf16* sV = sK + L::TILE;
-  bf16* sQ = sV + L::TILE;
-  bf16* sdO = sQ + L::TILE;
-  float* sLse = reinterpret_cast<float*>(sdO + L::TILE);
-  float* sDelta = sLse + 64;
+  bf16* sQb = sV + L::TILE;            // Q stage 0, Q stage 1
+  bf16* sdOb = sQb + 2 * L::TILE;      // dO stage 0, dO stage 1
+  float* sLseB = reinterpret_cast<float*>(sdOb + 2 * L::TILE);   // [2][64]
+  float* sDeltaB = sLseB + 128;                                   // [2][64]
 
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * BM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int D = H * hd;
   const int64_t ld = 3 * static_cast<int64_t>(D);
   const bf16* base = qkv + static_cast<int64_t>(b) * N * ld + h * hd;
+  const bf16* dbase = dout + static_cast<int64_t>(b) * N * D + h * hd;
   const int klen = kv_len ? min(kv_len[b], N) : N;
   const float sl2 = scale * LOG2E;
+  const bool tile_live = j0 < klen;   // a fully masked key tile gets zero gradients
+  const int q_begin = causal ? (j0 / BN) * BN : 0;   // queries before this key tile never see it
 
-  load_tile<HDP>(sK, base + D, ld, j0, N, hd);
-  load_tile<HDP>(sV, base + 2 * D, ld, j0, N, hd);
+  auto stage_stats = [&](int stage, int q0) {   // lse / delta of the 64 queries of a stage (plain loads, tiny)
+    if (threadIdx.x < 64) {
+      const int row = q0 + threadIdx.x;
+      const float l = row < N ? lse[(static_cast<int64_t>(b) * H + h) * N + row] : INFINITY;
+      sLseB[stage * 64 + threadIdx.x] = (l == -INFINITY) ? INFINITY : l * LOG2E;
+      sDeltaB[stage * 64 + threadIdx.x] = row < N ? delta[(static_cast<int64_t>(b) * H + h) * N + row] : 0.f;
+    }
+  };
+
+  load_tile_async<HDP>(sK, base + D, ld, j0, N, hd);
+  load_tile_async<HDP>(sV, base + 2 * D, ld, j0, N, hd);
+  if (tile_live && q_begin < N) {
+    load_tile_async<HDP>(sQb, base, ld, q_begin, N, hd);
+    load_tile_async<HDP>(sdOb, dbase, D, q_begin, N, hd);
+    stage_stats(0, q_begin);
+  }
+  cp_async_commit();
 
   float acc_dk[HDP / 8][4], acc_dv[HDP / 8][4];
 #pragma unroll
@@ -340,17 +399,19 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc_dk[i][k] = acc_dv[i][k] = 0.f;
 
-  const bool tile_live = j0 < klen;   // a fully masked key tile gets zero gradients
-  const int q_begin = causal ? (j0 / BN) * BN : 0;   // queries before this key tile never see it
-  for (int q0 = q_begin; tile_live && q0 < N; q0 += BN) {
-    __syncthreads();
-    load_tile<HDP>(sQ, base, ld, q0, N, hd);
-    load_tile<HDP>(sdO, dout + static_cast<int64_t>(b) * N * D + h * hd, D, q0, N, hd);
-    if (threadIdx.x < 64) {
-      const int row = q0 + threadIdx.x;
-      const float l = row < N ? lse[(static_cast<int64_t>(b) * H + h) * N + row] : INFINITY;
-      sLse[threadIdx.x] = (l == -INFINITY) ? INFINITY : l * LOG2E;
-      sDelta[threadIdx.x] = row < N ? delta[(static_cast<int64_t>(b) * H + h) * N + row] : 0.f;
+  for (int q0 = q_begin, it = 0; tile_live && q0 < N; q0 += BN, ++it) {
+    const bf16* sQ = sQb + (it & 1) * L::TILE;
+    const bf16* sdO = sdOb + (it & 1) * L::TILE;
+    const float* sLse = sLseB + (it & 1) * 64;
+    const float* sDelta = sDeltaB + (it & 1) * 64;
+    if (q0 + BN < N) {
+      load_tile_async<HDP>(sQb + ((it + 1) & 1) * L::TILE, base, ld, q0 + BN, N, hd);
+      load_tile_async<HDP>(sdOb + ((it + 1) & 1) * L::TILE, dbase, D, q0 + BN, N, hd);
+      stage_stats((it + 1) & 1, q0 + BN);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
 
@@ -379,7 +440,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
     acc_to_afrag(dpt, dsa);
     warp_gemm<HDP / 8, 4, true, true>(acc_dv, pa, nullptr, 0, 0, sdO, L::LD, 0);   // dV += P^T dO
     warp_gemm<HDP / 8, 4, true, true>(acc_dk, dsa, nullptr, 0, 0, sQ, L::LD, 0);   // dK += dS^T Q
+    __syncthreads();
   }
+  cp_async_wait<0>();
 
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -400,7 +463,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
 template <int HDP>
 int launch_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                cudaStream_t s) {
-  constexpr int smem = 3 * SmemLayout<HDP>::TILE * 2;
+  constexpr int smem = 5 * SmemLayout<HDP>::TILE * 2;   // Q + 2 stages of (K, V)
   static bool configured = false;
   if (!configured) {
     VLA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -416,8 +479,8 @@ int launch_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, i
 template <int HDP>
 int launch_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                const int* kv_len, int B, int N, int H, int hd, int causal, cudaStream_t s) {
-  constexpr int smem_dq = 4 * SmemLayout<HDP>::TILE * 2;
-  constexpr int smem_dkv = 4 * SmemLayout<HDP>::TILE * 2 + 2 * 64 * 4;
+  constexpr int smem_dq = 6 * SmemLayout<HDP>::TILE * 2;    // Q, dO + 2 stages of (K, V)
+  constexpr int smem_dkv = 6 * SmemLayout<HDP>::TILE * 2 + 4 * 64 * 4;   // K, V + 2 stages of (Q, dO, lse, delta)
   static bool configured = false;
   if (!configured) {
     VLA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq));
@@ -439,7 +502,7 @@ int launch_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* ls
 
 }  // namespace
 
-int g_attn_impl = 1;
+int g_attn_impl = 0;   // the tcgen05 forward is correct but not yet faster than the pipelined legacy kernel: opt-in
 
 int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                   cudaStream_t s) {

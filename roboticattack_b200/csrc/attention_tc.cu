@@ -240,7 +240,7 @@ int launch_fwd_tc(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B
 
 }  // namespace
 
-bool attention_tc_supported(int N, int hd) { return (hd == 64 || hd == 128) && N <= MAX_KV; }
+bool attention_tc_supported(int N, int hd) { return (hd == 64 || hd == 128) && N >= 64 && N <= MAX_KV; }
 
 int attention_fwd_tc(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                      float scale, cudaStream_t s) {

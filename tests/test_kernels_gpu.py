@@ -182,7 +182,7 @@ def test_attention(B, N, H, hd, causal, ragged, impl):
     try:
         _attention_case(B, N, H, hd, causal, ragged)
     finally:
-        _lib.check(L.vla_attention_set_impl(1))
+        _lib.check(L.vla_attention_set_impl(0))
 
 
 def _attention_case(B, N, H, hd, causal, ragged):
