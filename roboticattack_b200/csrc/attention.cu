@@ -22,6 +22,13 @@ constexpr int BN = 64;   // rows of the streamed tile
 constexpr int ATT_THREADS = 128;
 constexpr float LOG2E = 1.4426950408889634f;
 
+// ex2.approx: one MUFU op (inputs are <= 0 here: exponent of a softmax term; -inf -> 0)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---- shared-memory tile helpers ------------------------------------------------------------------------
 // Copy rows [r0, r0+64) x cols [0, hd) of a head slice (global row stride ldg) into smem [64][LD], zero filling
 // rows >= nrows and the hd..HDP padding.
@@ -39,18 +46,36 @@ __device__ __forceinline__ void load_tile(bf16* __restrict__ s, const bf16* __re
 }
 
 // Same tile copy with cp.async (16-byte, L2-only): issued for tile j+1 while tile j is being multiplied.
+// Thread -> (row, 16-byte chunk) mapping is fixed; passes step the row by a constant, so the loop is adds only.
 template <int HDP>
 __device__ __forceinline__ void load_tile_async(bf16* __restrict__ s, const bf16* __restrict__ g, int64_t ldg, int r0,
                                                 int nrows, int hd) {
   constexpr int LD = HDP + 8;
   constexpr int CH = HDP / 8;
-  for (int idx = threadIdx.x; idx < 64 * CH; idx += ATT_THREADS) {
-    const int r = idx / CH, c = idx % CH;
-    const bool ok = (r0 + r < nrows) && (c * 8 < hd);
-    const bf16* src = ok ? g + static_cast<int64_t>(r0 + r) * ldg + c * 8 : g;
-    const uint32_t dst = smem_u32(s + r * LD + c * 8);
-    const int bytes = ok ? 16 : 0;   // src-size 0 -> the 16 destination bytes are zero filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+  if constexpr (ATT_THREADS % CH == 0) {
+    constexpr int ROWS_PER_PASS = ATT_THREADS / CH;
+    const int c = threadIdx.x % CH, r = threadIdx.x / CH;
+    const bool col_ok = c * 8 < hd;
+    const bf16* src = g + static_cast<int64_t>(r0 + r) * ldg + c * 8;
+    uint32_t dst = smem_u32(s + r * LD + c * 8);
+    int row = r0 + r;
+#pragma unroll
+    for (int p = 0; p < 64 / ROWS_PER_PASS; ++p) {
+      const bool ok = col_ok && row < nrows;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src : g), "r"(ok ? 16 : 0) : "memory");
+      src += ROWS_PER_PASS * ldg;
+      dst += ROWS_PER_PASS * LD * 2;
+      row += ROWS_PER_PASS;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < 64 * CH; idx += ATT_THREADS) {
+      const int r = idx / CH, c = idx % CH;
+      const bool ok = (r0 + r < nrows) && (c * 8 < hd);
+      const bf16* src = ok ? g + static_cast<int64_t>(r0 + r) * ldg + c * 8 : g;
+      const uint32_t dst = smem_u32(s + r * LD + c * 8);
+      const int bytes = ok ? 16 : 0;   // src-size 0 -> the 16 destination bytes are zero filled
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    }
   }
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -61,11 +86,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   A: registers a[K16][4] (mma A-fragment order) when A_REG, else smem rows a_row0.. (row stride lda), cols k.
 //   B_TRANS == false: Bs is [n][k] (contraction along smem columns), n range starts at b_row0.
 //   B_TRANS == true : Bs is [k][n] (contraction along smem rows),    k range starts at b_row0.
+// The lane-dependent part of every ldmatrix address is computed once; the unrolled loops only add constants.
 template <int NT, int K16, bool B_TRANS, bool A_REG>
 __device__ __forceinline__ void warp_gemm(float (&acc)[NT][4], const uint32_t (*a_reg)[4], const bf16* __restrict__ As,
                                           int lda, int a_row0, const bf16* __restrict__ Bs, int ldb, int b_row0) {
   const int lane = threadIdx.x & 31;
   const int mi = lane >> 3, r = lane & 7;
+  uint32_t a_base = 0;
+  if (!A_REG) a_base = smem_u32(As) + static_cast<uint32_t>(((a_row0 + (mi & 1) * 8 + r) * lda + (mi >> 1) * 8) * 2);
+  const uint32_t b_base = smem_u32(Bs) + static_cast<uint32_t>(
+      (B_TRANS ? ((b_row0 + (mi & 1) * 8 + r) * ldb + (mi >> 1) * 8) : ((b_row0 + (mi >> 1) * 8 + r) * ldb + (mi & 1) * 8)) * 2);
 #pragma unroll
   for (int ks = 0; ks < K16; ++ks) {
     uint32_t a[4];
@@ -73,15 +103,15 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[NT][4], const uint32_t (*
 #pragma unroll
       for (int q = 0; q < 4; ++q) a[q] = a_reg[ks][q];
     } else {
-      ldmatrix_x4(a, smem_u32(As + (a_row0 + (mi & 1) * 8 + r) * lda + ks * 16 + (mi >> 1) * 8));
+      ldmatrix_x4(a, a_base + ks * 32);
     }
 #pragma unroll
     for (int np = 0; np < NT / 2; ++np) {
       uint32_t b[4];
       if (!B_TRANS)
-        ldmatrix_x4(b, smem_u32(Bs + (b_row0 + (np * 2 + (mi >> 1)) * 8 + r) * ldb + ks * 16 + (mi & 1) * 8));
+        ldmatrix_x4(b, b_base + static_cast<uint32_t>((np * 16 * ldb + ks * 16) * 2));
       else
-        ldmatrix_x4_trans(b, smem_u32(Bs + (b_row0 + ks * 16 + (mi & 1) * 8 + r) * ldb + (np * 2 + (mi >> 1)) * 8));
+        ldmatrix_x4_trans(b, b_base + static_cast<uint32_t>((ks * 16 * ldb + np * 16) * 2));
       mma_bf16_16816(acc[np * 2], a, b[0], b[1]);
       mma_bf16_16816(acc[np * 2 + 1], a, b[2], b[3]);
     }
@@ -159,35 +189,43 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
       for (int k = 0; k < 4; ++k) s[i][k] = 0.f;
     warp_gemm<8, HDP / 16, false, false>(s, nullptr, sQ, L::LD, warp * 16, sK, L::LD, 0);
 
-    // mask + online softmax (rows g and g+8 of this warp's 16)
+    // mask + online softmax (rows g and g+8 of this warp's 16).  Tiles that lie entirely below the causal diagonal
+    // and inside the key length need no masking (warp-uniform test): most of the work takes the short path.
+    const int row0 = q0 + warp * 16 + g;
+    const bool need_mask = (j0 + BN > klen) || (causal && j0 + BN - 1 > q0 + warp * 16);
+    if (need_mask) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int col = j0 + nt * 8 + 2 * t + (k & 1);
+          const int row = row0 + (k >> 1) * 8;
+          const bool ok = (col < klen) && (!causal || col <= row);
+          if (!ok) s[nt][k] = -INFINITY;
+        }
+    }
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int col = j0 + nt * 8 + 2 * t + (k & 1);
-        const int row = q0 + warp * 16 + g + (k >> 1) * 8;
-        const bool ok = (col < klen) && (!causal || col <= row);
-        s[nt][k] = ok ? s[nt][k] * sl2 : -INFINITY;
-        mx[k >> 1] = fmaxf(mx[k >> 1], s[nt][k]);
-      }
-    float alpha[2], mnew[2];
+    for (int nt = 0; nt < 8; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+    float alpha[2], mref[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      mnew[r] = fmaxf(m_run[r], mx[r]);
-      const float mref = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
-      alpha[r] = exp2f(m_run[r] - mref);   // m_run = -inf -> 0
-      m_run[r] = mnew[r];
-      mnew[r] = mref;
+      const float mnew = fmaxf(m_run[r], mx[r] * sl2);       // running max in the log2 domain (sl2 > 0)
+      mref[r] = (mnew == -INFINITY) ? 0.f : mnew;
+      alpha[r] = fast_exp2(m_run[r] - mref[r]);              // m_run = -inf -> 0
+      m_run[r] = mnew;
     }
     float rs[2] = {0.f, 0.f};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float p = exp2f(s[nt][k] - mnew[k >> 1]);
+        const float p = fast_exp2(fmaf(s[nt][k], sl2, -mref[k >> 1]));   // masked: -inf -> 0
         s[nt][k] = p;
         rs[k >> 1] += p;
       }
@@ -319,14 +357,24 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
       for (int k = 0; k < 4; ++k) s[i][k] = dp[i][k] = 0.f;
     warp_gemm<8, HDP / 16, false, false>(s, nullptr, sQ, L::LD, warp * 16, sK, L::LD, 0);
     warp_gemm<8, HDP / 16, false, false>(dp, nullptr, sdO, L::LD, warp * 16, sV, L::LD, 0);
+    const bool need_mask = (j0 + BN > klen) || (causal && j0 + BN - 1 > q0 + warp * 16);
+    if (need_mask) {
+      const int row0 = q0 + warp * 16 + g;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int col = j0 + nt * 8 + 2 * t + (k & 1);
+          const int row = row0 + (k >> 1) * 8;
+          const bool ok = (col < klen) && (!causal || col <= row);
+          if (!ok) s[nt][k] = -INFINITY;
+        }
+    }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int col = j0 + nt * 8 + 2 * t + (k & 1);
-        const int row = q0 + warp * 16 + g + (k >> 1) * 8;
-        const bool ok = (col < klen) && (!causal || col <= row);
-        const float p = ok ? exp2f(s[nt][k] * sl2 - lse2[k >> 1]) : 0.f;
+        const float p = fast_exp2(fmaf(s[nt][k], sl2, -lse2[k >> 1]));   // masked / padded rows: -inf -> 0
         s[nt][k] = p * (dp[nt][k] - dl[k >> 1]);   // dS
       }
     uint32_t dsa[4][4];
@@ -423,18 +471,32 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
       for (int k = 0; k < 4; ++k) st[i][k] = dpt[i][k] = 0.f;
     warp_gemm<8, HDP / 16, false, false>(st, nullptr, sK, L::LD, warp * 16, sQ, L::LD, 0);
     warp_gemm<8, HDP / 16, false, false>(dpt, nullptr, sV, L::LD, warp * 16, sdO, L::LD, 0);
+    // columns of S^T are queries, rows are keys.  Padded queries carry lse = +inf (p = 0) already; masking is only
+    // needed on the causal diagonal and for key rows beyond the key length.
+    const bool need_mask = (j0 + warp * 16 + 16 > klen) || (causal && j0 + warp * 16 + 15 > q0);
+    if (need_mask) {
+      const int krow0 = j0 + warp * 16 + g;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int qrow = q0 + nt * 8 + 2 * t + (k & 1);
+          const int kcol = krow0 + (k >> 1) * 8;
+          const bool ok = (kcol < klen) && (!causal || kcol <= qrow);
+          if (!ok) st[nt][k] = -INFINITY;
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float2 l2 = *reinterpret_cast<const float2*>(sLse + nt * 8 + 2 * t);
+      const float2 d2 = *reinterpret_cast<const float2*>(sDelta + nt * 8 + 2 * t);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int qc = nt * 8 + 2 * t + (k & 1);          // query index inside the tile (column of S^T)
-        const int qrow = q0 + qc;
-        const int kcol = j0 + warp * 16 + g + (k >> 1) * 8;   // key index (row of S^T)
-        const bool ok = (qrow < N) && (kcol < klen) && (!causal || kcol <= qrow);
-        const float p = ok ? exp2f(st[nt][k] * sl2 - sLse[qc]) : 0.f;
-        st[nt][k] = p;                                   // P^T
-        dpt[nt][k] = p * (dpt[nt][k] - sDelta[qc]);      // dS^T
+        const float p = fast_exp2(fmaf(st[nt][k], sl2, -((k & 1) ? l2.y : l2.x)));
+        st[nt][k] = p;                                                  // P^T
+        dpt[nt][k] = p * (dpt[nt][k] - ((k & 1) ? d2.y : d2.x));        // dS^T
       }
+    }
     uint32_t pa[4][4], dsa[4][4];
     acc_to_afrag(st, pa);
     acc_to_afrag(dpt, dsa);
