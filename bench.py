@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--text-len", type=int, default=33)
     ap.add_argument("--model", default="openvla-7b", choices=["openvla-7b", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=900, help="seconds before a hung run dumps stacks and exits")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: bracket ONE steady-state step with cudaProfilerStart/Stop and exit (no JSON line)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
@@ -312,11 +313,11 @@ def engine_arm(args):
     # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every GEMM launch of one more step
     roof = None
     eng.set_placements(xy, theta)
+    import ctypes
     if rank == 0:
-        import ctypes
-        eng.set_placements(xy, theta)
         lib.vla_profile_gemm_begin()
-        step(W)
+    step(W)                                   # every rank runs the step (it contains the all-reduce); rank 0 times its GEMMs
+    if rank == 0:
         tm, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
         _lib.check(lib.vla_profile_gemm_end(ctypes.byref(tm), ctypes.byref(fl), ctypes.byref(n)), "profile end")
         pk = peaks()
@@ -356,6 +357,8 @@ def engine_arm(args):
 
 def main():
     args = parse()
+    import faulthandler
+    faulthandler.dump_traceback_later(args.watchdog, exit=True)   # a hung collective dumps stacks and exits instead of burning the box
     if args.impl == "reference":
         return reference_arm(args)
     return engine_arm(args)
