@@ -145,9 +145,9 @@ def cpu_reference_rate(cfg, batch, patch_hw, text_len, budget_s, threads):
         return min(ts)
 
     t_start = time.perf_counter()
-    t1 = run(1, 1, 2)
-    t2 = run(2, 2, 2)
-    per_layer_all = max(t2 - t1, 1e-6)           # one Llama layer + one block of each tower
+    t1 = run(1, 1, 3)
+    t2 = run(3, 3, 3)
+    per_layer_all = max((t2 - t1) / 2.0, 1e-6)   # one Llama layer + one block of each tower
     base = max(t1 - per_layer_all, 0.0)          # front end, patch embed, projector, lm_head, loss, update
     # split the per-depth cost between LLM and towers by their FLOP shares
     from roboticattack_b200.config import flops_per_sample
@@ -158,9 +158,9 @@ def cpu_reference_rate(cfg, batch, patch_hw, text_len, budget_s, threads):
     tot = f_llm + f_d + f_s
     t_full = base + per_layer_all * (cfg.llm.layers * f_llm + cfg.dino.depth * f_d + cfg.siglip.depth * f_s) / tot
     t_iter = t_full * batch
-    sample = (f"oracle (PyTorch restatement of the reference path), bs=1, full widths, depth 1 and 2 of "
+    sample = (f"oracle (PyTorch restatement of the reference path, frozen weights), bs=1, full widths, depth 1 and 3 of "
               f"{cfg.llm.layers} Llama layers / {cfg.dino.depth}+{cfg.siglip.depth} ViT blocks, fwd + backward-to-patch + AdamW, "
-              f"best of 2 each ({t1:.2f}s, {t2:.2f}s); linear extrapolation to full depth ({t_full:.1f}s/sample) x bs={batch}; "
+              f"best of 3 each ({t1:.2f}s, {t2:.2f}s); linear extrapolation to full depth ({t_full:.1f}s/sample) x bs={batch}; "
               f"sample took {time.perf_counter() - t_start:.0f}s of CPU work")
     return 1.0 / t_iter, sample
 
@@ -186,7 +186,7 @@ def reference_arm(args):
             "config": {"workload": workload_name(args), "note": "reference arm = the reference's CPU PyTorch path on this box's host cores"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -349,13 +349,30 @@ def engine_arm(args):
                 "gpu_launches": int(launches), "launches_per_step": launches / K,
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "loss_first_last": [losses[0].item(), losses[-1].item()]}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was sent to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)            # fd 1 -> stderr for the whole run (NCCL prints its version banner on stdout)
     args = parse()
     import faulthandler
     faulthandler.dump_traceback_later(args.watchdog, exit=True)   # a hung collective dumps stacks and exits instead of burning the box
