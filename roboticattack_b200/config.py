@@ -111,7 +111,7 @@ def tiny(img: int = 56, llm_layers: int = 2, vit_depth: int = 3) -> OpenVLAConfi
     return OpenVLAConfig(
         dino=ViTConfig(dim=128, depth=vit_depth, heads=2, mlp_hidden=512, num_prefix=5, layerscale=True, img=img),
         siglip=ViTConfig(dim=144, depth=vit_depth, heads=2, mlp_hidden=536, num_prefix=0, layerscale=False, img=img),
-        llm=LlamaConfig(hidden=256, layers=llm_layers, heads=2, ffn=688),
+        llm=LlamaConfig(hidden=256, layers=llm_layers, heads=2, ffn=704),
         name=f"tiny-{img}",
     )
 

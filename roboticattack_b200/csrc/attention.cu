@@ -270,35 +270,43 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
 // =========================================================================================================
 // backward
 // =========================================================================================================
-// delta[b,h,n] = sum_d dO * O   (one warp per (row, head))
-__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta, int B,
-                                  int N, int H, int hd) {
-  const int64_t w = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= static_cast<int64_t>(B) * N * H) return;
-  const int h = static_cast<int>(w % H);
-  const int64_t row = w / H;   // b*N + n
-  const bf16* po = o + row * H * hd + h * hd;
-  const bf16* pd = dout + row * H * hd + h * hd;
-  float s = 0.f;
-  for (int c = lane * 2; c < hd; c += 64) {
-    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(po + c));
-    const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(pd + c));
-    s += a.x * d.x + a.y * d.y;
+// Writes one thread's share of a gradient row (columns i*8 + 2t, +1 of every 8-column tile) as bf16(acc * scale).
+// With rope tables (head dim 128) the rotary embedding's backward is applied on the way out: the gradient wrt the
+// pre-RoPE q / k is the inverse rotation of the gradient wrt the rotated ones (pairs (c, c + 64) live in tiles i, i + 8).
+template <int HDP>
+__device__ __forceinline__ void store_grad_row(bf16* __restrict__ drow, const float (&acc)[HDP / 8][4], int r, int t, int hd,
+                                               float scale, const float* __restrict__ rope_cos,
+                                               const float* __restrict__ rope_sin, int pos) {
+  if constexpr (HDP == 128) {
+    if (rope_cos != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int col = i * 8 + 2 * t;
+        const float2 c = *reinterpret_cast<const float2*>(rope_cos + pos * 64 + col);
+        const float2 sn = *reinterpret_cast<const float2*>(rope_sin + pos * 64 + col);
+        const float l0 = rbf(acc[i][r * 2] * scale), l1 = rbf(acc[i][r * 2 + 1] * scale);
+        const float h0 = rbf(acc[i + 8][r * 2] * scale), h1 = rbf(acc[i + 8][r * 2 + 1] * scale);
+        *reinterpret_cast<uint32_t*>(drow + col) = pack_bf16x2(rbf(l0 * c.x) + rbf(h0 * sn.x), rbf(l1 * c.y) + rbf(h1 * sn.y));
+        *reinterpret_cast<uint32_t*>(drow + 64 + col) = pack_bf16x2(rbf(h0 * c.x) + rbf(-l0 * sn.x), rbf(h1 * c.y) + rbf(-l1 * sn.y));
+      }
+      return;
+    }
   }
-  s = warp_sum(s);
-  if (lane == 0) {
-    const int n = static_cast<int>(row % N), b = static_cast<int>(row / N);
-    delta[(static_cast<int64_t>(b) * H + h) * N + n] = s;
+#pragma unroll
+  for (int i = 0; i < HDP / 8; ++i) {
+    const int col = i * 8 + 2 * t;
+    if (col < hd) *reinterpret_cast<uint32_t*>(drow + col) = pack_bf16x2(acc[i][r * 2] * scale, acc[i][r * 2 + 1] * scale);
   }
 }
 
 // dQ: CTA owns 64 query rows, streams K/V tiles.
 template <int HDP>
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
-                                                                  const float* __restrict__ lse, const float* __restrict__ delta,
-                                                                  bf16* __restrict__ dqkv, const int* __restrict__ kv_len, int N,
-                                                                  int H, int hd, int causal, float scale) {
+__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
+                                                                  const bf16* __restrict__ dout, const float* __restrict__ lse,
+                                                                  float* __restrict__ delta, bf16* __restrict__ dqkv,
+                                                                  const int* __restrict__ kv_len, int N, int H, int hd, int causal,
+                                                                  float scale, const float* __restrict__ rope_cos,
+                                                                  const float* __restrict__ rope_sin, int rope_L) {
   using L = SmemLayout<HDP>;
   extern __shared__ __align__(16) uint8_t smem_att[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_att);
@@ -321,14 +329,34 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
   load_tile_async<HDP>(sVb, base + 2 * D, ld, 0, N, hd);
   cp_async_commit();
 
-  float lse2[2], dl[2];
+  float lse2[2], dl[2] = {0.f, 0.f};
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int row = q0 + warp * 16 + g + r * 8;
     const bool ok = row < N;
     const float l = ok ? lse[(static_cast<int64_t>(b) * H + h) * N + row] : INFINITY;
     lse2[r] = (l == -INFINITY) ? INFINITY : l * LOG2E;   // fully masked / padded rows -> p = 0
-    dl[r] = ok ? delta[(static_cast<int64_t>(b) * H + h) * N + row] : 0.f;
+  }
+  // delta = rowsum(dO * O) for this warp's 16 rows (was a separate kernel): one coalesced row read each, warp reduce;
+  // written out for the dK/dV kernel that follows on the stream.
+  {
+    const bf16* obase = o + static_cast<int64_t>(b) * N * D + h * hd;
+    const bf16* dbase = dout + static_cast<int64_t>(b) * N * D + h * hd;
+    for (int rr = 0; rr < 16; ++rr) {
+      const int row = q0 + warp * 16 + rr;
+      float sum = 0.f;
+      if (row < N) {
+        for (int c = lane * 2; c < hd; c += 64) {
+          const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(obase + static_cast<int64_t>(row) * D + c));
+          const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dbase + static_cast<int64_t>(row) * D + c));
+          sum += a.x * d.x + a.y * d.y;
+        }
+      }
+      sum = warp_sum(sum);
+      if (rr == g) dl[0] = sum;
+      if (rr == g + 8) dl[1] = sum;
+      if (lane == 0 && row < N) delta[(static_cast<int64_t>(b) * H + h) * N + row] = sum;
+    }
   }
 
   float acc_dq[HDP / 8][4];
@@ -388,12 +416,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
     const int row = q0 + warp * 16 + g + r * 8;
     if (row >= N) continue;
     bf16* drow = dqkv + (static_cast<int64_t>(b) * N + row) * ld + h * hd;
-#pragma unroll
-    for (int i = 0; i < HDP / 8; ++i) {
-      const int col = i * 8 + 2 * t;
-      if (col < hd)
-        *reinterpret_cast<uint32_t*>(drow + col) = pack_bf16x2(acc_dq[i][r * 2] * scale, acc_dq[i][r * 2 + 1] * scale);
-    }
+    store_grad_row<HDP>(drow, acc_dq, r, t, hd, scale, rope_cos, rope_sin, row % (rope_L > 0 ? rope_L : 1));
   }
 }
 
@@ -402,7 +425,9 @@ template <int HDP>
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                    const float* __restrict__ lse, const float* __restrict__ delta,
                                                                    bf16* __restrict__ dqkv, const int* __restrict__ kv_len, int N,
-                                                                   int H, int hd, int causal, float scale) {
+                                                                   int H, int hd, int causal, float scale,
+                                                                   const float* __restrict__ rope_cos,
+                                                                   const float* __restrict__ rope_sin, int rope_L) {
   using L = SmemLayout<HDP>;
   extern __shared__ __align__(16) uint8_t smem_att[];
   bf16* sK = reinterpret_cast<bf16*>(smem_att);
@@ -511,14 +536,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
     const int row = j0 + warp * 16 + g + r * 8;
     if (row >= N) continue;
     bf16* drow = dqkv + (static_cast<int64_t>(b) * N + row) * ld + h * hd;
-#pragma unroll
-    for (int i = 0; i < HDP / 8; ++i) {
-      const int col = i * 8 + 2 * t;
-      if (col < hd) {
-        *reinterpret_cast<uint32_t*>(drow + D + col) = pack_bf16x2(acc_dk[i][r * 2] * scale, acc_dk[i][r * 2 + 1] * scale);
-        *reinterpret_cast<uint32_t*>(drow + 2 * D + col) = pack_bf16x2(acc_dv[i][r * 2], acc_dv[i][r * 2 + 1]);
-      }
-    }
+    store_grad_row<HDP>(drow + D, acc_dk, r, t, hd, scale, rope_cos, rope_sin, row % (rope_L > 0 ? rope_L : 1));
+    store_grad_row<HDP>(drow + 2 * D, acc_dv, r, t, hd, 1.f, nullptr, nullptr, 0);
   }
 }
 
@@ -540,7 +559,8 @@ int launch_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, i
 
 template <int HDP>
 int launch_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
-               const int* kv_len, int B, int N, int H, int hd, int causal, cudaStream_t s) {
+               const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
+               int rope_L, cudaStream_t s) {
   constexpr int smem_dq = 6 * SmemLayout<HDP>::TILE * 2;    // Q, dO + 2 stages of (K, V)
   constexpr int smem_dkv = 6 * SmemLayout<HDP>::TILE * 2 + 4 * 64 * 4;   // K, V + 2 stages of (Q, dO, lse, delta)
   static bool configured = false;
@@ -550,15 +570,14 @@ int launch_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* ls
     configured = true;
   }
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
-  const int64_t nwarps = static_cast<int64_t>(B) * N * H;
-  attn_delta_kernel<<<static_cast<unsigned>(ceil_div64(nwarps * 32, 256)), 256, 0, s>>>(o, dout, delta, B, N, H, hd);
-  VLA_LAUNCH_CHECK();
   dim3 grid(ceil_div(N, BM), H, B);
-  attn_bwd_dq_kernel<HDP><<<grid, ATT_THREADS, smem_dq, s>>>(qkv, dout, lse, delta, dqkv, kv_len, N, H, hd, causal, scale);
+  attn_bwd_dq_kernel<HDP><<<grid, ATT_THREADS, smem_dq, s>>>(qkv, o, dout, lse, delta, dqkv, kv_len, N, H, hd, causal, scale,
+                                                             rope_cos, rope_sin, rope_L);
   VLA_LAUNCH_CHECK();
-  attn_bwd_dkv_kernel<HDP><<<grid, ATT_THREADS, smem_dkv, s>>>(qkv, dout, lse, delta, dqkv, kv_len, N, H, hd, causal, scale);
+  attn_bwd_dkv_kernel<HDP><<<grid, ATT_THREADS, smem_dkv, s>>>(qkv, dout, lse, delta, dqkv, kv_len, N, H, hd, causal, scale,
+                                                               rope_cos, rope_sin, rope_L);
   VLA_LAUNCH_CHECK();
-  g_vla_launch_count += 3;
+  g_vla_launch_count += 2;
   return 0;
 }
 
@@ -577,9 +596,12 @@ int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B
 }
 
 int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
-                  const int* kv_len, int B, int N, int H, int hd, int causal, cudaStream_t s) {
+                  const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
+                  int rope_L, cudaStream_t s) {
   VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
-  if (hd <= 64) return launch_bwd<64>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, s);
-  if (hd <= 80) return launch_bwd<80>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, s);
-  return launch_bwd<128>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, s);
+  VLA_REQUIRE(rope_cos == nullptr || (hd == 128 && rope_sin != nullptr && rope_L > 0),
+              "attention_bwd: the fused RoPE backward needs head dim 128 and both tables");
+  if (hd <= 64) return launch_bwd<64>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, nullptr, nullptr, 0, s);
+  if (hd <= 80) return launch_bwd<80>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, nullptr, nullptr, 0, s);
+  return launch_bwd<128>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, rope_cos, rope_sin, rope_L, s);
 }

@@ -94,7 +94,8 @@ int vla_attention_fwd(const void* qkv, void* o, float* lse, const int32_t* kv_le
 }
 int vla_attention_bwd(const void* qkv, const void* o, const void* dout, const float* lse, float* delta, void* dqkv,
                       const int32_t* kv_len, int B, int N, int H, int hd, int causal, void* stream) {
-  return attention_bwd(CBF(qkv), CBF(o), CBF(dout), lse, delta, BF(dqkv), kv_len, B, N, H, hd, causal, S(stream));
+  return attention_bwd(CBF(qkv), CBF(o), CBF(dout), lse, delta, BF(dqkv), kv_len, B, N, H, hd, causal, nullptr, nullptr, 0,
+                       S(stream));
 }
 int vla_attention_set_impl(int impl) {
   VLA_REQUIRE(impl == 0 || impl == 1, "vla_attention_set_impl: 0 = legacy mma.sync, 1 = tcgen05 where supported");

@@ -114,8 +114,9 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
   const int c = static_cast<int>(idx % F8);
   const int64_t m = idx / F8;
   const int64_t F = static_cast<int64_t>(F8) * 8;
-  const uint4 g = *reinterpret_cast<const uint4*>(gu + m * 2 * F + c * 8);
-  const uint4 u = *reinterpret_cast<const uint4*>(gu + m * 2 * F + F + c * 8);
+  const int64_t gcol = static_cast<int64_t>(c / 8) * 128 + (c % 8) * 8;   // interleaved [gate 64 | up 64] groups
+  const uint4 g = *reinterpret_cast<const uint4*>(gu + m * 2 * F + gcol);
+  const uint4 u = *reinterpret_cast<const uint4*>(gu + m * 2 * F + gcol + 64);
   const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, uw[4] = {u.x, u.y, u.z, u.w};
   uint32_t o[4];
 #pragma unroll
@@ -133,9 +134,10 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __r
   const int c = static_cast<int>(idx % F8);
   const int64_t m = idx / F8;
   const int64_t F = static_cast<int64_t>(F8) * 8;
+  const int64_t gcol = static_cast<int64_t>(c / 8) * 128 + (c % 8) * 8;   // interleaved [gate 64 | up 64] groups
   const uint4 d = *reinterpret_cast<const uint4*>(dact + m * F + c * 8);
-  const uint4 g = *reinterpret_cast<const uint4*>(gu + m * 2 * F + c * 8);
-  const uint4 u = *reinterpret_cast<const uint4*>(gu + m * 2 * F + F + c * 8);
+  const uint4 g = *reinterpret_cast<const uint4*>(gu + m * 2 * F + gcol);
+  const uint4 u = *reinterpret_cast<const uint4*>(gu + m * 2 * F + gcol + 64);
   const uint32_t dw[4] = {d.x, d.y, d.z, d.w}, gw[4] = {g.x, g.y, g.z, g.w}, uw[4] = {u.x, u.y, u.z, u.w};
   uint32_t og[4], ou[4];
 #pragma unroll
@@ -154,8 +156,8 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __r
     og[t] = pack_bf16x2(r[0][0], r[0][1]);
     ou[t] = pack_bf16x2(r[1][0], r[1][1]);
   }
-  *reinterpret_cast<uint4*>(dgu + m * 2 * F + c * 8) = make_uint4(og[0], og[1], og[2], og[3]);
-  *reinterpret_cast<uint4*>(dgu + m * 2 * F + F + c * 8) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+  *reinterpret_cast<uint4*>(dgu + m * 2 * F + gcol) = make_uint4(og[0], og[1], og[2], og[3]);
+  *reinterpret_cast<uint4*>(dgu + m * 2 * F + gcol + 64) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
 }
 
 // one thread per (row, q|k, head, 8 consecutive rotation pairs): two 16-byte loads, two 16-byte stores
@@ -285,12 +287,12 @@ int scale_cols(const bf16* x, const bf16* gamma, bf16* y, int64_t rows, int cols
   EW_DONE();
 }
 int swiglu_fwd(const bf16* gu, bf16* act, int64_t M, int F, cudaStream_t s) {
-  VLA_REQUIRE(F % 8 == 0, "swiglu: F %% 8 != 0");
+  VLA_REQUIRE(F % 64 == 0, "swiglu: F must be a multiple of 64 (interleaved gate|up groups)");
   swiglu_fwd_kernel<<<blocks_for(M * (F / 8)), EW_THREADS, 0, s>>>(gu, act, M, F / 8);
   EW_DONE();
 }
 int swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int64_t M, int F, cudaStream_t s) {
-  VLA_REQUIRE(F % 8 == 0, "swiglu: F %% 8 != 0");
+  VLA_REQUIRE(F % 64 == 0, "swiglu: F must be a multiple of 64 (interleaved gate|up groups)");
   swiglu_bwd_kernel<<<blocks_for(M * (F / 8)), EW_THREADS, 0, s>>>(dact, gu, dgu, M, F / 8);
   EW_DONE();
 }

@@ -438,8 +438,16 @@ int vit_backward(vla_engine* e, int t, cudaStream_t s) {
       CK(scale_cols(dx, k.ls2, e->t_c, Mv, d, s));
       g = e->t_c;
     }
-    CK(G(g, d, k.fc2_t, d, e->t_wide, v.mlp, Mv, v.mlp, d, plain, s));
-    CK(gelu_bwd(e->t_wide, a.fc1_pre[i], e->t_wide, Mv * v.mlp, s));
+    if (v.mlp % 32 == 0) {
+      GemmEpilogue ep;   // GELU backward fused into the fc2^T GEMM epilogue
+      ep.aux_mode = 1;
+      ep.aux = a.fc1_pre[i];
+      ep.ldaux = v.mlp;
+      CK(G(g, d, k.fc2_t, d, e->t_wide, v.mlp, Mv, v.mlp, d, ep, s));
+    } else {
+      CK(G(g, d, k.fc2_t, d, e->t_wide, v.mlp, Mv, v.mlp, d, plain, s));
+      CK(gelu_bwd(e->t_wide, a.fc1_pre[i], e->t_wide, Mv * v.mlp, s));
+    }
     CK(G(e->t_wide, v.mlp, k.fc1_t, v.mlp, e->t_norm, d, Mv, d, v.mlp, plain, s));
     CK(layernorm_bwd(e->t_norm, a.x_mid[i], k.n2w, a.mean2[i], a.rstd2[i], dx, dxm, Mv, d, s));
     g = dxm;
@@ -448,7 +456,8 @@ int vit_backward(vla_engine* e, int t, cudaStream_t s) {
       g = e->t_c;
     }
     CK(G(g, d, k.proj_t, d, e->t_d, d, Mv, d, d, plain, s));
-    CK(attention_bwd(a.qkv[i], a.attn_o[i], e->t_d, a.lse[i], e->delta, e->t_qkv, nullptr, B, v.ntok, v.heads, v.hd, 0, s));
+    CK(attention_bwd(a.qkv[i], a.attn_o[i], e->t_d, a.lse[i], e->delta, e->t_qkv, nullptr, B, v.ntok, v.heads, v.hd, 0, nullptr,
+                     nullptr, 0, s));
     CK(G(e->t_qkv, 3 * d, k.qkv_t, 3 * d, e->t_norm, d, Mv, d, 3 * d, plain, s));
     CK(layernorm_bwd(e->t_norm, a.x[i], k.n1w, a.mean1[i], a.rstd1[i], dxm, dx, Mv, d, s));
   }
@@ -554,12 +563,23 @@ extern "C" int vla_engine_load_weight(vla_engine* e, const char* name_c, const v
       VLA_REQUIRE(sp && st, "unknown weight '%s'", name_c);
       VLA_REQUIRE(numel == static_cast<int64_t>(pk.rows) * h, "weight '%s': expected %lld elements, got %lld", name_c,
                   static_cast<long long>(pk.rows) * h, static_cast<long long>(numel));
-      bf16* dst = e->warena + sp->off + static_cast<size_t>(pk.index) * pk.rows * h;
-      VLA_CHECK_CUDA(cudaMemcpyAsync(dst, src, numel * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
-      // transposed: [h, total_rows], this block occupies columns [index*rows, (index+1)*rows)
-      CK(transpose_bf16(src, h, e->warena + st->off + static_cast<size_t>(pk.index) * pk.rows, st->cols, pk.rows, h, s));
+      const bool gate_up = pk.rows == f && strstr(pk.suffix, "mlp.") != nullptr;
+      if (!gate_up) {
+        // q | k | v stacked row-wise: block `index` occupies rows [index*rows, (index+1)*rows)
+        bf16* dst = e->warena + sp->off + static_cast<size_t>(pk.index) * pk.rows * h;
+        VLA_CHECK_CUDA(cudaMemcpyAsync(dst, src, numel * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+      } else {
+        // gate / up interleaved in groups of 64 output features: packed rows [128k, 128k+64) = gate rows [64k, 64k+64),
+        // [128k+64, 128k+128) = up rows -- so that one epilogue thread of the gate|up GEMM holds gate_i and up_i
+        VLA_REQUIRE(f % 64 == 0, "llm_ffn must be a multiple of 64 (got %d)", f);
+        bf16* dst = e->warena + sp->off + static_cast<size_t>(pk.index) * 64 * h;
+        VLA_CHECK_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(128) * h * sizeof(bf16), src, static_cast<size_t>(64) * h * sizeof(bf16),
+                                         static_cast<size_t>(64) * h * sizeof(bf16), f / 64, cudaMemcpyDeviceToDevice, s));
+      }
       sp->loaded++;
       st->loaded = sp->loaded;
+      if (sp->loaded == sp->needed)   // all parts in: one transpose of the packed matrix [rows, h] -> [h, rows]
+        CK(transpose_bf16(e->warena + sp->off, sp->cols, e->warena + st->off, st->cols, sp->rows, sp->cols, s));
       return 0;
     }
   }
@@ -729,8 +749,18 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
   for (int l = 0; l < c.llm_layers; ++l) {
     const LlamaLayerW& w = e->lw[l];
     CK(rmsnorm_fwd(la.x[l], w.n1, e->t_norm, la.rstd1[l], ML, h, c.rms_eps, s));
-    CK(G(e->t_norm, h, w.qkv, h, la.qkv[l], 3 * h, ML, 3 * h, h, plain, s));
-    CK(rope_inplace(la.qkv[l], e->rope_cos, e->rope_sin, ML, L, NH, hd, +1, s));
+    if (hd == 128) {   // RoPE fused into the q|k|v GEMM epilogue (pairs (c, c+64) of a head sit in one epilogue thread)
+      GemmEpilogue ep;
+      ep.pair_mode = 1;
+      ep.rope_cos = e->rope_cos;
+      ep.rope_sin = e->rope_sin;
+      ep.rope_L = L;
+      ep.rope_cols = 2 * h;
+      CK(G(e->t_norm, h, w.qkv, h, la.qkv[l], 3 * h, ML, 3 * h, h, ep, s));
+    } else {
+      CK(G(e->t_norm, h, w.qkv, h, la.qkv[l], 3 * h, ML, 3 * h, h, plain, s));
+      CK(rope_inplace(la.qkv[l], e->rope_cos, e->rope_sin, ML, L, NH, hd, +1, s));
+    }
     CK(attention_fwd(la.qkv[l], la.attn_o[l], la.lse[l], e->kv_len, B, L, NH, hd, 1, s));
     {
       GemmEpilogue ep;
@@ -739,8 +769,13 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
       CK(G(la.attn_o[l], h, w.o, h, la.x_mid[l], h, ML, h, h, ep, s));
     }
     CK(rmsnorm_fwd(la.x_mid[l], w.n2, e->t_norm, la.rstd2[l], ML, h, c.rms_eps, s));
-    CK(G(e->t_norm, h, w.gu, h, la.gu[l], 2 * f, ML, 2 * f, h, plain, s));
-    CK(swiglu_fwd(la.gu[l], e->t_wide, ML, f, s));
+    {   // gate|up GEMM with the SwiGLU fused: raw gate|up saved for the backward, act = silu(gate)*up feeds down_proj
+      GemmEpilogue ep;
+      ep.pair_mode = 2;
+      ep.act_out = e->t_wide;
+      ep.ld_act = f;
+      CK(G(e->t_norm, h, w.gu, h, la.gu[l], 2 * f, ML, 2 * f, h, ep, s));
+    }
     {
       GemmEpilogue ep;
       ep.resid = la.x_mid[l];
@@ -768,22 +803,41 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
   CK(scatter_rows(e->hn, e->sup_rows, dx, R, h, s));
   for (int l = c.llm_layers - 1; l >= 0; --l) {
     const LlamaLayerW& w = e->lw[l];
-    CK(G(dx, h, w.down_t, h, e->t_wide, f, ML, f, h, plain, s));
-    CK(swiglu_bwd(e->t_wide, la.gu[l], e->t_wide2, ML, f, s));
+    {   // d(act) = dX . W_down, with the SwiGLU backward fused: writes d(gate|up) directly
+      GemmEpilogue ep;
+      ep.aux_mode = 2;
+      ep.aux = la.gu[l];
+      ep.ldaux = 2 * f;
+      CK(G(dx, h, w.down_t, h, e->t_wide2, 2 * f, ML, f, h, ep, s));
+    }
     CK(G(e->t_wide2, 2 * f, w.gu_t, 2 * f, e->t_norm, h, ML, h, 2 * f, plain, s));
     CK(rmsnorm_bwd(e->t_norm, la.x_mid[l], w.n2, la.rstd2[l], dx, dxm, ML, h, s));
     CK(G(dxm, h, w.o_t, h, e->t_d, h, ML, h, h, plain, s));
-    CK(attention_bwd(la.qkv[l], la.attn_o[l], e->t_d, la.lse[l], e->delta, e->t_qkv, e->kv_len, B, L, NH, hd, 1, s));
-    CK(rope_inplace(e->t_qkv, e->rope_cos, e->rope_sin, ML, L, NH, hd, -1, s));
+    if (hd == 128) {   // RoPE backward fused into the attention backward's epilogues
+      CK(attention_bwd(la.qkv[l], la.attn_o[l], e->t_d, la.lse[l], e->delta, e->t_qkv, e->kv_len, B, L, NH, hd, 1, e->rope_cos,
+                       e->rope_sin, L, s));
+    } else {
+      CK(attention_bwd(la.qkv[l], la.attn_o[l], e->t_d, la.lse[l], e->delta, e->t_qkv, e->kv_len, B, L, NH, hd, 1, nullptr, nullptr,
+                       0, s));
+      CK(rope_inplace(e->t_qkv, e->rope_cos, e->rope_sin, ML, L, NH, hd, -1, s));
+    }
     CK(G(e->t_qkv, 3 * h, w.qkv_t, 3 * h, e->t_norm, h, ML, h, 3 * h, plain, s));
     CK(rmsnorm_bwd(e->t_norm, la.x[l], w.n1, la.rstd1[l], dxm, dx, ML, h, s));
   }
   // d X0 rows 1..P -> projector backward
   CK(copy_rows(dx, h, L, 1, e->t_c, h, P, 0, B, P, h, s));
-  CK(G(e->t_c, h, e->pj_t[2], h, e->t_d, h, MP, h, h, plain, s));
-  CK(gelu_bwd(e->t_d, e->p2_pre, e->t_d, MP * h, s));
-  CK(G(e->t_d, h, e->pj_t[1], h, e->t_wide, phd, MP, phd, h, plain, s));
-  CK(gelu_bwd(e->t_wide, e->p1_pre, e->t_wide, MP * phd, s));
+  {
+    GemmEpilogue ep;   // GELU backward fused into the GEMM that produces d(post-activation)
+    ep.aux_mode = 1;
+    ep.aux = e->p2_pre;
+    ep.ldaux = h;
+    CK(G(e->t_c, h, e->pj_t[2], h, e->t_d, h, MP, h, h, ep, s));
+    GemmEpilogue ep2;
+    ep2.aux_mode = 1;
+    ep2.aux = e->p1_pre;
+    ep2.ldaux = phd;
+    CK(G(e->t_d, h, e->pj_t[1], h, e->t_wide, phd, MP, phd, h, ep2, s));
+  }
   CK(G(e->t_wide, phd, e->pj_t[0], phd, e->feats, vd, MP, vd, phd, plain, s));
   col_off = 0;
   for (int t = 0; t < 2; ++t) {

@@ -25,6 +25,25 @@ struct GemmEpilogue {
   int out_group = 0, out_stride = 0, out_offset = 0;
   // resid row = r % resid_mod when > 0 (position embedding broadcast over the batch), else the output row
   int resid_mod = 0;
+
+  // ---- fused elementwise neighbours (each replaces a separate HBM-bound kernel) ----
+  // aux_mode 1 (GELU backward): out = bf16( bf16(acc) * gelu'(aux[m, n]) ), aux = saved pre-activation (ld = ldaux)
+  // aux_mode 2 (SwiGLU backward): the GEMM computes d(act) [M, N]; aux = saved gate|up pre-activations in the interleaved
+  //   layout below ([M, 2N]); `out` receives d(gate|up) in the same layout (ldc = 2N); d(act) itself is not stored.
+  int aux_mode = 0;
+  const bf16* aux = nullptr;
+  int64_t ldaux = 0;
+  // pair_mode works on column pairs (n, n + 64) inside each 128-column group (one epilogue warp owns both):
+  // pair_mode 1 (RoPE, HF rotate_half convention, head dim 128): columns < rope_cols are rotated with the cos / sin
+  //   tables [rope_L, 64] at position row % rope_L; the rest (v) is stored as is.
+  // pair_mode 2 (SwiGLU forward): columns are [gate 64 | up 64] per group (weights packed that way): `out` gets the raw
+  //   gate|up (saved for the backward) and act_out [M, N/2] gets bf16(bf16(silu(gate)) * up).
+  int pair_mode = 0;
+  const float* rope_cos = nullptr;
+  const float* rope_sin = nullptr;
+  int rope_L = 0, rope_cols = 0;
+  bf16* act_out = nullptr;
+  int64_t ld_act = 0;
 };
 
 // Returns 0 on success. No allocation, no synchronisation; launches on `stream`.

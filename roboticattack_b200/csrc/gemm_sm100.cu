@@ -113,6 +113,56 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
   const int row = e.out_group ? (row_in / e.out_group) * e.out_stride + e.out_offset + row_in % e.out_group : row_in;
   const int rrow = e.resid_mod ? row_in % e.resid_mod : row;
   const bool full = (col0 + 32 <= g.N);
+  if (e.aux_mode == 1) {   // GELU backward: dpre = bf16(dy) * gelu'(pre)
+    const uint4* ap = reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + col0);
+    uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 u = ap[q];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 pre = unpack_bf16x2(w[t]);
+        const float d0 = rbf(__uint_as_float(acc[q * 8 + t * 2])), d1 = rbf(__uint_as_float(acc[q * 8 + t * 2 + 1]));
+        o[t] = pack_bf16x2(d0 * gelu_erf_grad(pre.x), d1 * gelu_erf_grad(pre.y));
+      }
+      op[q] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    return;
+  }
+  if (e.aux_mode == 2) {   // SwiGLU backward on the interleaved [gate 64 | up 64] layout
+    const int64_t gcol = static_cast<int64_t>(col0 / 64) * 128 + (col0 % 64);
+    const bf16* gp = e.aux + static_cast<int64_t>(row) * e.ldaux + gcol;
+    bf16* dgp = static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + gcol;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 gu4 = *reinterpret_cast<const uint4*>(gp + q * 8);
+      const uint4 uu4 = *reinterpret_cast<const uint4*>(gp + 64 + q * 8);
+      const uint32_t gw[4] = {gu4.x, gu4.y, gu4.z, gu4.w}, uw[4] = {uu4.x, uu4.y, uu4.z, uu4.w};
+      uint32_t og[4], ou[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 gg = unpack_bf16x2(gw[t]), uu = unpack_bf16x2(uw[t]);
+        const float gv[2] = {gg.x, gg.y}, uv[2] = {uu.x, uu.y};
+        float rg[2], ru[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float dv = rbf(__uint_as_float(acc[q * 8 + t * 2 + k]));   // d(act) as the bf16 tensor autograd would hold
+          const float sig = 1.f / (1.f + expf(-gv[k]));
+          const float s_b = rbf(gv[k] * sig);
+          const float ds = rbf(dv * uv[k]);
+          rg[k] = ds * sig * (1.f + gv[k] * (1.f - sig));
+          ru[k] = dv * s_b;
+        }
+        og[t] = pack_bf16x2(rg[0], rg[1]);
+        ou[t] = pack_bf16x2(ru[0], ru[1]);
+      }
+      *reinterpret_cast<uint4*>(dgp + q * 8) = make_uint4(og[0], og[1], og[2], og[3]);
+      *reinterpret_cast<uint4*>(dgp + 64 + q * 8) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+    }
+    return;
+  }
   if (full && !e.bias && !e.gamma && !e.resid && !e.act && !e.out_f32) {
     // plain GEMM (every input-gradient GEMM, q|k|v, gate|up): one packed cvt per pair, four 16-byte stores
     uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0);
@@ -213,6 +263,53 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
       else
         static_cast<bf16*>(g.out)[static_cast<int64_t>(row) * g.ldc + n] = f2b(v);
     }
+  }
+}
+
+// Two 32-column chunks (columns col_a.. and col_a + 64..) of one row: RoPE rotation or SwiGLU.
+__device__ __forceinline__ void epilogue_store_pair(const GemmArgs& g, const uint32_t (&va)[32], const uint32_t (&vb)[32],
+                                                    int row, int col_a) {
+  const GemmEpilogue& e = g.epi;
+  bf16* oa = static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col_a;
+  bf16* ob = oa + 64;
+  float xa[32], xb[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    xa[j] = rbf(__uint_as_float(va[j]));   // the Linear output as a bf16 tensor
+    xb[j] = rbf(__uint_as_float(vb[j]));
+  }
+  if (e.pair_mode == 1 && col_a < e.rope_cols) {
+    const int pos = row % e.rope_L;
+    const float4* cp = reinterpret_cast<const float4*>(e.rope_cos + pos * 64 + (col_a & 63));
+    const float4* sp = reinterpret_cast<const float4*>(e.rope_sin + pos * 64 + (col_a & 63));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 c4 = __ldg(cp + q), s4 = __ldg(sp + q);
+      const float c[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x1 = xa[q * 4 + k], x2 = xb[q * 4 + k];
+        xa[q * 4 + k] = rbf(x1 * c[k]) + rbf(-x2 * sn[k]);   // q*cos + rotate_half(q)*sin
+        xb[q * 4 + k] = rbf(x2 * c[k]) + rbf(x1 * sn[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    reinterpret_cast<uint4*>(oa)[q] = make_uint4(pack_bf16x2(xa[q * 8], xa[q * 8 + 1]), pack_bf16x2(xa[q * 8 + 2], xa[q * 8 + 3]),
+                                                 pack_bf16x2(xa[q * 8 + 4], xa[q * 8 + 5]), pack_bf16x2(xa[q * 8 + 6], xa[q * 8 + 7]));
+    reinterpret_cast<uint4*>(ob)[q] = make_uint4(pack_bf16x2(xb[q * 8], xb[q * 8 + 1]), pack_bf16x2(xb[q * 8 + 2], xb[q * 8 + 3]),
+                                                 pack_bf16x2(xb[q * 8 + 4], xb[q * 8 + 5]), pack_bf16x2(xb[q * 8 + 6], xb[q * 8 + 7]));
+  }
+  if (e.pair_mode == 2) {   // act = bf16(bf16(silu(gate)) * up), feature index = (group * 64) + offset inside the gate half
+    bf16* ap = e.act_out + static_cast<int64_t>(row) * e.ld_act + (col_a / 128) * 64 + (col_a & 63);
+    float y[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = rbf(xa[j] / (1.f + expf(-xa[j]))) * xb[j];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      reinterpret_cast<uint4*>(ap)[q] = make_uint4(pack_bf16x2(y[q * 8], y[q * 8 + 1]), pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]),
+                                                   pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]), pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]));
   }
 }
 
@@ -346,14 +443,29 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tc_fence_after();
       const int row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+      if (g.epi.pair_mode) {
+        // chunks (4p + half) and (4p + half + 2) of every 128-column group: columns n and n + 64 in the same thread
 #pragma unroll 1
-      for (int c = half; c < BLOCK_N / 32; c += 2) {
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (col0 >= g.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
-        tmem_ld_wait();
-        if (row < g.M) epilogue_store_chunk(g, v, row, col0);
+        for (int p = 0; p < BLOCK_N / 128; ++p) {
+          const int ca = 4 * p + half;
+          const int col_a = n_blk * BLOCK_N + ca * 32;
+          if (col_a >= g.N) break;  // warp-uniform (N is a multiple of 128 in pair mode)
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(ca * 32), va);
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(ca * 32 + 64), vb);
+          tmem_ld_wait();
+          if (row < g.M) epilogue_store_pair(g, va, vb, row, col_a);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = half; c < BLOCK_N / 32; c += 2) {
+          const int col0 = n_blk * BLOCK_N + c * 32;
+          if (col0 >= g.N) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_wait();
+          if (row < g.M) epilogue_store_chunk(g, v, row, col0);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -486,6 +598,10 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
                   (reinterpret_cast<uintptr_t>(out) & 15) == 0,
               "gemm: operands must be 16-byte aligned");
   VLA_REQUIRE(!epi.resid || epi.ldr % 8 == 0, "gemm: residual ld must be a multiple of 8");
+  VLA_REQUIRE(!epi.pair_mode || N % 128 == 0, "gemm: pair-mode epilogues need N %% 128 == 0 (got %d)", N);
+  VLA_REQUIRE(!epi.aux_mode || (N % 32 == 0 && epi.aux && epi.ldaux % 8 == 0), "gemm: aux-mode epilogues need N %% 32 == 0 and an aux tensor");
+  VLA_REQUIRE(epi.pair_mode != 1 || (epi.rope_cos && epi.rope_sin && epi.rope_L > 0 && epi.rope_cols % 128 == 0), "gemm: bad RoPE epilogue");
+  VLA_REQUIRE(epi.pair_mode != 2 || (epi.act_out && epi.ld_act % 8 == 0), "gemm: bad SwiGLU epilogue");
   if (g_num_sms == 0) {
     int dev = 0;
     VLA_CHECK_CUDA(cudaGetDevice(&dev));

@@ -30,7 +30,9 @@ int embed_tokens_splice(const int64_t* ids, int ld_ids, const bf16* table, bf16*
                         cudaStream_t s);
 int gelu_bwd(const bf16* dy, const bf16* pre, bf16* dx, int64_t n, cudaStream_t s);
 int scale_cols(const bf16* x, const bf16* gamma, bf16* y, int64_t rows, int cols, cudaStream_t s);
-// gu [M, 2F] = [gate | up] -> act [M, F] = bf16(bf16(silu(gate)) * up)
+// gu [M, 2F] holds gate and up interleaved in groups of 64 features: columns [128k, 128k+64) = gate features
+// [64k, 64k+64), columns [128k+64, 128k+128) = up features (the layout the packed gate|up GEMM emits; F % 64 == 0).
+// act [M, F] = bf16(bf16(silu(gate)) * up)
 int swiglu_fwd(const bf16* gu, bf16* act, int64_t M, int F, cudaStream_t s);
 int swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int64_t M, int F, cudaStream_t s);
 // rotary embedding applied in place to the q and k thirds of qkv [M, 3*H*hd]; pos = row % L. dir=+1 fwd, -1 bwd
@@ -65,8 +67,11 @@ int attention_fwd_tc(const bf16* qkv, bf16* o, float* lse, const int* kv_len, in
                      float scale, cudaStream_t s);
 extern int g_attn_impl;   // 0 = legacy mma.sync kernels only, 1 = tcgen05 where supported (default)
 // dqkv [B*N, 3*H*hd]; delta scratch [B, H, N] fp32
+// rope_cos / rope_sin (nullable; head dim 128 only): when given, d(q) and d(k) are returned with the rotary embedding's
+// backward already applied (gradients wrt the PRE-RoPE projections), i.e. rope_inplace(dqkv, ..., dir = -1) is fused.
 int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
-                  const int* kv_len, int B, int N, int H, int hd, int causal, cudaStream_t s);
+                  const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
+                  int rope_L, cudaStream_t s);
 
 // ---- loss head (loss_head.cu) ----------------------------------------------------------------------------
 enum { LOSS_UADA = 0, LOSS_UADA_DDP = 1, LOSS_UPA = 2, LOSS_CE = 3, LOSS_NEG_CE = 4 };

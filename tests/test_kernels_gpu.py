@@ -240,18 +240,23 @@ def test_rope_swiglu_gelu():
     _lib.check(L.vla_rope_inplace(_lib.ptr(x), _lib.ptr(cos_d), _lib.ptr(sin_d), B * Ls, Ls, H, hd, 1, _lib.cur_stream()))
     assert torch.equal(x.view(B, Ls, 3, H, hd)[:, :, 2], qkv.view(B, Ls, 3, H, hd)[:, :, 2]), "v must be untouched"
     close(x, ref.reshape(B * Ls, -1), 1.01, "rope")
-    M, F = 70, 688
-    gu = torch.randn(M, 2 * F, device="cuda", generator=g).bfloat16()
+    M, F = 70, 704
+    gate = torch.randn(M, F, device="cuda", generator=g).bfloat16()
+    up = torch.randn(M, F, device="cuda", generator=g).bfloat16()
+    # kernel layout: gate / up interleaved in groups of 64 features ([g 64 | u 64] per 128 columns)
+    gu = torch.stack([gate.view(M, F // 64, 64), up.view(M, F // 64, 64)], dim=2).reshape(M, 2 * F).contiguous()
     dact = torch.randn(M, F, device="cuda", generator=g).bfloat16()
     act = torch.empty(M, F, device="cuda", dtype=torch.bfloat16)
     _lib.check(L.vla_swiglu_fwd(_lib.ptr(gu), _lib.ptr(act), M, F, _lib.cur_stream()))
-    gr = gu.clone().requires_grad_(True)
-    refa = torch.nn.functional.silu(gr[:, :F]) * gr[:, F:]
+    gr, ur = gate.clone().requires_grad_(True), up.clone().requires_grad_(True)
+    refa = torch.nn.functional.silu(gr) * ur
     close(act, refa.detach(), 1.01, "swiglu fwd")
     refa.backward(dact)
     dgu = torch.empty_like(gu)
     _lib.check(L.vla_swiglu_bwd(_lib.ptr(dact), _lib.ptr(gu), _lib.ptr(dgu), M, F, _lib.cur_stream()))
-    close(dgu, gr.grad, 1.5, "swiglu bwd")
+    dgu_v = dgu.view(M, F // 64, 2, 64)
+    close(dgu_v[:, :, 0].reshape(M, F), gr.grad, 1.5, "swiglu bwd dgate")
+    close(dgu_v[:, :, 1].reshape(M, F), ur.grad, 1.5, "swiglu bwd dup")
     pre = torch.randn(M, F, device="cuda", generator=g).bfloat16()
     pr = pre.clone().requires_grad_(True)
     torch.nn.functional.gelu(pr).backward(dact)
