@@ -1,0 +1,103 @@
+"""Size-independent properties at the BASELINE.json sizes (OpenVLA-7B shapes, per-GPU bs = 8, patch 3x50x50, T = 33):
+the oracle cannot run here in seconds, so the full-size engine is checked through properties the path must have.
+
+  * sharding: for the DDP loss (mean over tokens, equal token count per sample) the gradient of the batch of 8 equals the
+    mean of the gradients of its two halves of 4 -- exactly what the multi-GPU path relies on (UADA_ddp.py:157-166,206);
+  * sample-permutation invariance of loss and gradient;
+  * run-to-run reproducibility (the only non-deterministic reduction is the fp32 atomics of the front-end backward);
+  * forward-only (validation) pass returns the same scalars as the training pass.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from roboticattack_b200 import _lib, labels as lab  # noqa: E402
+from roboticattack_b200.config import openvla_7b  # noqa: E402
+from roboticattack_b200.engine import LossSpec, VLAEngine  # noqa: E402
+from roboticattack_b200.synthetic import draw_placements, synthetic_batch  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def full():
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~45 GB of device memory")
+    cfg = openvla_7b()
+    eng = VLAEngine(cfg, 8, 33)
+    eng.load_random_weights(seed=0, init="reference")
+    batch = synthetic_batch(cfg, 8, 33, seed=1234, ragged=True)
+    batch["labels"] = lab.mask_labels_uada(batch["labels"].clone(), [0, 1, 2])
+    random.seed(42)
+    np.random.seed(42)
+    xy, theta = draw_placements(8, (224, 224), (50, 50), True, steps=1)
+    torch.manual_seed(42)
+    patch = torch.rand(3, 50, 50).cuda()
+    return cfg, eng, batch, xy, theta, patch
+
+
+def run(eng, batch, xy, theta, patch, idx, loss, forward_only=False):
+    sub = {k: v[idx] for k, v in batch.items()}
+    eng.ensure_plan(len(idx), batch["input_ids"].shape[1])
+    eng.set_batch(sub["obs"], sub["input_ids"], sub["attention_mask"], sub["labels"])
+    eng.set_placements(xy[:, idx], theta[:, idx])
+    g = torch.zeros_like(patch)
+    sc = torch.zeros(_lib.NUM_SCALARS, device="cuda")
+    pred = torch.zeros(eng.num_supervised, dtype=torch.int32, device="cuda")
+    eng.fwd_bwd(patch, 0, _lib.FE_WARP, loss, g, sc, pred, forward_only=forward_only)
+    torch.cuda.synchronize()
+    return sc.cpu(), g.cpu(), pred.cpu()
+
+
+def rel(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def test_fullsize_properties(full):
+    cfg, eng, batch, xy, theta, patch = full
+    ddp = LossSpec(_lib.LOSS_UADA_DDP, mse_weight=5.0)
+    all8 = list(range(8))
+    sc8, g8, pred8 = run(eng, batch, xy, theta, patch, all8, ddp)
+    assert torch.isfinite(g8).all() and g8.abs().max() > 0 and np.isfinite(sc8[_lib.S_LOSS].item())
+    assert sc8[_lib.S_NTOK].item() == 8 * 4 and sc8[_lib.S_NACT].item() == 8 * 3      # maskidx 0,1,2 + EOS per sample
+
+    # reproducibility
+    sc8b, g8b, pred8b = run(eng, batch, xy, theta, patch, all8, ddp)
+    assert torch.equal(pred8, pred8b) and sc8[_lib.S_LOSS].item() == sc8b[_lib.S_LOSS].item()
+    assert rel(g8b, g8) < 1e-5
+
+    # sharding: grad(8) == mean(grad(first 4), grad(last 4)); loss likewise
+    scA, gA, _ = run(eng, batch, xy, theta, patch, [0, 1, 2, 3], ddp)
+    scB, gB, _ = run(eng, batch, xy, theta, patch, [4, 5, 6, 7], ddp)
+    np.testing.assert_allclose(0.5 * (scA[_lib.S_LOSS].item() + scB[_lib.S_LOSS].item()), sc8[_lib.S_LOSS].item(), rtol=2e-3)
+    r = rel(0.5 * (gA + gB), g8)
+    print(f"sharding: rel diff of mean-of-halves vs full batch gradient = {r:.4f}")
+    assert r < 0.05          # different GEMM M -> different tile variants / accumulation order: bf16-level agreement
+
+    # permutation invariance
+    perm = [3, 7, 0, 5, 1, 6, 2, 4]
+    scP, gP, _ = run(eng, batch, xy, theta, patch, perm, ddp)
+    np.testing.assert_allclose(scP[_lib.S_LOSS].item(), sc8[_lib.S_LOSS].item(), rtol=1e-4)
+    assert rel(gP, g8) < 0.02
+
+    # validation pass == training pass scalars
+    scF, gF, predF = run(eng, batch, xy, theta, patch, all8, ddp, forward_only=True)
+    assert scF[_lib.S_LOSS].item() == sc8[_lib.S_LOSS].item() and torch.equal(predF, pred8) and gF.abs().max() == 0
+
+
+def test_fullsize_update_moves_patch_inside_unit_box(full):
+    cfg, eng, batch, xy, theta, patch = full
+    loss = LossSpec(_lib.LOSS_UADA, mse_weight=5.0)
+    p = patch.clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    sc, g, _ = run(eng, batch, xy, theta, p, list(range(8)), loss)
+    eng.patch_update(p, g.cuda(), m, v, 1, 2e-3)
+    torch.cuda.synchronize()
+    d = (p - patch).abs()
+    assert 0 < d.max().item() <= 2e-3 * 1.001 and p.min() >= 0 and p.max() <= 1
+    # first AdamW step is sign-like: |delta| ~ lr wherever the gradient is not tiny
+    big = g.abs() > 1e-3 * g.abs().max()
+    assert (d.cpu()[big] > 1.9e-3).float().mean() > 0.95
