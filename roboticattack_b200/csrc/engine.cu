@@ -51,6 +51,10 @@ struct VitActs {   // per tower
   std::vector<bf16*> qkv, attn_o, x_mid, fc1_pre;
   std::vector<float*> mean1, rstd1, mean2, rstd2, lse;
 };
+struct Transients {   // scratch reused across layers; one set per concurrently running chain
+  bf16 *norm = nullptr, *wide = nullptr, *wide2 = nullptr, *qkv = nullptr, *a = nullptr, *b = nullptr, *c = nullptr, *d = nullptr;
+  float* delta = nullptr;
+};
 struct LlmActs {
   std::vector<bf16*> x;           // x[l]: residual stream entering layer l; x[layers] = final  [ML, h]
   std::vector<bf16*> qkv, attn_o, x_mid, gu;
@@ -93,10 +97,13 @@ struct vla_engine {
   bf16 *feats = nullptr, *p1_pre = nullptr, *p2_pre = nullptr;
   LlmActs la;
   bf16 *hs = nullptr, *hn = nullptr, *dlogits = nullptr;
-  float *rstd_f = nullptr, *logits = nullptr, *row_stats = nullptr, *delta = nullptr;
-  // transients
-  bf16 *t_norm = nullptr, *t_wide = nullptr, *t_wide2 = nullptr, *t_qkv = nullptr, *t_a = nullptr, *t_b = nullptr,
-       *t_c = nullptr, *t_d = nullptr;
+  float *rstd_f = nullptr, *logits = nullptr, *row_stats = nullptr;
+  // transients: tr[0] for the main chain (LLM, projector, DINOv2 tower), tr[1] for the SigLIP tower, which runs
+  // concurrently with the DINOv2 tower on a second stream (the two towers are independent until the feature concat)
+  Transients tr[2];
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool single_stream = false;
   FrontendNorm nrm;
 };
 
@@ -348,15 +355,29 @@ size_t plan(vla_engine* e, uint8_t* base, int B, int T) {
   e->logits = bp.take<float>(static_cast<size_t>(Rmax) * V);
   e->dlogits = bp.take<bf16>(static_cast<size_t>(Rmax) * V);
   e->row_stats = bp.take<float>(loss_head_row_stats_floats(Rmax));
-  e->delta = bp.take<float>(max_lse);
-  e->t_norm = bp.take<bf16>(max_md);
-  e->t_wide = bp.take<bf16>(max_wide);
-  e->t_wide2 = bp.take<bf16>(max_wide);
-  e->t_qkv = bp.take<bf16>(max_qkv);
-  e->t_a = bp.take<bf16>(max_md);
-  e->t_b = bp.take<bf16>(max_md);
-  e->t_c = bp.take<bf16>(max_md);
-  e->t_d = bp.take<bf16>(max_md);
+  {
+    Transients& t0 = e->tr[0];
+    t0.delta = bp.take<float>(max_lse);
+    t0.norm = bp.take<bf16>(max_md);
+    t0.wide = bp.take<bf16>(max_wide);
+    t0.wide2 = bp.take<bf16>(max_wide);
+    t0.qkv = bp.take<bf16>(max_qkv);
+    t0.a = bp.take<bf16>(max_md);
+    t0.b = bp.take<bf16>(max_md);
+    t0.c = bp.take<bf16>(max_md);
+    t0.d = bp.take<bf16>(max_md);
+    const VitDims& v = e->vit[1];
+    const size_t Mv = static_cast<size_t>(B) * v.ntok;
+    Transients& t1 = e->tr[1];
+    t1.delta = bp.take<float>(static_cast<size_t>(B) * v.heads * v.ntok);
+    t1.norm = bp.take<bf16>(Mv * v.dim);
+    t1.wide = bp.take<bf16>(Mv * v.mlp);
+    t1.qkv = bp.take<bf16>(Mv * 3 * v.dim);
+    t1.a = bp.take<bf16>(Mv * v.dim);
+    t1.b = bp.take<bf16>(Mv * v.dim);
+    t1.c = bp.take<bf16>(Mv * v.dim);
+    t1.d = bp.take<bf16>(Mv * v.dim);
+  }
   return align_up(bp.off, 256);
 }
 
@@ -366,7 +387,7 @@ int G(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t
 }
 
 // ---- vision tower -----------------------------------------------------------------------------------------
-int vit_forward(vla_engine* e, int t, cudaStream_t s) {
+int vit_forward(vla_engine* e, int t, Transients& tr, cudaStream_t s) {
   const VitDims& v = e->vit[t];
   const VitW& w = e->vw[t];
   VitActs& a = e->va[t];
@@ -386,11 +407,11 @@ int vit_forward(vla_engine* e, int t, cudaStream_t s) {
   }
   for (int i = 0; i < v.used; ++i) {
     const VitBlockW& k = w.blk[i];
-    CK(layernorm_fwd(a.x[i], k.n1w, k.n1b, e->t_norm, a.mean1[i], a.rstd1[i], Mv, d, e->cfg.vit_ln_eps, s));
+    CK(layernorm_fwd(a.x[i], k.n1w, k.n1b, tr.norm, a.mean1[i], a.rstd1[i], Mv, d, e->cfg.vit_ln_eps, s));
     {
       GemmEpilogue ep;
       ep.bias = k.qkv_b;
-      CK(G(e->t_norm, d, k.qkv_w, d, a.qkv[i], 3 * d, Mv, 3 * d, d, ep, s));
+      CK(G(tr.norm, d, k.qkv_w, d, a.qkv[i], 3 * d, Mv, 3 * d, d, ep, s));
     }
     CK(attention_fwd(a.qkv[i], a.attn_o[i], a.lse[i], nullptr, B, v.ntok, v.heads, v.hd, 0, s));
     {
@@ -401,13 +422,13 @@ int vit_forward(vla_engine* e, int t, cudaStream_t s) {
       ep.ldr = d;
       CK(G(a.attn_o[i], d, k.proj_w, d, a.x_mid[i], d, Mv, d, d, ep, s));
     }
-    CK(layernorm_fwd(a.x_mid[i], k.n2w, k.n2b, e->t_norm, a.mean2[i], a.rstd2[i], Mv, d, e->cfg.vit_ln_eps, s));
+    CK(layernorm_fwd(a.x_mid[i], k.n2w, k.n2b, tr.norm, a.mean2[i], a.rstd2[i], Mv, d, e->cfg.vit_ln_eps, s));
     {
       GemmEpilogue ep;
       ep.bias = k.fc1_b;
       ep.act = 1;
       ep.preact_out = a.fc1_pre[i];
-      CK(G(e->t_norm, d, k.fc1_w, d, e->t_wide, v.mlp, Mv, v.mlp, d, ep, s));
+      CK(G(tr.norm, d, k.fc1_w, d, tr.wide, v.mlp, Mv, v.mlp, d, ep, s));
     }
     {
       GemmEpilogue ep;
@@ -415,55 +436,55 @@ int vit_forward(vla_engine* e, int t, cudaStream_t s) {
       ep.gamma = v.layerscale ? k.ls2 : nullptr;
       ep.resid = a.x_mid[i];
       ep.ldr = d;
-      CK(G(e->t_wide, v.mlp, k.fc2_w, v.mlp, a.x[i + 1], d, Mv, d, v.mlp, ep, s));
+      CK(G(tr.wide, v.mlp, k.fc2_w, v.mlp, a.x[i + 1], d, Mv, d, v.mlp, ep, s));
     }
   }
   return 0;
 }
 
-// dx_in: gradient wrt the tower output in e->t_a ([Mv, d], prefix rows zero). Leaves d(im2col rows) in a.a_col.
-int vit_backward(vla_engine* e, int t, cudaStream_t s) {
+// dx_in: gradient wrt the tower output in tr.a ([Mv, d], prefix rows zero). Leaves d(im2col rows) in a.a_col.
+int vit_backward(vla_engine* e, int t, Transients& tr, cudaStream_t s) {
   const VitDims& v = e->vit[t];
   const VitW& w = e->vw[t];
   VitActs& a = e->va[t];
   const int B = e->B, d = v.dim;
   const int64_t Mv = static_cast<int64_t>(B) * v.ntok;
-  bf16* dx = e->t_a;       // gradient wrt x[i+1]
-  bf16* dxm = e->t_b;      // gradient wrt x_mid[i]
+  bf16* dx = tr.a;       // gradient wrt x[i+1]
+  bf16* dxm = tr.b;      // gradient wrt x_mid[i]
   GemmEpilogue plain;
   for (int i = v.used - 1; i >= 0; --i) {
     const VitBlockW& k = w.blk[i];
     const bf16* g = dx;
     if (v.layerscale) {
-      CK(scale_cols(dx, k.ls2, e->t_c, Mv, d, s));
-      g = e->t_c;
+      CK(scale_cols(dx, k.ls2, tr.c, Mv, d, s));
+      g = tr.c;
     }
     if (v.mlp % 32 == 0) {
       GemmEpilogue ep;   // GELU backward fused into the fc2^T GEMM epilogue
       ep.aux_mode = 1;
       ep.aux = a.fc1_pre[i];
       ep.ldaux = v.mlp;
-      CK(G(g, d, k.fc2_t, d, e->t_wide, v.mlp, Mv, v.mlp, d, ep, s));
+      CK(G(g, d, k.fc2_t, d, tr.wide, v.mlp, Mv, v.mlp, d, ep, s));
     } else {
-      CK(G(g, d, k.fc2_t, d, e->t_wide, v.mlp, Mv, v.mlp, d, plain, s));
-      CK(gelu_bwd(e->t_wide, a.fc1_pre[i], e->t_wide, Mv * v.mlp, s));
+      CK(G(g, d, k.fc2_t, d, tr.wide, v.mlp, Mv, v.mlp, d, plain, s));
+      CK(gelu_bwd(tr.wide, a.fc1_pre[i], tr.wide, Mv * v.mlp, s));
     }
-    CK(G(e->t_wide, v.mlp, k.fc1_t, v.mlp, e->t_norm, d, Mv, d, v.mlp, plain, s));
-    CK(layernorm_bwd(e->t_norm, a.x_mid[i], k.n2w, a.mean2[i], a.rstd2[i], dx, dxm, Mv, d, s));
+    CK(G(tr.wide, v.mlp, k.fc1_t, v.mlp, tr.norm, d, Mv, d, v.mlp, plain, s));
+    CK(layernorm_bwd(tr.norm, a.x_mid[i], k.n2w, a.mean2[i], a.rstd2[i], dx, dxm, Mv, d, s));
     g = dxm;
     if (v.layerscale) {
-      CK(scale_cols(dxm, k.ls1, e->t_c, Mv, d, s));
-      g = e->t_c;
+      CK(scale_cols(dxm, k.ls1, tr.c, Mv, d, s));
+      g = tr.c;
     }
-    CK(G(g, d, k.proj_t, d, e->t_d, d, Mv, d, d, plain, s));
-    CK(attention_bwd(a.qkv[i], a.attn_o[i], e->t_d, a.lse[i], e->delta, e->t_qkv, nullptr, B, v.ntok, v.heads, v.hd, 0, nullptr,
+    CK(G(g, d, k.proj_t, d, tr.d, d, Mv, d, d, plain, s));
+    CK(attention_bwd(a.qkv[i], a.attn_o[i], tr.d, a.lse[i], tr.delta, tr.qkv, nullptr, B, v.ntok, v.heads, v.hd, 0, nullptr,
                      nullptr, 0, s));
-    CK(G(e->t_qkv, 3 * d, k.qkv_t, 3 * d, e->t_norm, d, Mv, d, 3 * d, plain, s));
-    CK(layernorm_bwd(e->t_norm, a.x[i], k.n1w, a.mean1[i], a.rstd1[i], dxm, dx, Mv, d, s));
+    CK(G(tr.qkv, 3 * d, k.qkv_t, 3 * d, tr.norm, d, Mv, d, 3 * d, plain, s));
+    CK(layernorm_bwd(tr.norm, a.x[i], k.n1w, a.mean1[i], a.rstd1[i], dxm, dx, Mv, d, s));
   }
   // patch-token rows of d x[0] -> d conv output [B*np, d] -> d im2col rows [B*np, kpad]
-  CK(copy_rows(dx, d, v.ntok, v.npre, e->t_c, d, e->np, 0, B, e->np, d, s));
-  CK(G(e->t_c, d, w.pe_t, d, a.a_col, e->kpad, static_cast<int64_t>(B) * e->np, e->kpad, d, plain, s));
+  CK(copy_rows(dx, d, v.ntok, v.npre, tr.c, d, e->np, 0, B, e->np, d, s));
+  CK(G(tr.c, d, w.pe_t, d, a.a_col, e->kpad, static_cast<int64_t>(B) * e->np, e->kpad, d, plain, s));
   return 0;
 }
 
@@ -500,7 +521,15 @@ extern "C" int vla_engine_create(const vla_config* cfg, vla_engine** out) {
   return 0;
 }
 
-extern "C" void vla_engine_destroy(vla_engine* e) { delete e; }
+extern "C" void vla_engine_destroy(vla_engine* e) {
+  if (!e) return;
+  if (e->side) {
+    cudaStreamDestroy(e->side);
+    cudaEventDestroy(e->ev_fork);
+    cudaEventDestroy(e->ev_join);
+  }
+  delete e;
+}
 
 extern "C" size_t vla_engine_weight_bytes(const vla_engine* e) { return e->weight_elems * sizeof(bf16); }
 
@@ -529,6 +558,13 @@ extern "C" int vla_engine_set_buffers(vla_engine* e, void* weight_arena, size_t 
   // CE pairs logits[:, :-1] with labels[:, 1:]), so the loss and every gradient are unchanged.
   e->L = T + e->np - 1;
   plan(e, e->ws, B, T);
+  if (!e->side) {
+    VLA_CHECK_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+    VLA_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    VLA_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    const char* ss = getenv("VLA_SINGLE_STREAM");
+    e->single_stream = ss && atoi(ss) != 0;
+  }
   e->batch_set = false;
   e->rope_set = false;
   e->n_place = 0;
@@ -719,36 +755,50 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
   // ---------------- forward ----------------
   CK(patch_frontend_fwd(e->obs, patch, xy, th, e->px, B, H, H, ph, pw, fe_mode, e->nrm, s));
   CK(im2col_patches(e->px, e->va[0].a_col, e->va[1].a_col, B, H, H, c.patch, e->kpad, s));
+  // The two towers are independent until the feature concat: DINOv2 stays on the caller's stream, SigLIP runs on the
+  // engine's side stream (fork / join with events), so the many small kernels of one tower fill the launch gaps, ramps
+  // and tails of the other.  VLA_SINGLE_STREAM=1 keeps everything on one stream.
+  const bool two_streams = e->side != nullptr && !e->single_stream;
+  cudaStream_t s1 = two_streams ? e->side : s;
+  if (two_streams) {
+    VLA_CHECK_CUDA(cudaEventRecord(e->ev_fork, s));
+    VLA_CHECK_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+  }
   int col_off = 0;
   for (int t = 0; t < 2; ++t) {
-    CK(vit_forward(e, t, s));
+    cudaStream_t st = t == 0 ? s : s1;
+    CK(vit_forward(e, t, e->tr[two_streams ? t : 0], st));
     const VitDims& v = e->vit[t];
-    CK(copy_rows(e->va[t].x[v.used], v.dim, v.ntok, v.npre, e->feats + col_off, vd, P, 0, B, P, v.dim, s));
+    CK(copy_rows(e->va[t].x[v.used], v.dim, v.ntok, v.npre, e->feats + col_off, vd, P, 0, B, P, v.dim, st));
     col_off += v.dim;
+  }
+  if (two_streams) {
+    VLA_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
+    VLA_CHECK_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
   }
   {
     GemmEpilogue ep;
     ep.bias = e->pj_b[0];
     ep.act = 1;
     ep.preact_out = e->p1_pre;
-    CK(G(e->feats, vd, e->pj_w[0], vd, e->t_wide, phd, MP, phd, vd, ep, s));
+    CK(G(e->feats, vd, e->pj_w[0], vd, e->tr[0].wide, phd, MP, phd, vd, ep, s));
     GemmEpilogue ep2;
     ep2.bias = e->pj_b[1];
     ep2.act = 1;
     ep2.preact_out = e->p2_pre;
-    CK(G(e->t_wide, phd, e->pj_w[1], phd, e->t_a, h, MP, h, phd, ep2, s));
+    CK(G(e->tr[0].wide, phd, e->pj_w[1], phd, e->tr[0].a, h, MP, h, phd, ep2, s));
     GemmEpilogue ep3;   // fc3 writes straight into rows 1..P of each sample's multimodal sequence
     ep3.bias = e->pj_b[2];
     ep3.out_group = P;
     ep3.out_stride = L;
     ep3.out_offset = 1;
-    CK(G(e->t_a, h, e->pj_w[2], h, e->la.x[0], h, MP, h, h, ep3, s));
+    CK(G(e->tr[0].a, h, e->pj_w[2], h, e->la.x[0], h, MP, h, h, ep3, s));
   }
   CK(embed_tokens_splice(e->ids, T, e->embed, e->la.x[0], B, T - 1, P, h, s));
   LlmActs& la = e->la;
   for (int l = 0; l < c.llm_layers; ++l) {
     const LlamaLayerW& w = e->lw[l];
-    CK(rmsnorm_fwd(la.x[l], w.n1, e->t_norm, la.rstd1[l], ML, h, c.rms_eps, s));
+    CK(rmsnorm_fwd(la.x[l], w.n1, e->tr[0].norm, la.rstd1[l], ML, h, c.rms_eps, s));
     if (hd == 128) {   // RoPE fused into the q|k|v GEMM epilogue (pairs (c, c+64) of a head sit in one epilogue thread)
       GemmEpilogue ep;
       ep.pair_mode = 1;
@@ -756,9 +806,9 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
       ep.rope_sin = e->rope_sin;
       ep.rope_L = L;
       ep.rope_cols = 2 * h;
-      CK(G(e->t_norm, h, w.qkv, h, la.qkv[l], 3 * h, ML, 3 * h, h, ep, s));
+      CK(G(e->tr[0].norm, h, w.qkv, h, la.qkv[l], 3 * h, ML, 3 * h, h, ep, s));
     } else {
-      CK(G(e->t_norm, h, w.qkv, h, la.qkv[l], 3 * h, ML, 3 * h, h, plain, s));
+      CK(G(e->tr[0].norm, h, w.qkv, h, la.qkv[l], 3 * h, ML, 3 * h, h, plain, s));
       CK(rope_inplace(la.qkv[l], e->rope_cos, e->rope_sin, ML, L, NH, hd, +1, s));
     }
     CK(attention_fwd(la.qkv[l], la.attn_o[l], la.lse[l], e->kv_len, B, L, NH, hd, 1, s));
@@ -768,19 +818,19 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
       ep.ldr = h;
       CK(G(la.attn_o[l], h, w.o, h, la.x_mid[l], h, ML, h, h, ep, s));
     }
-    CK(rmsnorm_fwd(la.x_mid[l], w.n2, e->t_norm, la.rstd2[l], ML, h, c.rms_eps, s));
+    CK(rmsnorm_fwd(la.x_mid[l], w.n2, e->tr[0].norm, la.rstd2[l], ML, h, c.rms_eps, s));
     {   // gate|up GEMM with the SwiGLU fused: raw gate|up saved for the backward, act = silu(gate)*up feeds down_proj
       GemmEpilogue ep;
       ep.pair_mode = 2;
-      ep.act_out = e->t_wide;
+      ep.act_out = e->tr[0].wide;
       ep.ld_act = f;
-      CK(G(e->t_norm, h, w.gu, h, la.gu[l], 2 * f, ML, 2 * f, h, ep, s));
+      CK(G(e->tr[0].norm, h, w.gu, h, la.gu[l], 2 * f, ML, 2 * f, h, ep, s));
     }
     {
       GemmEpilogue ep;
       ep.resid = la.x_mid[l];
       ep.ldr = h;
-      CK(G(e->t_wide, f, w.down, f, la.x[l + 1], h, ML, h, f, ep, s));
+      CK(G(e->tr[0].wide, f, w.down, f, la.x[l + 1], h, ML, h, f, ep, s));
     }
   }
   const int R = e->R;
@@ -795,10 +845,10 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
   if (flags & VLA_FLAG_FORWARD_ONLY) return 0;
 
   // ---------------- backward (input gradients only) ----------------
-  CK(G(e->dlogits, V, e->lm_head_t, V, e->t_norm, h, R, h, V, plain, s));
-  CK(rmsnorm_bwd(e->t_norm, e->hs, e->final_norm, e->rstd_f, nullptr, e->hn, R, h, s));
-  bf16* dx = e->t_a;
-  bf16* dxm = e->t_b;
+  CK(G(e->dlogits, V, e->lm_head_t, V, e->tr[0].norm, h, R, h, V, plain, s));
+  CK(rmsnorm_bwd(e->tr[0].norm, e->hs, e->final_norm, e->rstd_f, nullptr, e->hn, R, h, s));
+  bf16* dx = e->tr[0].a;
+  bf16* dxm = e->tr[0].b;
   VLA_CHECK_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(ML) * h * sizeof(bf16), s));
   CK(scatter_rows(e->hn, e->sup_rows, dx, R, h, s));
   for (int l = c.llm_layers - 1; l >= 0; --l) {
@@ -808,45 +858,55 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
       ep.aux_mode = 2;
       ep.aux = la.gu[l];
       ep.ldaux = 2 * f;
-      CK(G(dx, h, w.down_t, h, e->t_wide2, 2 * f, ML, f, h, ep, s));
+      CK(G(dx, h, w.down_t, h, e->tr[0].wide2, 2 * f, ML, f, h, ep, s));
     }
-    CK(G(e->t_wide2, 2 * f, w.gu_t, 2 * f, e->t_norm, h, ML, h, 2 * f, plain, s));
-    CK(rmsnorm_bwd(e->t_norm, la.x_mid[l], w.n2, la.rstd2[l], dx, dxm, ML, h, s));
-    CK(G(dxm, h, w.o_t, h, e->t_d, h, ML, h, h, plain, s));
+    CK(G(e->tr[0].wide2, 2 * f, w.gu_t, 2 * f, e->tr[0].norm, h, ML, h, 2 * f, plain, s));
+    CK(rmsnorm_bwd(e->tr[0].norm, la.x_mid[l], w.n2, la.rstd2[l], dx, dxm, ML, h, s));
+    CK(G(dxm, h, w.o_t, h, e->tr[0].d, h, ML, h, h, plain, s));
     if (hd == 128) {   // RoPE backward fused into the attention backward's epilogues
-      CK(attention_bwd(la.qkv[l], la.attn_o[l], e->t_d, la.lse[l], e->delta, e->t_qkv, e->kv_len, B, L, NH, hd, 1, e->rope_cos,
+      CK(attention_bwd(la.qkv[l], la.attn_o[l], e->tr[0].d, la.lse[l], e->tr[0].delta, e->tr[0].qkv, e->kv_len, B, L, NH, hd, 1, e->rope_cos,
                        e->rope_sin, L, s));
     } else {
-      CK(attention_bwd(la.qkv[l], la.attn_o[l], e->t_d, la.lse[l], e->delta, e->t_qkv, e->kv_len, B, L, NH, hd, 1, nullptr, nullptr,
+      CK(attention_bwd(la.qkv[l], la.attn_o[l], e->tr[0].d, la.lse[l], e->tr[0].delta, e->tr[0].qkv, e->kv_len, B, L, NH, hd, 1, nullptr, nullptr,
                        0, s));
-      CK(rope_inplace(e->t_qkv, e->rope_cos, e->rope_sin, ML, L, NH, hd, -1, s));
+      CK(rope_inplace(e->tr[0].qkv, e->rope_cos, e->rope_sin, ML, L, NH, hd, -1, s));
     }
-    CK(G(e->t_qkv, 3 * h, w.qkv_t, 3 * h, e->t_norm, h, ML, h, 3 * h, plain, s));
-    CK(rmsnorm_bwd(e->t_norm, la.x[l], w.n1, la.rstd1[l], dxm, dx, ML, h, s));
+    CK(G(e->tr[0].qkv, 3 * h, w.qkv_t, 3 * h, e->tr[0].norm, h, ML, h, 3 * h, plain, s));
+    CK(rmsnorm_bwd(e->tr[0].norm, la.x[l], w.n1, la.rstd1[l], dxm, dx, ML, h, s));
   }
   // d X0 rows 1..P -> projector backward
-  CK(copy_rows(dx, h, L, 1, e->t_c, h, P, 0, B, P, h, s));
+  CK(copy_rows(dx, h, L, 1, e->tr[0].c, h, P, 0, B, P, h, s));
   {
     GemmEpilogue ep;   // GELU backward fused into the GEMM that produces d(post-activation)
     ep.aux_mode = 1;
     ep.aux = e->p2_pre;
     ep.ldaux = h;
-    CK(G(e->t_c, h, e->pj_t[2], h, e->t_d, h, MP, h, h, ep, s));
+    CK(G(e->tr[0].c, h, e->pj_t[2], h, e->tr[0].d, h, MP, h, h, ep, s));
     GemmEpilogue ep2;
     ep2.aux_mode = 1;
     ep2.aux = e->p1_pre;
     ep2.ldaux = phd;
-    CK(G(e->t_d, h, e->pj_t[1], h, e->t_wide, phd, MP, phd, h, ep2, s));
+    CK(G(e->tr[0].d, h, e->pj_t[1], h, e->tr[0].wide, phd, MP, phd, h, ep2, s));
   }
-  CK(G(e->t_wide, phd, e->pj_t[0], phd, e->feats, vd, MP, vd, phd, plain, s));
+  CK(G(e->tr[0].wide, phd, e->pj_t[0], phd, e->feats, vd, MP, vd, phd, plain, s));
+  if (two_streams) {
+    VLA_CHECK_CUDA(cudaEventRecord(e->ev_fork, s));
+    VLA_CHECK_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+  }
   col_off = 0;
   for (int t = 0; t < 2; ++t) {
     const VitDims& v = e->vit[t];
     const int64_t Mv = static_cast<int64_t>(B) * v.ntok;
-    VLA_CHECK_CUDA(cudaMemsetAsync(e->t_a, 0, static_cast<size_t>(Mv) * v.dim * sizeof(bf16), s));
-    CK(copy_rows(e->feats + col_off, vd, P, 0, e->t_a, v.dim, v.ntok, v.npre, B, P, v.dim, s));
-    CK(vit_backward(e, t, s));
+    cudaStream_t st = t == 0 ? s : s1;
+    Transients& tr = e->tr[two_streams ? t : 0];
+    VLA_CHECK_CUDA(cudaMemsetAsync(tr.a, 0, static_cast<size_t>(Mv) * v.dim * sizeof(bf16), st));
+    CK(copy_rows(e->feats + col_off, vd, P, 0, tr.a, v.dim, v.ntok, v.npre, B, P, v.dim, st));
+    CK(vit_backward(e, t, tr, st));
     col_off += v.dim;
+  }
+  if (two_streams) {
+    VLA_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
+    VLA_CHECK_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
   }
   CK(col2im_patches(e->va[0].a_col, e->va[1].a_col, e->dpx, B, H, H, c.patch, e->kpad, s));
   CK(patch_frontend_bwd(e->dpx, patch, xy, th, dpatch, B, H, H, ph, pw, fe_mode, e->nrm, s));
@@ -873,7 +933,7 @@ extern "C" int64_t vla_engine_debug_tap(vla_engine* e, const char* what_c, void*
   else if (what == "llm_out") set(e->la.x[c.llm_layers], ML * c.llm_hidden, 2);
   else if (what == "logits") set(e->logits, static_cast<int64_t>(e->R) * c.vocab, 4);
   else if (what == "dlogits") set(e->dlogits, static_cast<int64_t>(e->R) * c.vocab, 2);
-  else if (what == "d_llm_x0") set(e->t_a, ML * c.llm_hidden, 2);
+  else if (what == "d_llm_x0") set(e->tr[0].a, ML * c.llm_hidden, 2);
   else {
     vla_set_error("unknown tap '%s'", what_c);
     return -1;

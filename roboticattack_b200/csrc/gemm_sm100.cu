@@ -29,6 +29,8 @@ struct GemmProf {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // pairs (start, stop)
   std::vector<double> flops;
+  std::vector<uint64_t> shape;   // (M << 42) | (N << 21) | K, and the kernel variant in the top bits of a parallel array
+  std::vector<int> variant;
   size_t used = 0;
 } g_prof;
 }  // namespace
@@ -37,6 +39,8 @@ extern "C" int vla_profile_gemm_begin(void) {
   g_prof.on = true;
   g_prof.used = 0;
   g_prof.flops.clear();
+  g_prof.shape.clear();
+  g_prof.variant.clear();
   return 0;
 }
 
@@ -50,6 +54,26 @@ extern "C" int vla_profile_gemm_end(double* total_ms, double* total_flops, int* 
     VLA_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
     ms += t;
     fl += g_prof.flops[i];
+  }
+  if (getenv("VLA_PROFILE_VERBOSE")) {   // per-shape table on stderr (in-step, warm, power-capped clocks)
+    struct Agg { double ms = 0, fl = 0; int n = 0, variant = 0; };
+    std::unordered_map<uint64_t, Agg> agg;
+    for (size_t i = 0; i < g_prof.flops.size(); ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]);
+      Agg& a = agg[g_prof.shape[i]];
+      a.ms += t;
+      a.fl += g_prof.flops[i];
+      a.n++;
+      a.variant = g_prof.variant[i];
+    }
+    fprintf(stderr, "%8s %8s %8s %5s %8s %10s %10s %8s\n", "M", "N", "K", "n", "variant", "total_ms", "avg_us", "TFLOP/s");
+    for (auto& kv : agg) {
+      const uint64_t k = kv.first;
+      fprintf(stderr, "%8llu %8llu %8llu %5d   (%d,%3d) %10.3f %10.1f %8.0f\n", (unsigned long long)(k >> 42),
+              (unsigned long long)((k >> 21) & 0x1FFFFF), (unsigned long long)(k & 0x1FFFFF), kv.second.n, kv.second.variant / 1000,
+              kv.second.variant % 1000, kv.second.ms, kv.second.ms * 1e3 / kv.second.n, kv.second.fl / kv.second.ms / 1e9);
+    }
   }
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;
@@ -536,6 +560,8 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g,
   if (e1) {
     VLA_CHECK_CUDA(cudaEventRecord(e1, stream));
     g_prof.flops.push_back(2.0 * g.M * g.N * g.K);
+    g_prof.shape.push_back((static_cast<uint64_t>(g.M) << 42) | (static_cast<uint64_t>(g.N) << 21) | static_cast<uint64_t>(g.K));
+    g_prof.variant.push_back(CTAS * 1000 + BLOCK_N);
   }
   ++g_vla_launch_count;
   return 0;
