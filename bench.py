@@ -314,9 +314,11 @@ def engine_arm(args):
     roof = None
     eng.set_placements(xy, theta)
     import ctypes
+    eng.set_single_stream(True)               # per-kernel event timing needs the kernels of a stream back to back
     if rank == 0:
         lib.vla_profile_gemm_begin()
     step(W)                                   # every rank runs the step (it contains the all-reduce); rank 0 times its GEMMs
+    eng.set_single_stream(False)
     if rank == 0:
         tm, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
         _lib.check(lib.vla_profile_gemm_end(ctypes.byref(tm), ctypes.byref(fl), ctypes.byref(n)), "profile end")

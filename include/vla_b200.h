@@ -152,6 +152,10 @@ int vla_engine_set_batch(vla_engine* e, const uint8_t* obs, int obs_on_device, c
 /* placements of the next nsteps inner iterations: xy i32 [nsteps,B,2], theta f32 [nsteps,B,2,3] (host) */
 int vla_engine_set_placements(vla_engine* e, const int32_t* xy_host, const float* theta_host, int nsteps, void* stream);
 int vla_engine_num_supervised(const vla_engine* e);
+/* The DINOv2 and SigLIP towers are independent until the feature concat; by default the SigLIP tower runs on an
+ * engine-owned side stream (fork / join with events on the caller's stream).  on = 1 keeps everything on the caller's
+ * stream (used for per-kernel timing). */
+int vla_engine_set_single_stream(vla_engine* e, int on);
 
 enum { VLA_FLAG_FORWARD_ONLY = 1 };   /* validation pass: loss heads + metrics, no backward */
 /* patch f32 [3,ph,pw] -> dpatch f32 [3,ph,pw], scalars f32 [VLA_NUM_SCALARS], pred_ids i32 [num_supervised] */

@@ -83,6 +83,7 @@ SIGNATURES = {
     "vla_engine_set_batch": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "vla_engine_set_placements": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vla_engine_num_supervised": (c_int, [c_void_p]),
+    "vla_engine_set_single_stream": (c_int, [c_void_p, c_int]),
     "vla_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(LossParams), c_void_p, c_void_p,
                             c_void_p, c_int, c_void_p]),
     "vla_engine_debug_tap": (c_int64, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),

@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
                                                                int H, int hd, int causal, float scale) {
   using L = SmemLayout<HDP>;
   extern __shared__ __align__(16) uint8_t smem_att[];
+  pdl_trigger();
+  pdl_wait();
   bf16* sQ = reinterpret_cast<bf16*>(smem_att);
   bf16* sKb = sQ + L::TILE;            // K stage 0, K stage 1
   bf16* sVb = sKb + 2 * L::TILE;       // V stage 0, V stage 1
@@ -309,6 +311,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
                                                                   const float* __restrict__ rope_sin, int rope_L) {
   using L = SmemLayout<HDP>;
   extern __shared__ __align__(16) uint8_t smem_att[];
+  pdl_trigger();
+  pdl_wait();
   bf16* sQ = reinterpret_cast<bf16*>(smem_att);
   bf16* sdO = sQ + L::TILE;
   bf16* sKb = sdO + L::TILE;           // K stage 0, K stage 1
@@ -430,6 +434,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
                                                                    const float* __restrict__ rope_sin, int rope_L) {
   using L = SmemLayout<HDP>;
   extern __shared__ __align__(16) uint8_t smem_att[];
+  pdl_trigger();
+  pdl_wait();
   bf16* sK = reinterpret_cast<bf16*>(smem_att);
   bf16* sV = sK + L::TILE;
   bf16* sQb = sV + L::TILE;            // Q stage 0, Q stage 1
@@ -551,8 +557,8 @@ int launch_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, i
     configured = true;
   }
   dim3 grid(ceil_div(N, BM), H, B);
-  attn_fwd_kernel<HDP><<<grid, ATT_THREADS, smem, s>>>(qkv, o, lse, kv_len, N, H, hd, causal, 1.f / sqrtf(static_cast<float>(hd)));
-  VLA_LAUNCH_CHECK();
+  VLA_CHECK_CUDA(vla_launch(attn_fwd_kernel<HDP>, grid, dim3(ATT_THREADS), smem, s, qkv, o, lse, kv_len, N, H, hd, causal,
+                            1.f / sqrtf(static_cast<float>(hd))));
   ++g_vla_launch_count;
   return 0;
 }
@@ -571,12 +577,10 @@ int launch_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* ls
   }
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
   dim3 grid(ceil_div(N, BM), H, B);
-  attn_bwd_dq_kernel<HDP><<<grid, ATT_THREADS, smem_dq, s>>>(qkv, o, dout, lse, delta, dqkv, kv_len, N, H, hd, causal, scale,
-                                                             rope_cos, rope_sin, rope_L);
-  VLA_LAUNCH_CHECK();
-  attn_bwd_dkv_kernel<HDP><<<grid, ATT_THREADS, smem_dkv, s>>>(qkv, dout, lse, delta, dqkv, kv_len, N, H, hd, causal, scale,
-                                                               rope_cos, rope_sin, rope_L);
-  VLA_LAUNCH_CHECK();
+  VLA_CHECK_CUDA(vla_launch(attn_bwd_dq_kernel<HDP>, grid, dim3(ATT_THREADS), smem_dq, s, qkv, o, dout, lse, delta, dqkv, kv_len, N, H,
+                            hd, causal, scale, rope_cos, rope_sin, rope_L));
+  VLA_CHECK_CUDA(vla_launch(attn_bwd_dkv_kernel<HDP>, grid, dim3(ATT_THREADS), smem_dkv, s, qkv, dout, lse,
+                            static_cast<const float*>(delta), dqkv, kv_len, N, H, hd, causal, scale, rope_cos, rope_sin, rope_L));
   g_vla_launch_count += 2;
   return 0;
 }

@@ -1,11 +1,18 @@
 // Error state + the building-block entry points of include/vla_b200.h (thin casts onto kernels.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/vla_b200.h"
 #include "kernels.h"
 
 static thread_local char g_err[1024] = "";
+
+static int init_pdl() {
+  const char* s = getenv("VLA_PDL");
+  return (s && atoi(s) == 0) ? 0 : 1;
+}
+int g_vla_pdl = init_pdl();
 
 void vla_set_error(const char* fmt, ...) {
   va_list ap;

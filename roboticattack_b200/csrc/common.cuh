@@ -34,6 +34,33 @@ void vla_set_error(const char* fmt, ...);
 
 #define VLA_LAUNCH_CHECK() VLA_CHECK_CUDA(cudaGetLastError())
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): kernels launched through vla_launch() may start while the previous kernel of
+// the stream is still draining; they run their prologue (smem carve-up, barrier init, TMEM alloc, descriptor
+// prefetch) and then block in pdl_wait() until the predecessor has completed and its writes are visible.  Every such
+// kernel calls pdl_trigger() first, which lets ITS successor be scheduled once all of its CTAs have started.
+// ---------------------------------------------------------------------------------------------
+extern int g_vla_pdl;   // 1 (default) = launch with programmatic stream serialization; VLA_PDL=0 disables
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t vla_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_vla_pdl;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

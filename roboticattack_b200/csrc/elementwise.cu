@@ -55,6 +55,8 @@ __global__ void prefix_tokens_kernel(const bf16* __restrict__ cls, const bf16* _
 __global__ void copy_rows_kernel(const bf16* __restrict__ src, int64_t lds, int rows_src, int src_off,
                                  bf16* __restrict__ dst, int64_t ldd, int rows_dst, int dst_off, int B, int rows,
                                  int cols8) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<int64_t>(B) * rows * cols8) return;
   const int c = static_cast<int>(idx % cols8), r = static_cast<int>((idx / cols8) % rows);
@@ -77,6 +79,8 @@ __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, int ld_ids,
 }
 
 __global__ void gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre, bf16* __restrict__ dx, int64_t n8) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (idx >= n8) return;
   const uint4 g = reinterpret_cast<const uint4*>(dy)[idx], p = reinterpret_cast<const uint4*>(pre)[idx];
@@ -92,6 +96,8 @@ __global__ void gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restr
 
 __global__ void scale_cols_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, bf16* __restrict__ y,
                                   int64_t rows, int cols8) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (idx >= rows * cols8) return;
   const int c = static_cast<int>(idx % cols8);
@@ -266,8 +272,8 @@ int write_prefix_tokens(const bf16* cls, const bf16* reg, bf16* x, int B, int nt
 int copy_rows(const bf16* src, int64_t lds, int rows_src, int src_off, bf16* dst, int64_t ldd, int rows_dst, int dst_off,
               int B, int rows, int cols, cudaStream_t s) {
   VLA_REQUIRE(cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "copy_rows: cols/ld must be multiples of 8");
-  copy_rows_kernel<<<blocks_for(static_cast<int64_t>(B) * rows * (cols / 8)), EW_THREADS, 0, s>>>(
-      src, lds, rows_src, src_off, dst, ldd, rows_dst, dst_off, B, rows, cols / 8);
+  VLA_CHECK_CUDA(vla_launch(copy_rows_kernel, dim3(blocks_for(static_cast<int64_t>(B) * rows * (cols / 8))), dim3(EW_THREADS), 0, s,
+                            src, lds, rows_src, src_off, dst, ldd, rows_dst, dst_off, B, rows, cols / 8));
   EW_DONE();
 }
 int embed_tokens_splice(const int64_t* ids, int ld_ids, const bf16* table, bf16* x, int B, int T, int P, int d,
@@ -278,12 +284,12 @@ int embed_tokens_splice(const int64_t* ids, int ld_ids, const bf16* table, bf16*
 }
 int gelu_bwd(const bf16* dy, const bf16* pre, bf16* dx, int64_t n, cudaStream_t s) {
   VLA_REQUIRE(n % 8 == 0, "gelu_bwd: n %% 8 != 0");
-  gelu_bwd_kernel<<<blocks_for(n / 8), EW_THREADS, 0, s>>>(dy, pre, dx, n / 8);
+  VLA_CHECK_CUDA(vla_launch(gelu_bwd_kernel, dim3(blocks_for(n / 8)), dim3(EW_THREADS), 0, s, dy, pre, dx, n / 8));
   EW_DONE();
 }
 int scale_cols(const bf16* x, const bf16* gamma, bf16* y, int64_t rows, int cols, cudaStream_t s) {
   VLA_REQUIRE(cols % 8 == 0, "scale_cols: cols %% 8 != 0");
-  scale_cols_kernel<<<blocks_for(rows * (cols / 8)), EW_THREADS, 0, s>>>(x, gamma, y, rows, cols / 8);
+  VLA_CHECK_CUDA(vla_launch(scale_cols_kernel, dim3(blocks_for(rows * (cols / 8))), dim3(EW_THREADS), 0, s, x, gamma, y, rows, cols / 8));
   EW_DONE();
 }
 int swiglu_fwd(const bf16* gu, bf16* act, int64_t M, int F, cudaStream_t s) {

@@ -732,6 +732,14 @@ extern "C" int vla_engine_set_placements(vla_engine* e, const int* xy_host, cons
 
 extern "C" int vla_engine_num_supervised(const vla_engine* e) { return e->R; }
 
+// 1 = keep both vision towers on the caller's stream (clean per-kernel timing for profiling); 0 = fork the SigLIP
+// tower onto the engine's side stream (default).
+extern "C" int vla_engine_set_single_stream(vla_engine* e, int on) {
+  VLA_REQUIRE(e != nullptr, "vla_engine_set_single_stream: null engine");
+  e->single_stream = on != 0;
+  return 0;
+}
+
 extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, int step_idx, int fe_mode,
                            const vla_loss_params* lp_c, float* dpatch, float* scalars, int* pred_ids, int flags,
                            void* stream) {

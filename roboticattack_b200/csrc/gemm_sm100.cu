@@ -345,6 +345,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TILE_M = BLOCK_M * CTAS;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();   // the next kernel of the stream may start its own prologue as CTAs of this one retire
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
   // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr
@@ -388,6 +389,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (CTAS == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_wait();      // everything above overlapped the predecessor's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ===== TMA producer (one per CTA) =====
@@ -549,13 +551,15 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g,
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_vla_pdl;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   VLA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BLOCK_N, CTAS>, ma, mb, g));
   if (e1) {
     VLA_CHECK_CUDA(cudaEventRecord(e1, stream));

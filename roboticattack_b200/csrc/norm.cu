@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(NORM_THREADS) layernorm_fwd_kernel(const bf16*
                                                                       float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                                       int d, float eps) {
   __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
   const int64_t row = blockIdx.x;
   const int d8 = d / 8;
   float xv[MAX_VEC][8];
@@ -77,6 +79,8 @@ __global__ void __launch_bounds__(NORM_THREADS) layernorm_bwd_kernel(const bf16*
                                                                       const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
                                                                       bf16* __restrict__ dx, int d) {
   __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
   const int64_t row = blockIdx.x;
   const int d8 = d / 8;
   const float mean = mean_in[row], rstd = rstd_in[row];
@@ -115,6 +119,8 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const bf16* _
                                                                     bf16* __restrict__ y, float* __restrict__ rstd_out, int d,
                                                                     float eps) {
   __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
   const int64_t row = blockIdx.x;
   const int d8 = d / 8;
   float xv[MAX_VEC][8];
@@ -139,6 +145,8 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(const bf16* _
                                                                     const bf16* __restrict__ w, const float* __restrict__ rstd_in,
                                                                     const bf16* __restrict__ dres, bf16* __restrict__ dx, int d) {
   __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
   const int64_t row = blockIdx.x;
   const int d8 = d / 8;
   const float rstd = rstd_in[row];
@@ -181,7 +189,7 @@ int check_dims(int64_t M, int d, const char* what) {
 int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* mean, float* rstd, int64_t M, int d, float eps,
                   cudaStream_t s) {
   if (int rc = check_dims(M, d, "layernorm_fwd")) return rc;
-  layernorm_fwd_kernel<<<static_cast<unsigned>(M), NORM_THREADS, 0, s>>>(x, w, b, y, mean, rstd, d, eps);
+  VLA_CHECK_CUDA(vla_launch(layernorm_fwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, x, w, b, y, mean, rstd, d, eps));
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
@@ -189,14 +197,14 @@ int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* m
 int layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* mean, const float* rstd, const bf16* dres,
                   bf16* dx, int64_t M, int d, cudaStream_t s) {
   if (int rc = check_dims(M, d, "layernorm_bwd")) return rc;
-  layernorm_bwd_kernel<<<static_cast<unsigned>(M), NORM_THREADS, 0, s>>>(dy, x, w, mean, rstd, dres, dx, d);
+  VLA_CHECK_CUDA(vla_launch(layernorm_bwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, dy, x, w, mean, rstd, dres, dx, d));
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
 }
 int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int64_t M, int d, float eps, cudaStream_t s) {
   if (int rc = check_dims(M, d, "rmsnorm_fwd")) return rc;
-  rmsnorm_fwd_kernel<<<static_cast<unsigned>(M), NORM_THREADS, 0, s>>>(x, w, y, rstd, d, eps);
+  VLA_CHECK_CUDA(vla_launch(rmsnorm_fwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, x, w, y, rstd, d, eps));
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
@@ -204,7 +212,7 @@ int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int64_t M, i
 int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx, int64_t M, int d,
                 cudaStream_t s) {
   if (int rc = check_dims(M, d, "rmsnorm_bwd")) return rc;
-  rmsnorm_bwd_kernel<<<static_cast<unsigned>(M), NORM_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d);
+  VLA_CHECK_CUDA(vla_launch(rmsnorm_bwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, dy, x, w, rstd, dres, dx, d));
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;

@@ -174,6 +174,10 @@ class VLAEngine:
                                               step, lr, betas[0], betas[1], eps, kind, grad_scale, clip_l1,
                                               _lib.ptr(scalars), _lib.cur_stream()), "vla_patch_update")
 
+    def set_single_stream(self, on: bool):
+        """True: both vision towers on the caller's stream (clean per-kernel timing); False (default): two streams."""
+        _lib.check(self._lib.vla_engine_set_single_stream(self._h, int(on)), "vla_engine_set_single_stream")
+
     def tap(self, what: str, dtype=torch.bfloat16, max_elems=1 << 28):
         buf = torch.empty(max_elems, dtype=dtype, device=self.device)
         n = self._lib.vla_engine_debug_tap(self._h, what.encode(), _lib.ptr(buf), buf.numel() * buf.element_size(),
