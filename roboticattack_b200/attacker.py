@@ -211,7 +211,8 @@ class UADAAttacker(_AttackerBase):
         opt_kind = _lib.OPT_ADAMW if self.optimizer == "adamW" else _lib.OPT_PGD
         total = int(num_iter / accumulate_steps)
         sched_step = 0
-        train_it, val_it = iter(train_dataloader), iter(val_dataloader)
+        train_it = iter(train_dataloader)
+        val_it = iter(val_dataloader) if val_dataloader is not None else None
         for i in range(num_iter):
             data, train_it = self._next(train_it, train_dataloader)
             data = dict(data)
@@ -234,7 +235,7 @@ class UADAAttacker(_AttackerBase):
                 log[f"train_rd_{idx}"] = rd[:, k].mean().item()
             self.loss_buffer.append(log["TRAIN_attack_loss (MSE_Distance)"])
             self._log(args, log, i)
-            if i % self.val_every == 0:
+            if i % self.val_every == 0 and val_dataloader is not None:
                 val_it = self._validate(i, val_it, val_dataloader, maskidx, fe_mode, loss, args)
         return h.patch.detach().cpu()
 

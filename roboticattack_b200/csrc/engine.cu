@@ -104,6 +104,7 @@ struct vla_engine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool single_stream = false;
+  bool fuse_swiglu_bwd = true;
   FrontendNorm nrm;
 };
 
@@ -564,6 +565,8 @@ extern "C" int vla_engine_set_buffers(vla_engine* e, void* weight_arena, size_t 
     VLA_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     const char* ss = getenv("VLA_SINGLE_STREAM");
     e->single_stream = ss && atoi(ss) != 0;
+    const char* fs = getenv("VLA_FUSE_SWIGLU_BWD");
+    e->fuse_swiglu_bwd = !(fs && atoi(fs) == 0);
   }
   e->batch_set = false;
   e->rope_set = false;
@@ -861,12 +864,15 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
   CK(scatter_rows(e->hn, e->sup_rows, dx, R, h, s));
   for (int l = c.llm_layers - 1; l >= 0; --l) {
     const LlamaLayerW& w = e->lw[l];
-    {   // d(act) = dX . W_down, with the SwiGLU backward fused: writes d(gate|up) directly
+    if (e->fuse_swiglu_bwd) {   // d(act) = dX . W_down, with the SwiGLU backward fused: writes d(gate|up) directly
       GemmEpilogue ep;
       ep.aux_mode = 2;
       ep.aux = la.gu[l];
       ep.ldaux = 2 * f;
       CK(G(dx, h, w.down_t, h, e->tr[0].wide2, 2 * f, ML, f, h, ep, s));
+    } else {
+      CK(G(dx, h, w.down_t, h, e->tr[0].wide, f, ML, f, h, plain, s));
+      CK(swiglu_bwd(e->tr[0].wide, la.gu[l], e->tr[0].wide2, ML, f, s));
     }
     CK(G(e->tr[0].wide2, 2 * f, w.gu_t, 2 * f, e->tr[0].norm, h, ML, h, 2 * f, plain, s));
     CK(rmsnorm_bwd(e->tr[0].norm, la.x_mid[l], w.n2, la.rstd2[l], dx, dxm, ML, h, s));

@@ -103,3 +103,48 @@ def test_fullsize_update_moves_patch_inside_unit_box(full):
     inside = (patch.cpu() > 0.01) & (patch.cpu() < 0.99)
     torch.testing.assert_close(d[inside], expect[inside], rtol=2e-3, atol=1e-7)
     assert torch.equal(torch.sign(p.cpu() - patch.cpu())[inside], -torch.sign(g)[inside])
+
+
+def _loader(cfg, n, B, T, seed):
+    out = []
+    for i in range(n):
+        b = synthetic_batch(cfg, B, T, seed=seed + i, ragged=(i % 2 == 1))
+        out.append({"pixel_values": b["obs"], "input_ids": b["input_ids"], "attention_mask": b["attention_mask"], "labels": b["labels"]})
+    return out
+
+
+def test_baseline_configs_run_at_full_size(full, tmp_path):
+    """BASELINE.json configs 2-4 through the drop-in classes on OpenVLA-7B shapes (two outer x two inner iterations each):
+    UADA bs=8 p=50; TMA (zero target) bs=8 geometry; UPA bs=16 p=70 with a maskidx sweep in its -CE mode and the default
+    position-aware loss.  One engine (30 GB of weights) is shared; the activation arena is re-planned per (B, T)."""
+    import argparse
+    from roboticattack_b200.attacker import TMAAttacker, UADAAttacker, UPAAttacker
+    cfg, eng, *_ = full
+    args = argparse.Namespace(wandb_project="false")
+    random.seed(42)
+    np.random.seed(42)
+    torch.manual_seed(42)
+
+    a = UADAAttacker(eng, None, save_dir=str(tmp_path / "uada"), optimizer="adamW", cfg=cfg)
+    a.val_batches = 1
+    p = a.patchattack_unconstrained(_loader(cfg, 2, 8, 33, 10), _loader(cfg, 1, 8, 33, 20), num_iter=2, patch_size=[3, 50, 50], lr=2e-3,
+                                    maskidx=[0, 1, 2], warmup=0, geometry=True, innerLoop=2, args=args)
+    assert p.shape == (3, 50, 50) and torch.isfinite(p).all() and len(a.train_CE_loss) == 4 and np.isfinite(a.train_CE_loss).all()
+
+    t = TMAAttacker(eng, None, save_dir=str(tmp_path / "tma"), optimizer="adamW", cfg=cfg)
+    p = t.patchattack_unconstrained(_loader(cfg, 2, 8, 33, 30), None, num_iter=2, target_action=np.zeros(7), patch_size=[3, 50, 50],
+                                    alpha=2e-3, maskidx=[0, 1, 2], warmup=0, geometry=True, innerLoop=2, args=args)
+    assert torch.isfinite(p).all() and np.isfinite(t.train_CE_loss).all()
+    first, last = t.train_inner_avg_loss[0], t.train_CE_loss[-1]
+    assert first > 0 and last > 0
+
+    for maskidx in ([0], [3], [6]):
+        u = UPAAttacker(eng, None, save_dir=str(tmp_path / f"upa{maskidx[0]}"), optimizer="adamW", alpha=0.8, belta=0.2, cfg=cfg)
+        p = u.patchattack_unconstrained(_loader(cfg, 1, 16, 33, 40), None, num_iter=1, patch_size=[3, 70, 70], lr=2e-3, maskidx=maskidx,
+                                        warmup=0, geometry=True, innerLoop=2, reverse_direction=False, args=args)
+        assert p.shape == (3, 70, 70) and torch.isfinite(p).all() and np.isfinite(u.train_CE_loss).all()
+    u = UPAAttacker(eng, None, save_dir=str(tmp_path / "upa"), optimizer="adamW", alpha=0.8, belta=0.2, cfg=cfg)
+    p = u.patchattack_unconstrained(_loader(cfg, 1, 16, 33, 50), None, num_iter=1, patch_size=[3, 70, 70], lr=2e-3, maskidx=[0, 1, 2],
+                                    warmup=0, geometry=True, innerLoop=2, reverse_direction=True, args=args)
+    assert torch.isfinite(p).all() and np.isfinite(u.train_CE_loss).all()
+    eng.ensure_plan(8, 33)
