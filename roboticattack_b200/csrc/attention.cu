@@ -341,25 +341,36 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
     const float l = ok ? lse[(static_cast<int64_t>(b) * H + h) * N + row] : INFINITY;
     lse2[r] = (l == -INFINITY) ? INFINITY : l * LOG2E;   // fully masked / padded rows -> p = 0
   }
-  // delta = rowsum(dO * O) for this warp's 16 rows (was a separate kernel): one coalesced row read each, warp reduce;
-  // written out for the dK/dV kernel that follows on the stream.
+  // delta = rowsum(dO * O) for this warp's 16 rows (was a separate kernel).  All 16 rows' loads are issued before any
+  // reduction (independent, fully unrolled) so that their latency overlaps; written out for the dK/dV kernel.
   {
     const bf16* obase = o + static_cast<int64_t>(b) * N * D + h * hd;
     const bf16* dbase = dout + static_cast<int64_t>(b) * N * D + h * hd;
+    float part[16];
+#pragma unroll
     for (int rr = 0; rr < 16; ++rr) {
       const int row = q0 + warp * 16 + rr;
       float sum = 0.f;
       if (row < N) {
-        for (int c = lane * 2; c < hd; c += 64) {
-          const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(obase + static_cast<int64_t>(row) * D + c));
-          const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dbase + static_cast<int64_t>(row) * D + c));
-          sum += a.x * d.x + a.y * d.y;
+#pragma unroll
+        for (int c0 = 0; c0 < HDP; c0 += 64) {
+          const int c = c0 + lane * 2;
+          if (c < hd) {
+            const float2 a = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(obase + static_cast<int64_t>(row) * D + c)));
+            const float2 d = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(dbase + static_cast<int64_t>(row) * D + c)));
+            sum += a.x * d.x + a.y * d.y;
+          }
         }
       }
-      sum = warp_sum(sum);
+      part[rr] = sum;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const float sum = warp_sum(part[rr]);
       if (rr == g) dl[0] = sum;
       if (rr == g + 8) dl[1] = sum;
-      if (lane == 0 && row < N) delta[(static_cast<int64_t>(b) * H + h) * N + row] = sum;
+      const int row = q0 + warp * 16 + rr;
+      if (lane == rr && row < N) delta[(static_cast<int64_t>(b) * H + h) * N + row] = sum;
     }
   }
 
