@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int TC_THREADS = 160;
+constexpr int TC_THREADS = 288;      // warps 0-7: softmax / epilogue, warp 8: TMA + MMA issue
 constexpr int MAX_KV = 320;          // keys per (batch, head) supported in one pass
 constexpr int PANEL_ROWS_Q = 128;
 constexpr float LOG2E_F = 1.4426950408889634f;
@@ -53,8 +53,16 @@ struct FwdSmem {
   static constexpr int OFF_V = OFF_K + KV_BYTES;
   static constexpr int OFF_P = P_ALIASES_K ? OFF_K : OFF_V + KV_BYTES;
   static constexpr int OFF_BAR = (P_ALIASES_K ? OFF_V + KV_BYTES : OFF_P + P_BYTES);
-  static constexpr int TOTAL = OFF_BAR + 64 + 1024;
+  static constexpr int TOTAL = OFF_BAR + 64 + 1024 /* s_red */ + 1024 /* alignment slack */;
 };
+
+// named barrier among the 256 softmax threads only (the control warp never joins it)
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int HD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -62,26 +70,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict
                    const int* __restrict__ kv_len, int N, int H, int causal, float scale) {
   using SM = FwdSmem<HD>;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sQ = base + SM::OFF_Q, sK = base + SM::OFF_K, sV = base + SM::OFF_V, sP = base + SM::OFF_P;
   const uint32_t bar_qk = base + SM::OFF_BAR, bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_p = bar_qk + 24, bar_o = bar_qk + 32;
   const uint32_t tmem_slot = bar_qk + 40;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + SM::OFF_BAR + 40);
+  float* s_red = reinterpret_cast<float*>(gen + SM::OFF_BAR + 64);   // [2 halves][128 rows]: partial max, then partial sum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
+  // heavy tiles first: under the causal mask the last query tile sees the most keys
+  const int b = blockIdx.z, h = blockIdx.y, q0 = (gridDim.x - 1 - blockIdx.x) * 128;
   const int D = H * HD;
   const int klen = kv_len ? min(kv_len[b], N) : N;
   const int kv_vis = causal ? min(klen, q0 + 128) : klen;        // keys any row of this tile can see
   const int nkv = ((kv_vis + 63) / 64) * 64;                     // MMA N extent (multiple of 64, <= MAX_KV)
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     mbar_init(bar_qk, 1);
     mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, 256);
     mbar_init(bar_o, 1);
     fence_mbar_init();
   }
@@ -94,8 +105,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_gen;
   const uint32_t tmem_S = tmem, tmem_O = tmem + 384;
+  pdl_wait();
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       // ---- loads ----
       const int kv_boxes = nkv / 64;
@@ -141,40 +153,56 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict
     }
     __syncwarp();
   } else {
-    // ---- softmax: thread r <-> query row q0 + r, TMEM lane r ----
-    const int r = warp * 32 + lane;
+    // ---- softmax: 8 warps; warp w owns TMEM lanes 32*(w%4).. (query rows) and the 32-column chunks c with c%2 == w/4 ----
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;
     const int q = q0 + r;
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const float sl2 = scale * LOG2E_F;
+    const int nchunks = nkv / 32;
+    const int row_lo = q0 + quarter * 32;            // smallest query index of this warp
     mbar_wait(bar_s, 0);
     tc_fence_after();
-    float mx = -INFINITY;
-    for (int c = 0; c < nkv / 32; ++c) {
+    // pass 1: row max over this warp's chunks (four independent chains), combined with the partner warp through smem
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int c = half; c < nchunks; c += 2) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
       tmem_ld_wait();
+      const bool need_mask = (c * 32 + 32 > klen) || (causal && c * 32 + 31 > row_lo);   // warp-uniform
+      if (need_mask) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = c * 32 + j;
-        const bool ok = (col < klen) && (!causal || col <= q);
-        if (ok) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j) {
+          const int col = c * 32 + j;
+          if (!((col < klen) && (!causal || col <= q))) v[j] = 0xff800000u;   // -inf
+        }
       }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
     }
+    s_red[half * 128 + r] = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    softmax_bar();
+    const float mx = fmaxf(s_red[r], s_red[128 + r]);
     const float mref = (mx == -INFINITY) ? 0.f : mx * sl2;
-    float l = 0.f;
-    for (int c = 0; c < nkv / 32; ++c) {
+    softmax_bar();   // both halves have read the maxima before the slots are reused for the sums
+    // pass 2: p = exp2(s*scale*log2e - m), row sum, P -> smem (bf16, canonical K-major 128B-swizzled panels)
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = half; c < nchunks; c += 2) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
       tmem_ld_wait();
+      const bool need_mask = (c * 32 + 32 > klen) || (causal && c * 32 + 31 > row_lo);
       float p[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int col = c * 32 + j;
-        const bool ok = (col < klen) && (!causal || col <= q);
-        p[j] = ok ? exp2f(__uint_as_float(v[j]) * sl2 - mref) : 0.f;
-        l += p[j];
+        float x = fmaf(__uint_as_float(v[j]), sl2, -mref);
+        if (need_mask) {
+          const int col = c * 32 + j;
+          if (!((col < klen) && (!causal || col <= q))) x = -INFINITY;
+        }
+        p[j] = fast_exp2(x);
+        l4[j & 3] += p[j];
       }
-      // P[r, c*32 .. +31] -> canonical K-major SW128 panel (c/2), 16-byte chunk index (c%2)*4 + t, XOR (r & 7)
       const uint32_t prow = sP + (c / 2) * SM::P_PANEL_BYTES + r * 128;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -186,15 +214,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict
                      : "memory");
       }
     }
+    s_red[half * 128 + r] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
     tc_fence_before();
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     mbar_arrive(bar_p);
-    // ---- epilogue ----
+    softmax_bar();
+    const float l = s_red[r] + s_red[128 + r];
+    // ---- epilogue: O / l, the two warps of a lane quarter take alternate 32-column chunks ----
     mbar_wait(bar_o, 0);
     tc_fence_after();
     const float inv = l > 0.f ? 1.f / l : 0.f;
 #pragma unroll 1
-    for (int c = 0; c < HD / 32; ++c) {
+    for (int c = half; c < HD / 32; c += 2) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
       tmem_ld_wait();
@@ -208,7 +239,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict
                              pack_bf16x2(__uint_as_float(v[t * 8 + 6]) * inv, __uint_as_float(v[t * 8 + 7]) * inv));
       }
     }
-    if (q < N) lse[(static_cast<int64_t>(b) * H + h) * N + q] = (l > 0.f) ? (mref + log2f(l)) / LOG2E_F : -INFINITY;
+    if (half == 0 && q < N) lse[(static_cast<int64_t>(b) * H + h) * N + q] = (l > 0.f) ? (mref + log2f(l)) / LOG2E_F : -INFINITY;
   }
 
   tc_fence_before();
@@ -232,8 +263,8 @@ int launch_fwd_tc(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B
   CUtensorMap map;
   if (int rc = make_tmap_bf16(qkv, 3 * D, N, B, 3 * static_cast<int64_t>(D), static_cast<int64_t>(N) * 3 * D, 64, 64, &map)) return rc;
   dim3 grid(ceil_div(N, 128), H, B);
-  attn_fwd_tc_kernel<HD><<<grid, TC_THREADS, SM::TOTAL, s>>>(map, o, lse, kv_len, N, H, causal, scale);
-  VLA_LAUNCH_CHECK();
+  VLA_CHECK_CUDA(vla_launch(attn_fwd_tc_kernel<HD>, grid, dim3(TC_THREADS), static_cast<size_t>(SM::TOTAL), s, map, o, lse, kv_len, N, H,
+                            causal, scale));
   ++g_vla_launch_count;
   return 0;
 }
