@@ -106,8 +106,14 @@ int vla_attention_fwd(const void* qkv, void* o, float* lse, const int32_t* kv_le
                       int causal, void* stream);
 int vla_attention_bwd(const void* qkv, const void* o, const void* dout, const float* lse, float* delta_scratch,
                       void* dqkv, const int32_t* kv_len, int B, int N, int H, int hd, int causal, void* stream);
-/* 0 (default) = pipelined mma.sync attention kernels; 1 = tcgen05 forward kernel where the shape is supported
- * (hd 64/128, 64 <= N <= 320) */
+/* Same, with the backward of the rotary embedding fused (head dim 128): d(q), d(k) are returned wrt the PRE-RoPE
+ * projections.  cos_tab / sin_tab f32 [rope_L, 64]; position of row n = n % rope_L
+ * (replaces autograd through apply_rotary_pos_emb, transformers modeling_llama.py). */
+int vla_attention_bwd_rope(const void* qkv, const void* o, const void* dout, const float* lse, float* delta_scratch,
+                           void* dqkv, const int32_t* kv_len, int B, int N, int H, int hd, int causal,
+                           const float* cos_tab, const float* sin_tab, int rope_L, void* stream);
+/* Kernel selection, bit mask: bit 0 = tcgen05 forward kernel (hd 64/128, 64 <= N <= 320; default off), bit 1 = tcgen05
+ * backward kernels (hd 64/72/128; default on).  0 = pipelined mma.sync kernels only.  Env VLA_ATTN_IMPL sets the default. */
 int vla_attention_set_impl(int impl);
 int vla_rope_inplace(void* qkv, const float* cos_tab, const float* sin_tab, int64_t M, int L, int H, int hd, int dir,
                      void* stream);

@@ -67,6 +67,8 @@ SIGNATURES = {
     "vla_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vla_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int, c_int, c_int, c_void_p]),
+    "vla_attention_bwd_rope": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                       c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "vla_attention_set_impl": (c_int, [c_int]),
     "vla_rope_inplace": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "vla_swiglu_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),

@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "--compiler-options", "-fPIC",
     "-Xcompiler", "-fvisibility=default",
     "-shared",
-]
+] + os.environ.get("VLA_NVCC_EXTRA", "").split()
 
 
 def _sources():

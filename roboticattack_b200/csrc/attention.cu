@@ -12,6 +12,7 @@
 // Layout: qkv [B*N, 3*H*hd] = [q | k | v] with heads contiguous inside each third (the natural output of the fused
 // qkv GEMM); o, dout [B*N, H*hd]; lse, delta [B, H, N] fp32.
 #include <math.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -598,12 +599,21 @@ int launch_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* ls
 
 }  // namespace
 
-int g_attn_impl = 0;   // the tcgen05 forward is correct but not yet faster than the pipelined legacy kernel: opt-in
+// bit 0: tcgen05 forward (correct, not yet faster than the pipelined legacy kernel: opt-in); bit 1: tcgen05 backward.
+// VLA_ATTN_IMPL overrides the default at first use.
+int g_attn_impl = -1;
+static int attn_impl() {
+  if (g_attn_impl < 0) {
+    const char* e = getenv("VLA_ATTN_IMPL");
+    g_attn_impl = e ? (atoi(e) & 3) : 2;
+  }
+  return g_attn_impl;
+}
 
 int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                   cudaStream_t s) {
   VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
-  if (g_attn_impl && attention_tc_supported(N, hd))
+  if ((attn_impl() & 1) && attention_tc_supported(N, hd))
     return attention_fwd_tc(qkv, o, lse, kv_len, B, N, H, hd, causal, 1.f / sqrtf(static_cast<float>(hd)), s);
   if (hd <= 64) return launch_fwd<64>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   if (hd <= 80) return launch_fwd<80>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
@@ -616,6 +626,8 @@ int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float*
   VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
   VLA_REQUIRE(rope_cos == nullptr || (hd == 128 && rope_sin != nullptr && rope_L > 0),
               "attention_bwd: the fused RoPE backward needs head dim 128 and both tables");
+  if ((attn_impl() & 2) && attention_bwd_tc_supported(N, hd))
+    return attention_bwd_tc(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, rope_cos, rope_sin, rope_L, s);
   if (hd <= 64) return launch_bwd<64>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, nullptr, nullptr, 0, s);
   if (hd <= 80) return launch_bwd<80>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, nullptr, nullptr, 0, s);
   return launch_bwd<128>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, rope_cos, rope_sin, rope_L, s);

@@ -104,8 +104,14 @@ int vla_attention_bwd(const void* qkv, const void* o, const void* dout, const fl
   return attention_bwd(CBF(qkv), CBF(o), CBF(dout), lse, delta, BF(dqkv), kv_len, B, N, H, hd, causal, nullptr, nullptr, 0,
                        S(stream));
 }
+int vla_attention_bwd_rope(const void* qkv, const void* o, const void* dout, const float* lse, float* delta, void* dqkv,
+                           const int32_t* kv_len, int B, int N, int H, int hd, int causal, const float* cos_tab,
+                           const float* sin_tab, int rope_L, void* stream) {
+  return attention_bwd(CBF(qkv), CBF(o), CBF(dout), lse, delta, BF(dqkv), kv_len, B, N, H, hd, causal, cos_tab, sin_tab, rope_L,
+                       S(stream));
+}
 int vla_attention_set_impl(int impl) {
-  VLA_REQUIRE(impl == 0 || impl == 1, "vla_attention_set_impl: 0 = legacy mma.sync, 1 = tcgen05 where supported");
+  VLA_REQUIRE(impl >= 0 && impl <= 3, "vla_attention_set_impl: bit 0 = tcgen05 forward, bit 1 = tcgen05 backward (0 = legacy mma.sync only)");
   g_attn_impl = impl;
   return 0;
 }

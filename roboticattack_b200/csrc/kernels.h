@@ -65,7 +65,12 @@ int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B
 bool attention_tc_supported(int N, int hd);
 int attention_fwd_tc(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                      float scale, cudaStream_t s);
-extern int g_attn_impl;   // 0 = legacy mma.sync kernels only, 1 = tcgen05 where supported (default)
+// tcgen05 backward (attention_bwd_tc.cu): head dims 64 / 72 / 128, any N; same contract as attention_bwd.
+bool attention_bwd_tc_supported(int N, int hd);
+int attention_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
+                     const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
+                     int rope_L, cudaStream_t s);
+extern int g_attn_impl;   // bit 0 = tcgen05 forward, bit 1 = tcgen05 backward where supported; -1 = unset (default 2 / env)
 // dqkv [B*N, 3*H*hd]; delta scratch [B, H, N] fp32
 // rope_cos / rope_sin (nullable; head dim 128 only): when given, d(q) and d(k) are returned with the rotary embedding's
 // backward already applied (gradients wrt the PRE-RoPE projections), i.e. rope_inplace(dqkv, ..., dir = -1) is fused.
