@@ -122,25 +122,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict
       for (int p = 0; p < SM::PANELS; ++p)
         for (int r = 0; r < kv_boxes; ++r)
           tma_load_3d(sV + p * SM::KV_PANEL_BYTES + r * 8192, &map_qkv, bar_v, 2 * D + h * HD + p * 64, r * 64, b);
+    }
+    __syncwarp();
+    // The MMA issue runs warp-converged with the tcgen05 instructions under one elect.sync per batch (issued back to back).
+    {
       // ---- S = Q K^T ----
       mbar_wait(bar_qk, 0);
       tc_fence_after();
-      for (int c0 = 0; c0 < nkv; c0 += 256) {
-        const int n = min(256, nkv - c0);
-        const uint32_t id = idesc_bf16(128, n, 0, 0);
+      if (elect_one_sync()) {
+        for (int c0 = 0; c0 < nkv; c0 += 256) {
+          const int n = min(256, nkv - c0);
+          const uint32_t id = idesc_bf16(128, n, 0, 0);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint64_t da = smem_desc(sQ + (k / 4) * (PANEL_ROWS_Q * 128) + (k % 4) * 32, 16, 1024);
-          const uint64_t db = smem_desc(sK + (k / 4) * SM::KV_PANEL_BYTES + c0 * 128 + (k % 4) * 32, 16, 1024);
-          umma_bf16_ss<1>(tmem_S + c0, da, db, id, k > 0 ? 1u : 0u);
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint64_t da = smem_desc(sQ + (k / 4) * (PANEL_ROWS_Q * 128) + (k % 4) * 32, 16, 1024);
+            const uint64_t db = smem_desc(sK + (k / 4) * SM::KV_PANEL_BYTES + c0 * 128 + (k % 4) * 32, 16, 1024);
+            umma_bf16_ss<1>(tmem_S + c0, da, db, id, k > 0 ? 1u : 0u);
+          }
         }
+        umma_commit<1>(bar_s);
       }
-      umma_commit<1>(bar_s);
+      __syncwarp();
       // ---- O = P V  (P: K-major A operand written by the softmax warps; V: MN-major B operand) ----
       mbar_wait(bar_p, 0);
       mbar_wait(bar_v, 0);
       tc_fence_after();
-      {
+      if (elect_one_sync()) {
         const uint32_t id = idesc_bf16(128, HD, 0, 1);
         for (int kk = 0; kk < nkv / 16; ++kk) {
           const uint64_t da = smem_desc(sP + (kk / 4) * SM::P_PANEL_BYTES + (kk % 4) * 32, 16, 1024);
@@ -148,8 +155,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict
           const uint64_t db = smem_desc(sV + kk * 16 * 128, SM::KV_PANEL_BYTES, 1024);
           umma_bf16_ss<1>(tmem_O, da, db, id, kk > 0 ? 1u : 0u);
         }
+        umma_commit<1>(bar_o);
       }
-      umma_commit<1>(bar_o);
     }
     __syncwarp();
   } else {

@@ -69,7 +69,13 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // compute in fp32 and call rbf() wherever PyTorch would have materialised a bf16 tensor, so that
 // the engine's rounding points mirror the eager path.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// Round to bf16 and back.  The packed conversion (F2FP on the ALU pipe) + a mask replaces the scalar F2F conversion, which
+// issues at a quarter of the rate: rounding is the most frequent op of the fused epilogues.  RNE, NaN -> NaN.
+__device__ __forceinline__ float rbf(float x) {
+  uint32_t p;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(x), "f"(0.f));   // x -> upper half
+  return __uint_as_float(p & 0xFFFF0000u);
+}
 __device__ __forceinline__ float b2f(bf16 x) { return __bfloat162float(x); }
 __device__ __forceinline__ bf16 f2b(float x) { return __float2bfloat16_rn(x); }
 
@@ -105,12 +111,32 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-// exact (erf) GELU as torch.nn.GELU() default, and its derivative
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// exact (erf) GELU as torch.nn.GELU() default, and its derivative.
+// erf(x / sqrt 2) by Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. at the level of fp32 erff's own rounding
+// near +-1, which is what matters in 1 + erf): 2 MUFU ops (rcp, ex2) + ~10 FMA-pipe ops instead of libdevice erff's ~30;
+// the exp(-x^2 / 2) factor is shared with the Gaussian pdf of the derivative.
+__device__ __forceinline__ void erf_sqrt2_parts(float x, float& erf_v, float& gauss) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  p *= t;
+  erf_v = copysignf(fmaf(-p, e, 1.f), x);
+  gauss = e;   // exp(-x^2 / 2)
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float er, g;
+  erf_sqrt2_parts(x, er, g);
+  return 0.5f * x * (1.f + er);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float er, g;
+  erf_sqrt2_parts(x, er, g);
+  return fmaf(x * 0.39894228040143268f, g, 0.5f * (1.f + er));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -208,6 +234,19 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtens
       :
       : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// true in exactly one lane of a converged warp (elect.sync); tcgen05 instructions guarded by it are issued back to back
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // --- tcgen05 / TMEM ---  (CTAS = 1: cta_group::1; CTAS = 2: cta_group::2, executed by the same warp of both CTAs)

@@ -131,18 +131,40 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
 };
 
-// One row x 32 columns of the accumulator -> global, with the fused epilogue.
-__device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const uint32_t (&acc)[32], int row_in, int col0) {
+// The per-thread "side" operand of a chunk (64 contiguous bytes of this thread's row: the residual, or the saved
+// pre-activation of the GELU backward) is the only epilogue input with a full L2 / HBM latency; the epilogue loop
+// fetches it one chunk ahead (side_ptr + load_side), so the latency hides behind the MMAs / the previous chunk.
+__device__ __forceinline__ const uint4* side_ptr(const GemmArgs& g, int row_in, int col0) {
+  const GemmEpilogue& e = g.epi;
+  if (row_in >= g.M || col0 + 32 > g.N) return nullptr;
+  const int row = e.out_group ? (row_in / e.out_group) * e.out_stride + e.out_offset + row_in % e.out_group : row_in;
+  if (e.aux_mode == 1) return reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + col0);
+  if (e.aux_mode == 0 && e.resid) {
+    const int rrow = e.resid_mod ? row_in % e.resid_mod : row;
+    return reinterpret_cast<const uint4*>(e.resid + static_cast<int64_t>(rrow) * e.ldr + col0);
+  }
+  return nullptr;
+}
+__device__ __forceinline__ void load_side(const uint4* p, uint4 (&buf)[4]) {
+  if (p != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) buf[q] = p[q];
+  }
+}
+
+// One row x 32 columns of the accumulator -> global, with the fused epilogue.  `side` = this chunk's prefetched side operand
+// (valid when side_ptr() of the chunk is non-null).
+__device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const uint32_t (&acc)[32], int row_in, int col0,
+                                                     const uint4 (&side)[4]) {
   const GemmEpilogue& e = g.epi;
   const int row = e.out_group ? (row_in / e.out_group) * e.out_stride + e.out_offset + row_in % e.out_group : row_in;
   const int rrow = e.resid_mod ? row_in % e.resid_mod : row;
   const bool full = (col0 + 32 <= g.N);
   if (e.aux_mode == 1) {   // GELU backward: dpre = bf16(dy) * gelu'(pre)
-    const uint4* ap = reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + col0);
     uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint4 u = ap[q];
+      const uint4 u = side[q];
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
       uint32_t o[4];
 #pragma unroll
@@ -227,8 +249,13 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
                            pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]));
     }
     if (e.act == 1) {
+      if (e.gamma || e.resid) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = rbf(gelu_erf(x[j]));
+        for (int j = 0; j < 32; ++j) x[j] = rbf(gelu_erf(x[j]));
+      } else {   // rounded by the final pack
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+      }
     }
     if (e.gamma) {
       const uint4* gp = reinterpret_cast<const uint4*>(e.gamma + col0);
@@ -245,10 +272,9 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
       }
     }
     if (e.resid) {
-      const uint4* rp = reinterpret_cast<const uint4*>(e.resid + static_cast<int64_t>(rrow) * e.ldr + col0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint4 u = rp[q];
+        const uint4 u = side[q];
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -270,11 +296,12 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
                            pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]));
     }
   } else {
-    // ragged N edge: scalar path
-#pragma unroll 1
+    // ragged N edge: scalar path.  Fully unrolled with static indices: a dynamically indexed x[] would be placed in
+    // local memory for the WHOLE function (8 STL.128 per chunk on the hot path above).
+#pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int n = col0 + j;
-      if (n >= g.N) break;
+      if (n >= g.N) continue;
       float v = x[j];
       if (e.bias) v += b2f(e.bias[n]);
       v = rbf(v);
@@ -424,7 +451,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer (single thread; the leader CTA issues for the pair) =====
-    if (lane == 0 && leader) {
+    // The whole warp runs the loop converged; the tcgen05 instructions of a k-block are guarded by one elect.sync so
+    // that ptxas emits them back to back (under a plain `lane == 0` branch every tcgen05.mma is wrapped in its own
+    // elect / branch "waterfall" sequence, ~100 issue cycles per MMA -- more than a 128 x 128 x 16 MMA takes).
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -440,18 +470,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t da = make_umma_desc_sw128(sa);
           const uint64_t db = make_umma_desc_sw128(sa + A_TILE_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 32 B (= UMMA_K bf16) inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16_ss<CTAS>(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 32 B (= UMMA_K bf16) inside the 128 B swizzle row: +2 in the (addr >> 4) field
+              umma_bf16_ss<CTAS>(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit<CTAS>(empty_bar(stage));
+            if (kb == num_k_blocks - 1) umma_commit<CTAS>(tfull_bar(acc));
           }
-          umma_commit<CTAS>(empty_bar(stage));
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit<CTAS>(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -465,10 +498,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t acc_phase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile % g.num_m_blocks, n_blk = tile / g.num_m_blocks;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const int row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+      const bool waited = g.epi.pair_mode != 0;
+      if (waited) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+      }
       if (g.epi.pair_mode) {
         // chunks (4p + half) and (4p + half + 2) of every 128-column group: columns n and n + 64 in the same thread
 #pragma unroll 1
@@ -483,14 +519,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (row < g.M) epilogue_store_pair(g, va, vb, row, col_a);
         }
       } else {
+        uint4 side_cur[4], side_nxt[4];
+        load_side(side_ptr(g, row, n_blk * BLOCK_N + half * 32), side_nxt);   // first chunk: overlaps the wait for the MMAs
+        if (!waited) {
+          mbar_wait(tfull_bar(acc), acc_phase);
+          tc_fence_after();
+        }
 #pragma unroll 1
         for (int c = half; c < BLOCK_N / 32; c += 2) {
           const int col0 = n_blk * BLOCK_N + c * 32;
           if (col0 >= g.N) break;  // warp-uniform
+#pragma unroll
+          for (int q = 0; q < 4; ++q) side_cur[q] = side_nxt[q];
+          if (c + 2 < BLOCK_N / 32) load_side(side_ptr(g, row, col0 + 64), side_nxt);
           uint32_t v[32];
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();
-          if (row < g.M) epilogue_store_chunk(g, v, row, col0);
+          if (row < g.M) epilogue_store_chunk(g, v, row, col0, side_cur);
         }
       }
       tc_fence_before();
