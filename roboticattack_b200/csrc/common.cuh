@@ -128,6 +128,14 @@ __device__ __forceinline__ void erf_sqrt2_parts(float x, float& erf_v, float& ga
   erf_v = copysignf(fmaf(-p, e, 1.f), x);
   gauss = e;   // exp(-x^2 / 2)
 }
+// logistic sigmoid with the two approximate MUFU ops (ex2, rcp; ~2 ulp each, far below the bf16 rounding that follows);
+// expf + an IEEE division cost ~25 instructions and a slow-path call in the fused SwiGLU epilogues.
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   float er, g;
   erf_sqrt2_parts(x, er, g);

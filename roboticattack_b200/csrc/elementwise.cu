@@ -112,7 +112,7 @@ __global__ void scale_cols_kernel(const bf16* __restrict__ x, const bf16* __rest
   reinterpret_cast<uint4*>(y)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_fast(x); }
 
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int64_t M, int F8) {
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -153,7 +153,7 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __r
     const float dv[2] = {dd.x, dd.y}, gv[2] = {gg.x, gg.y}, uv[2] = {uu.x, uu.y};
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float sig = 1.f / (1.f + expf(-gv[e]));
+      const float sig = sigmoid_fast(gv[e]);
       const float s_b = rbf(gv[e] * sig);                 // saved bf16 output of silu
       const float ds = rbf(dv[e] * uv[e]);                // grad wrt silu output
       r[0][e] = ds * sig * (1.f + gv[e] * (1.f - sig));   // grad wrt gate

@@ -105,6 +105,12 @@ struct vla_engine {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool single_stream = false;
   bool fuse_swiglu_bwd = true;
+  // Last decoder layer on the supervised rows only (see vla_fwd_bwd): only those rows of its output reach the loss, so
+  // everything after its attention (o_proj, MLP and their backward) runs on R gathered rows instead of B*L.
+  bool prune_last = true;
+  bf16 *ll_xs = nullptr, *ll_as = nullptr, *ll_xm = nullptr, *ll_norm = nullptr, *ll_gu = nullptr, *ll_act = nullptr,
+       *ll_dgu = nullptr, *ll_dnorm = nullptr, *ll_dxm = nullptr, *ll_dattn = nullptr;
+  float* ll_rstd2 = nullptr;
   FrontendNorm nrm;
 };
 
@@ -357,6 +363,20 @@ size_t plan(vla_engine* e, uint8_t* base, int B, int T) {
   e->dlogits = bp.take<bf16>(static_cast<size_t>(Rmax) * V);
   e->row_stats = bp.take<float>(loss_head_row_stats_floats(Rmax));
   {
+    const size_t Rh = static_cast<size_t>(Rmax) * h, Rf = static_cast<size_t>(Rmax) * f;
+    e->ll_xs = bp.take<bf16>(Rh);
+    e->ll_as = bp.take<bf16>(Rh);
+    e->ll_xm = bp.take<bf16>(Rh);
+    e->ll_norm = bp.take<bf16>(Rh);
+    e->ll_gu = bp.take<bf16>(2 * Rf);
+    e->ll_act = bp.take<bf16>(Rf);
+    e->ll_dgu = bp.take<bf16>(2 * Rf);
+    e->ll_dnorm = bp.take<bf16>(Rh);
+    e->ll_dxm = bp.take<bf16>(Rh);
+    e->ll_dattn = bp.take<bf16>(Rh);
+    e->ll_rstd2 = bp.take<float>(Rmax);
+  }
+  {
     Transients& t0 = e->tr[0];
     t0.delta = bp.take<float>(max_lse);
     t0.norm = bp.take<bf16>(max_md);
@@ -567,6 +587,8 @@ extern "C" int vla_engine_set_buffers(vla_engine* e, void* weight_arena, size_t 
     e->single_stream = ss && atoi(ss) != 0;
     const char* fs = getenv("VLA_FUSE_SWIGLU_BWD");
     e->fuse_swiglu_bwd = !(fs && atoi(fs) == 0);
+    const char* pl = getenv("VLA_PRUNE_LAST");
+    e->prune_last = !(pl && atoi(pl) == 0);
   }
   e->batch_set = false;
   e->rope_set = false;
@@ -807,6 +829,7 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
   }
   CK(embed_tokens_splice(e->ids, T, e->embed, e->la.x[0], B, T - 1, P, h, s));
   LlmActs& la = e->la;
+  const bool prune = e->prune_last && e->fuse_swiglu_bwd && e->R > 0;
   for (int l = 0; l < c.llm_layers; ++l) {
     const LlamaLayerW& w = e->lw[l];
     CK(rmsnorm_fwd(la.x[l], w.n1, e->tr[0].norm, la.rstd1[l], ML, h, c.rms_eps, s));
@@ -823,6 +846,28 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
       CK(rope_inplace(la.qkv[l], e->rope_cos, e->rope_sin, ML, L, NH, hd, +1, s));
     }
     CK(attention_fwd(la.qkv[l], la.attn_o[l], la.lse[l], e->kv_len, B, L, NH, hd, 1, s));
+    if (prune && l == c.llm_layers - 1) {
+      // Last layer: from here on every op is row-wise and only the R supervised rows of its output are read (lm_head on
+      // the supervised rows), so gather those rows of the attention output / residual and run o_proj + MLP on R rows.
+      const int R = e->R;
+      CK(gather_rows(la.attn_o[l], e->sup_rows, e->ll_as, R, h, s));
+      CK(gather_rows(la.x[l], e->sup_rows, e->ll_xs, R, h, s));
+      GemmEpilogue ep;
+      ep.resid = e->ll_xs;
+      ep.ldr = h;
+      CK(G(e->ll_as, h, w.o, h, e->ll_xm, h, R, h, h, ep, s));
+      CK(rmsnorm_fwd(e->ll_xm, w.n2, e->ll_norm, e->ll_rstd2, R, h, c.rms_eps, s));
+      GemmEpilogue eg;
+      eg.pair_mode = 2;
+      eg.act_out = e->ll_act;
+      eg.ld_act = f;
+      CK(G(e->ll_norm, h, w.gu, h, e->ll_gu, 2 * f, R, 2 * f, h, eg, s));
+      GemmEpilogue ed;
+      ed.resid = e->ll_xm;
+      ed.ldr = h;
+      CK(G(e->ll_act, f, w.down, f, e->hs, h, R, h, f, ed, s));   // = the supervised rows of the final hidden state
+      break;
+    }
     {
       GemmEpilogue ep;
       ep.resid = la.x[l];
@@ -845,7 +890,7 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
     }
   }
   const int R = e->R;
-  CK(gather_rows(la.x[c.llm_layers], e->sup_rows, e->hs, R, h, s));
+  if (!prune) CK(gather_rows(la.x[c.llm_layers], e->sup_rows, e->hs, R, h, s));
   CK(rmsnorm_fwd(e->hs, e->final_norm, e->hn, e->rstd_f, R, h, c.rms_eps, s));
   {
     GemmEpilogue ep;
@@ -860,9 +905,40 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
   CK(rmsnorm_bwd(e->tr[0].norm, e->hs, e->final_norm, e->rstd_f, nullptr, e->hn, R, h, s));
   bf16* dx = e->tr[0].a;
   bf16* dxm = e->tr[0].b;
-  VLA_CHECK_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(ML) * h * sizeof(bf16), s));
-  CK(scatter_rows(e->hn, e->sup_rows, dx, R, h, s));
-  for (int l = c.llm_layers - 1; l >= 0; --l) {
+  int l_first = c.llm_layers - 1;
+  if (prune) {
+    // last layer on the R supervised rows: MLP backward, RMSNorm backward, o_proj backward; the attention backward then
+    // spreads the gradient to every row through K and V, and the residual path carries d(x_mid) of the R rows only
+    const int l = c.llm_layers - 1;
+    const LlamaLayerW& w = e->lw[l];
+    GemmEpilogue ep;
+    ep.aux_mode = 2;
+    ep.aux = e->ll_gu;
+    ep.ldaux = 2 * f;
+    CK(G(e->hn, h, w.down_t, h, e->ll_dgu, 2 * f, R, f, h, ep, s));
+    CK(G(e->ll_dgu, 2 * f, w.gu_t, 2 * f, e->ll_dnorm, h, R, h, 2 * f, plain, s));
+    CK(rmsnorm_bwd(e->ll_dnorm, e->ll_xm, w.n2, e->ll_rstd2, e->hn, e->ll_dxm, R, h, s));
+    CK(G(e->ll_dxm, h, w.o_t, h, e->ll_dattn, h, R, h, h, plain, s));
+    VLA_CHECK_CUDA(cudaMemsetAsync(e->tr[0].d, 0, static_cast<size_t>(ML) * h * sizeof(bf16), s));
+    CK(scatter_rows(e->ll_dattn, e->sup_rows, e->tr[0].d, R, h, s));
+    VLA_CHECK_CUDA(cudaMemsetAsync(dxm, 0, static_cast<size_t>(ML) * h * sizeof(bf16), s));
+    CK(scatter_rows(e->ll_dxm, e->sup_rows, dxm, R, h, s));
+    if (hd == 128) {
+      CK(attention_bwd(la.qkv[l], la.attn_o[l], e->tr[0].d, la.lse[l], e->tr[0].delta, e->tr[0].qkv, e->kv_len, B, L, NH, hd, 1, e->rope_cos,
+                       e->rope_sin, L, s));
+    } else {
+      CK(attention_bwd(la.qkv[l], la.attn_o[l], e->tr[0].d, la.lse[l], e->tr[0].delta, e->tr[0].qkv, e->kv_len, B, L, NH, hd, 1, nullptr, nullptr,
+                       0, s));
+      CK(rope_inplace(e->tr[0].qkv, e->rope_cos, e->rope_sin, ML, L, NH, hd, -1, s));
+    }
+    CK(G(e->tr[0].qkv, 3 * h, w.qkv_t, 3 * h, e->tr[0].norm, h, ML, h, 3 * h, plain, s));
+    CK(rmsnorm_bwd(e->tr[0].norm, la.x[l], w.n1, la.rstd1[l], dxm, dx, ML, h, s));
+    l_first = l - 1;
+  } else {
+    VLA_CHECK_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(ML) * h * sizeof(bf16), s));
+    CK(scatter_rows(e->hn, e->sup_rows, dx, R, h, s));
+  }
+  for (int l = l_first; l >= 0; --l) {
     const LlamaLayerW& w = e->lw[l];
     if (e->fuse_swiglu_bwd) {   // d(act) = dX . W_down, with the SwiGLU backward fused: writes d(gate|up) directly
       GemmEpilogue ep;

@@ -195,7 +195,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const float dv = rbf(__uint_as_float(acc[q * 8 + t * 2 + k]));   // d(act) as the bf16 tensor autograd would hold
-          const float sig = 1.f / (1.f + expf(-gv[k]));
+          const float sig = sigmoid_fast(gv[k]);
           const float s_b = rbf(gv[k] * sig);
           const float ds = rbf(dv * uv[k]);
           rg[k] = ds * sig * (1.f + gv[k] * (1.f - sig));
@@ -356,7 +356,7 @@ __device__ __forceinline__ void epilogue_store_pair(const GemmArgs& g, const uin
     bf16* ap = e.act_out + static_cast<int64_t>(row) * e.ld_act + (col_a / 128) * 64 + (col_a & 63);
     float y[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) y[j] = rbf(xa[j] / (1.f + expf(-xa[j]))) * xb[j];
+    for (int j = 0; j < 32; ++j) y[j] = rbf(xa[j] * sigmoid_fast(xa[j])) * xb[j];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       reinterpret_cast<uint4*>(ap)[q] = make_uint4(pack_bf16x2(y[q * 8], y[q * 8 + 1]), pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]),

@@ -176,3 +176,40 @@ def test_engine_attack_trajectory(tiny_setup):
     assert abs(e_losses[0] - o_losses[0]) <= 2e-2 * abs(o_losses[0]) + 1e-3
     assert dev_.mean().item() < 2 * lr
     assert ((pe.cpu() - patch0).abs().max().item()) > 0
+
+
+@pytest.mark.parametrize("loss_kind", ["uada", "upa"])
+def test_last_layer_row_pruning_is_exact(tiny_setup, loss_kind, monkeypatch):
+    """The last decoder layer runs o_proj + MLP (forward and backward) on the supervised rows only.  Every op there is
+    row-wise, so scalars and predictions must be BIT-identical to the full-row path; the patch gradient is compared to fp32
+    round-off (the front end's backward accumulates the taps of a patch pixel with fp32 atomics, whose order varies)."""
+    from oracle import losses as ol
+    cfg, sd, _, B, T = tiny_setup
+    batch = synthetic_batch(cfg, B, T, seed=77, ragged=True)
+    if loss_kind == "uada":
+        batch["labels"] = ol.mask_labels_uada(batch["labels"].clone(), [0, 2, 5])
+    torch.manual_seed(1)
+    p = 10
+    patch = torch.rand(3, p, p).cuda()
+    from oracle import frontend as ofe
+    random.seed(3)
+    np.random.seed(3)
+    xy, theta = ofe.draw_placements(B, (cfg.img, cfg.img), (p, p), True)
+    outs = []
+    for prune in ("1", "0"):
+        monkeypatch.setenv("VLA_PRUNE_LAST", prune)
+        eng = VLAEngine(cfg, B, T)
+        eng.load_state_dict(sd)
+        eng.set_batch(batch["obs"], batch["input_ids"], batch["attention_mask"], batch["labels"])
+        eng.set_placements(xy[None], theta[None])
+        dp = torch.zeros_like(patch)
+        sc = torch.zeros(_lib.NUM_SCALARS, device="cuda")
+        pred = torch.zeros(eng.num_supervised, dtype=torch.int32, device="cuda")
+        eng.fwd_bwd(patch, 0, _lib.FE_WARP, SPECS[loss_kind], dp, sc, pred)
+        torch.cuda.synchronize()
+        outs.append((dp.cpu(), sc.cpu(), pred.cpu()))
+        del eng
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-8)
+    assert torch.equal(outs[0][1][:_lib.S_GRAD_MEAN], outs[1][1][:_lib.S_GRAD_MEAN])
+    assert torch.equal(outs[0][2], outs[1][2])
+    assert outs[0][0].abs().sum() > 0
