@@ -57,6 +57,13 @@ int vla_patch_frontend_fwd(const uint8_t* obs, const float* patch, const int32_t
 /* dpatch f32 [3,ph,pw] = d loss / d patch given dout bf16 [B,6,H,W]; overwrites dpatch */
 int vla_patch_frontend_bwd(const void* dout_bf16, const float* patch, const int32_t* xy, const float* theta,
                            float* dpatch, int B, int H, int W, int ph, int pw, int mode, const float* norm, void* stream);
+/* Eval-time paste: RandomPatchTransform.simulation_random_patch (appply_random_transform.py:43-78), the consumer-side
+ * paste used by the closed-loop evaluation (experiments/robot/libero/run_libero_eval_args_geo_batch.py:207).
+ * img / out uint8 [B,H,W,3] (device); patch f32 [3,ph,pw] in [0,1], quantised like ToPILImage (floor(p*255)); xy i32 [B,2]
+ * = fixed (x, y); theta f32 [B,2,3] = (S.R)[:2] of the fixed (angle, shx, shy), read when geometry != 0.
+ * out = canvas < 0 ? img : uint8(canvas). */
+int vla_patch_sim_paste(const uint8_t* img, const float* patch, const int32_t* xy, const float* theta, uint8_t* out,
+                        int B, int H, int W, int ph, int pw, int geometry, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Loss heads (UADA.py:145-147,381-418; UADA_ddp.py:99-136,203-206; UPA.py:145-150,367-387; TMA.py:148) */

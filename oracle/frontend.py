@@ -92,3 +92,21 @@ def apply_patch_batch(obs_u8, patch, xy, theta, mode, mean, std):
         im1 = (im[None] - m1[None, :, None, None]) / s1[None, :, None, None]
         out.append(torch.cat([im0, im1], dim=1))
     return torch.cat(out, dim=0)
+
+
+def simulation_paste(image_u8, patch, geometry, angle=1, shx=0.1, shy=0.1, position=(0, 0)):
+    """Restatement of ``simulation_random_patch`` (appply_random_transform.py:43-78): image uint8 ndarray [H,W,3], patch f32
+    [3,ph,pw] in [0,1] -> uint8 ndarray [H,W,3].  ToPILImage on a float tensor is ``mul(255).byte()`` (truncation)."""
+    image = torch.from_numpy(np.asarray(image_u8)).permute(2, 0, 1)
+    C, H, W = image.shape
+    canvas = torch.ones(C, H, W) * -100
+    ph, pw = patch.shape[1:]
+    q = patch.detach().mul(255).byte()
+    x, y = position
+    canvas[:, y:y + ph, x:x + pw] = q
+    if geometry:
+        m = torch.tensor(np.dot(shear_matrix(shx, shy), rotation_matrix(angle)))
+        grid = F.affine_grid(m[:2, :].unsqueeze(0), (1, C, H, W), align_corners=False)
+        canvas = F.grid_sample(canvas.unsqueeze(0), grid, align_corners=False, padding_mode="border")
+    out = torch.where(canvas < 0, image, canvas)
+    return out.squeeze(0).permute(1, 2, 0).numpy().astype(np.uint8)

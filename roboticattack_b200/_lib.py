@@ -50,6 +50,8 @@ SIGNATURES = {
     "vla_profile_gemm_end": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int)]),
     "vla_patch_frontend_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_int, POINTER(c_float), c_void_p]),
+    "vla_patch_sim_paste": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p]),
     "vla_patch_frontend_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_int, POINTER(c_float), c_void_p]),
     "vla_loss_head": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(LossParams), c_void_p, c_void_p,

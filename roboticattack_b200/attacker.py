@@ -14,6 +14,7 @@ from __future__ import annotations
 import math
 import os
 import pickle
+import random
 from typing import Iterable, Optional
 
 import numpy as np
@@ -90,6 +91,27 @@ class AttackEngineHost:
         self.grad = torch.zeros_like(self.patch)
         self.opt_step = 0
 
+    def state_dict(self, outer_iter: int, sched_step: int) -> dict:
+        """Everything a restart needs beyond ``patch.pt`` (the reference cannot resume): the optimiser moments
+        and step counter, the outer / scheduler position and the three host RNG streams that drive placements and init."""
+        return {"patch": self.patch.detach().cpu(), "m": self.m.detach().cpu(), "v": self.v.detach().cpu(),
+                "opt_step": int(self.opt_step), "outer_iter": int(outer_iter), "sched_step": int(sched_step),
+                "py_random": random.getstate(), "np_random": np.random.get_state(), "torch_rng": torch.get_rng_state()}
+
+    def load_state_dict(self, st: dict):
+        """Restores patch / moments / counters and the RNG streams; returns (next outer iteration, scheduler step)."""
+        if self.patch is not None and tuple(st["patch"].shape) != tuple(self.patch.shape):
+            raise ValueError(f"resume: patch shape {tuple(st['patch'].shape)} != configured {tuple(self.patch.shape)}")
+        self.patch = st["patch"].to(self.device, torch.float32).contiguous()
+        self.m = st["m"].to(self.device, torch.float32).contiguous()
+        self.v = st["v"].to(self.device, torch.float32).contiguous()
+        self.grad = torch.zeros_like(self.patch)
+        self.opt_step = int(st["opt_step"])
+        random.setstate(st["py_random"])
+        np.random.set_state(st["np_random"])
+        torch.set_rng_state(st["torch_rng"])
+        return int(st["outer_iter"]) + 1, int(st["sched_step"])
+
     def run_inner_loop(self, batch, n_inner, fe_mode, loss: LossSpec, lr, opt_kind, clip_l1=0.0, do_step=True,
                        accumulate=None):
         """One outer iteration. Returns (scalars [n_inner, 8] on the host, pred_ids [R] of the last inner step)."""
@@ -144,11 +166,15 @@ def _decoded_pairs(pred_ids: torch.Tensor, labels: torch.Tensor):
 class _AttackerBase(object):
     KIND = "UADA"
 
+    STATE_FILE = "attack_state.pt"
+
     def __init__(self, vla, processor=None, save_dir="", optimizer="pgd", resize_patch=False, cfg=None, device="cuda:0",
-                 engine_factory=None):
+                 engine_factory=None, resume=None):
         self.vla = vla
         self.processor = processor
         self.save_dir = save_dir
+        # resume: a run sub-directory written by this class (e.g. <save_dir>/last) or its attack_state.pt; env VLA_ATTACK_RESUME
+        self.resume = resume or os.environ.get("VLA_ATTACK_RESUME") or None
         self.optimizer = optimizer
         if resize_patch:
             raise NotImplementedError("resize_patch=True is dead code in the reference (appply_random_transform.py:113-118)")
@@ -164,11 +190,23 @@ class _AttackerBase(object):
     def mask_labels(self, labels, maskidx):
         return lab.mask_labels_uada(labels, maskidx)
 
-    def _save_patch(self, patch, sub):
+    def _save_patch(self, patch, sub, outer_iter=None, sched_step=0):
         d = os.path.join(self.save_dir, sub)
         os.makedirs(d, exist_ok=True)
         torch.save(patch.detach().cpu(), os.path.join(d, "patch.pt"))     # fp32 [3,h,w] CPU tensor, as the reference
+        if outer_iter is not None:   # restart state next to it (not in the reference's run-dir format; ignored by its consumers)
+            torch.save(self.host.state_dict(outer_iter, sched_step), os.path.join(d, self.STATE_FILE))
         return d
+
+    def _maybe_resume(self):
+        """-> (first outer iteration to run, scheduler step).  (0, 0) without ``resume``."""
+        if not self.resume:
+            return 0, 0
+        path = self.resume
+        if os.path.isdir(path):
+            path = os.path.join(path, self.STATE_FILE)
+        st = torch.load(path, map_location="cpu", weights_only=False)
+        return self.host.load_state_dict(st)
 
     def _dump(self, **lists):
         os.makedirs(self.save_dir, exist_ok=True)
@@ -210,10 +248,11 @@ class UADAAttacker(_AttackerBase):
         fe_mode = _lib.FE_WARP if geometry else _lib.FE_PASTE20
         opt_kind = _lib.OPT_ADAMW if self.optimizer == "adamW" else _lib.OPT_PGD
         total = int(num_iter / accumulate_steps)
-        sched_step = 0
+        start_iter, sched_step = self._maybe_resume()
+        self._sched_step = sched_step
         train_it = iter(train_dataloader)
         val_it = iter(val_dataloader) if val_dataloader is not None else None
-        for i in range(num_iter):
+        for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
             data = dict(data)
             data["labels"] = self.mask_labels(data["labels"].clone(), maskidx)
@@ -224,6 +263,7 @@ class UADAAttacker(_AttackerBase):
             self.train_UAD += scalars[:, _lib.S_UAD].tolist()
             if self.optimizer == "adamW" and ((i + 1) % accumulate_steps == 0):
                 sched_step += 1
+            self._sched_step = sched_step
             pr, gt = _decoded_pairs(pred, data["labels"])
             rd = lab.relative_distance(pr, gt).view(-1, max(1, len(maskidx)))
             log = {"TRAIN_attack_loss(CE)": scalars[-1, _lib.S_CE].item(),
@@ -237,6 +277,8 @@ class UADAAttacker(_AttackerBase):
             self._log(args, log, i)
             if i % self.val_every == 0 and val_dataloader is not None:
                 val_it = self._validate(i, val_it, val_dataloader, maskidx, fe_mode, loss, args)
+            elif i % self.val_every == 0 and self.save_dir:
+                self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
         return h.patch.detach().cpu()
 
     def _validate(self, i, val_it, val_dataloader, maskidx, fe_mode, loss, args):
@@ -263,7 +305,7 @@ class UADAAttacker(_AttackerBase):
         if avg_mse < self.MSE_Distance_best:
             self.MSE_Distance_best = avg_mse
             self._save_patch(h.patch, str(i))
-        self._save_patch(h.patch, "last")
+        self._save_patch(h.patch, "last", outer_iter=i, sched_step=getattr(self, "_sched_step", 0))
         self.val_CE_loss.append(avg_ce)
         self.val_MSE_Distance.append(avg_mse)
         self.val_UAD.append(avg_uad)
@@ -301,10 +343,10 @@ class UPAAttacker(_AttackerBase):
         fe_mode = _lib.FE_WARP if geometry else _lib.FE_PASTE20
         opt_kind = _lib.OPT_ADAMW if self.optimizer == "adamW" else _lib.OPT_PGD
         total = int(num_iter / accumulate_steps)
-        sched_step = 0
+        start_iter, sched_step = self._maybe_resume()
         acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
         train_it = iter(train_dataloader)
-        for i in range(num_iter):
+        for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
             data = dict(data)
             labels = data["labels"].clone()
@@ -326,7 +368,7 @@ class UPAAttacker(_AttackerBase):
             self.loss_buffer.append(log["TRAIN_attack_loss(CE)"])
             self._log(args, log, i)
             if i % self.val_every == 0:
-                self._save_patch(h.patch, "last")
+                self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
                 self._dump(train_CE_loss=self.train_CE_loss)
         return h.patch.detach().cpu()
 
@@ -350,10 +392,10 @@ class TMAAttacker(_AttackerBase):
         fe_mode = _lib.FE_WARP if geometry else _lib.FE_FIX          # paste_patch_fix when no geometry (TMA.py:133-135)
         opt_kind = _lib.OPT_ADAMW if self.optimizer == "adamW" else _lib.OPT_PGD
         total = int(num_iter / accumulate_steps)
-        sched_step = 0
+        start_iter, sched_step = self._maybe_resume()
         acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
         train_it = iter(train_dataloader)
-        for i in range(num_iter):
+        for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
             data = dict(data)
             data["labels"] = lab.tma_labels(data["labels"], target)
@@ -373,7 +415,7 @@ class TMAAttacker(_AttackerBase):
             self.loss_buffer.append(log["TRAIN_attack_loss(CE)"])
             self._log(args, log, i)
             if i % self.val_every == 0:
-                self._save_patch(h.patch, "last")
+                self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
                 self._dump(train_CE_loss=self.train_CE_loss, train_inner_avg_loss=self.train_inner_avg_loss)
         return h.patch.detach().cpu()
 
@@ -386,10 +428,10 @@ class UADADDPAttacker(_AttackerBase):
 
     def __init__(self, vla, dataloaders=None, save_dir="", resize_patch=False, patch_size=[3, 50, 50], lr=0.01, bs=1,
                  warmup=20, num_iter=10000, maskidx=[], innerLoop=1, geometry=True, use_wandb=False, MSE_weights=1,
-                 cfg=None, device=None, engine_factory=None, backend="nccl"):
+                 cfg=None, device=None, engine_factory=None, backend="nccl", resume=None):
         rank = int(os.environ.get("LOCAL_RANK", 0))
         device = device or f"cuda:{rank}"
-        super().__init__(vla, None, save_dir, "adamW", resize_patch, cfg=cfg, device=device, engine_factory=engine_factory)
+        super().__init__(vla, None, save_dir, "adamW", resize_patch, cfg=cfg, device=device, engine_factory=engine_factory, resume=resume)
         self.backend = backend
         self.dataloaders = dataloaders
         self.patch_size, self.lr, self.bs, self.warmup, self.num_iter = patch_size, lr, bs, warmup, num_iter
@@ -411,11 +453,12 @@ class UADADDPAttacker(_AttackerBase):
         h = self.host
         train_dataloader = train_dataloader or self.dataloaders[0]
         h.init_patch(self.patch_size)
+        start_iter, _ = self._maybe_resume()   # every rank restores the same replicated state (scheduler step = outer index)
         loss = LossSpec(_lib.LOSS_UADA_DDP, mse_weight=float(self.MSE_weights))
         fe_mode = _lib.FE_WARP if self.geometry else _lib.FE_PASTE20
         logs = []
-        for i, data in enumerate(train_dataloader):
-            if i == self.num_iter:
+        for i, data in enumerate(train_dataloader, start=start_iter):
+            if i >= self.num_iter:
                 break
             data = dict(data)
             data["labels"] = self.mask_labels(data["labels"].clone(), self.maskidx)
@@ -433,6 +476,6 @@ class UADADDPAttacker(_AttackerBase):
                    "TRAIN_UAD": pack[2].item(), "TRAIN_patch_gradient": pack[3].item(), "TRAIN_LR": cur_lr}
             logs.append(log)
             if rank == 0 and i % self.val_every == 0 and self.save_dir:
-                self._save_patch(h.patch, "last")
+                self._save_patch(h.patch, "last", outer_iter=i, sched_step=i + 1)
         self.train_logs = logs
         return h.patch.detach().cpu()

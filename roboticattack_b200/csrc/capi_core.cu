@@ -56,6 +56,11 @@ int vla_patch_frontend_bwd(const void* dout, const float* patch, const int32_t* 
   VLA_REQUIRE(dout && dpatch && norm, "vla_patch_frontend_bwd: null argument");
   return patch_frontend_bwd(CBF(dout), patch, xy, theta, dpatch, B, H, W, ph, pw, mode, make_norm(norm), S(stream));
 }
+int vla_patch_sim_paste(const uint8_t* img, const float* patch, const int32_t* xy, const float* theta, uint8_t* out, int B, int H,
+                        int W, int ph, int pw, int geometry, void* stream) {
+  VLA_REQUIRE(img && patch && xy && out && (theta || !geometry), "vla_patch_sim_paste: null argument");
+  return patch_sim_paste(img, patch, xy, theta, out, B, H, W, ph, pw, geometry, S(stream));
+}
 int vla_loss_head(const float* logits, const int32_t* meta, int R, int V, int B, const vla_loss_params* lp, float* row_stats,
                   void* dlogits, float* scalars, int32_t* pred_ids, void* stream) {
   VLA_REQUIRE(logits && meta && lp && row_stats && dlogits && scalars && pred_ids, "vla_loss_head: null argument");

@@ -785,6 +785,16 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
   LossParams lp{lp_c->kind, lp_c->mse_weight, lp_c->alpha, lp_c->belta, lp_c->ce_scale};
   GemmEpilogue plain;
 
+  // VLA_PHASE_TIMING=1 (diagnostics): events at the phase boundaries, printed after a synchronise
+  static const bool phase_timing = getenv("VLA_PHASE_TIMING") && atoi(getenv("VLA_PHASE_TIMING")) != 0;
+  static cudaEvent_t pev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  auto mark = [&](int i) {
+    if (!phase_timing) return;
+    if (!pev[i]) cudaEventCreate(&pev[i]);
+    cudaEventRecord(pev[i], s);
+  };
+  mark(0);
+
   // ---------------- forward ----------------
   CK(patch_frontend_fwd(e->obs, patch, xy, th, e->px, B, H, H, ph, pw, fe_mode, e->nrm, s));
   CK(im2col_patches(e->px, e->va[0].a_col, e->va[1].a_col, B, H, H, c.patch, e->kpad, s));
@@ -809,6 +819,7 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
     VLA_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
     VLA_CHECK_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
   }
+  mark(1);
   {
     GemmEpilogue ep;
     ep.bias = e->pj_b[0];
@@ -900,6 +911,7 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
   CK(loss_head_fwd_bwd(e->logits, e->meta, R, V, B, lp, e->row_stats, e->dlogits, scalars, pred_ids, s));
   if (flags & VLA_FLAG_FORWARD_ONLY) return 0;
 
+  mark(2);
   // ---------------- backward (input gradients only) ----------------
   CK(G(e->dlogits, V, e->lm_head_t, V, e->tr[0].norm, h, R, h, V, plain, s));
   CK(rmsnorm_bwd(e->tr[0].norm, e->hs, e->final_norm, e->rstd_f, nullptr, e->hn, R, h, s));
@@ -964,6 +976,7 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
     CK(G(e->tr[0].qkv, 3 * h, w.qkv_t, 3 * h, e->tr[0].norm, h, ML, h, 3 * h, plain, s));
     CK(rmsnorm_bwd(e->tr[0].norm, la.x[l], w.n1, la.rstd1[l], dxm, dx, ML, h, s));
   }
+  mark(3);
   // d X0 rows 1..P -> projector backward
   CK(copy_rows(dx, h, L, 1, e->tr[0].c, h, P, 0, B, P, h, s));
   {
@@ -998,8 +1011,17 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
     VLA_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
     VLA_CHECK_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
   }
+  mark(4);
   CK(col2im_patches(e->va[0].a_col, e->va[1].a_col, e->dpx, B, H, H, c.patch, e->kpad, s));
   CK(patch_frontend_bwd(e->dpx, patch, xy, th, dpatch, B, H, H, ph, pw, fe_mode, e->nrm, s));
+  mark(5);
+  if (phase_timing) {
+    cudaEventSynchronize(pev[5]);
+    float t[5];
+    for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], pev[i], pev[i + 1]);
+    fprintf(stderr, "[phase ms] front+vit_fwd %.3f | projector+llm_fwd+loss %.3f | llm_bwd %.3f | projector+vit_bwd %.3f | tail %.3f\n", t[0],
+            t[1], t[2], t[3], t[4]);
+  }
   return 0;
 }
 

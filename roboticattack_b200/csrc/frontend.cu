@@ -175,6 +175,51 @@ __global__ void patch_frontend_bwd_kernel(const bf16* __restrict__ dout, const f
   }
 }
 
+
+// Eval-time paste (RandomPatchTransform.simulation_random_patch, appply_random_transform.py:43-78): the patch is
+// quantised to uint8 (ToPILImage: floor(p * 255)), pasted at a FIXED position on a -100 canvas, optionally warped by a
+// FIXED affine map, composited with `canvas < 0 ? image : canvas` and truncated back to uint8 HWC (numpy astype).
+// One thread per pixel; 3 B read + 3 B written per pixel.
+__global__ void patch_sim_paste_kernel(const uint8_t* __restrict__ img, const float* __restrict__ patch,
+                                       const int* __restrict__ xy, const float* __restrict__ theta, uint8_t* __restrict__ out,
+                                       int B, int H, int W, int ph, int pw, int geometry) {
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<int64_t>(B) * H * W) return;
+  const int j = static_cast<int>(idx % W);
+  const int i = static_cast<int>((idx / W) % H);
+  const int b = static_cast<int>(idx / (static_cast<int64_t>(W) * H));
+  const int px = xy[b * 2 + 0], py = xy[b * 2 + 1];
+  const uint8_t* ip = img + idx * 3;
+  uint8_t* op = out + idx * 3;
+  auto q_at = [&](const float* pc, int yy, int xx) -> float {   // quantised canvas
+    if (yy >= H || xx >= W) return 0.f;
+    const int u = yy - py, v = xx - px;
+    if (u >= 0 && u < ph && v >= 0 && v < pw) return truncf(__ldg(pc + u * pw + v) * 255.f);
+    return -100.f;
+  };
+  Taps t;
+  bool near = true;
+  if (geometry) {
+    t = warp_taps(theta + b * 6, i, j, H, W);
+    near = (t.x0 + 1 >= px) && (t.x0 < px + pw) && (t.y0 + 1 >= py) && (t.y0 < py + ph);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* pc = patch + c * ph * pw;
+    float v = -100.f;
+    if (geometry) {
+      if (near) {
+        v = q_at(pc, t.y0, t.x0) * t.nw;
+        v += q_at(pc, t.y0, t.x0 + 1) * t.ne;
+        v += q_at(pc, t.y0 + 1, t.x0) * t.sw;
+        v += q_at(pc, t.y0 + 1, t.x0 + 1) * t.se;
+      }
+    } else {
+      v = q_at(pc, i, j);
+    }
+    op[c] = (v < 0.f) ? ip[c] : static_cast<uint8_t>(v);   // torch.where(canvas < 0, image, canvas).astype(uint8)
+  }
+}
 }  // namespace
 
 int patch_frontend_fwd(const uint8_t* obs, const float* patch, const int* xy, const float* theta, bf16* out, int B,
@@ -200,6 +245,17 @@ int patch_frontend_bwd(const bf16* dout, const float* patch, const int* xy, cons
   const int threads = 256;
   patch_frontend_bwd_kernel<<<static_cast<unsigned>(ceil_div64(n, threads)), threads, 0, stream>>>(
       dout, patch, xy, theta, dpatch, B, H, W, ph, pw, mode, nrm);
+  VLA_LAUNCH_CHECK();
+  ++g_vla_launch_count;
+  return 0;
+}
+
+int patch_sim_paste(const uint8_t* img, const float* patch, const int* xy, const float* theta, uint8_t* out, int B, int H,
+                    int W, int ph, int pw, int geometry, cudaStream_t stream) {
+  VLA_REQUIRE(B > 0 && H > 0 && W > 0 && ph > 0 && pw > 0 && ph <= H && pw <= W, "patch_sim_paste: bad shape B=%d %dx%d patch %dx%d", B,
+              H, W, ph, pw);
+  const int64_t n = static_cast<int64_t>(B) * H * W;
+  patch_sim_paste_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(img, patch, xy, theta, out, B, H, W, ph, pw, geometry);
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;

@@ -14,6 +14,10 @@ int patch_frontend_fwd(const uint8_t* obs, const float* patch, const int* xy, co
 int patch_frontend_bwd(const bf16* dout, const float* patch, const int* xy, const float* theta, float* dpatch, int B,
                        int H, int W, int ph, int pw, int mode, const FrontendNorm& nrm, cudaStream_t stream);
 
+// eval-time paste (simulation_random_patch): img / out uint8 [B,H,W,3]; patch f32 [3,ph,pw] in [0,1] (quantised in-kernel)
+int patch_sim_paste(const uint8_t* img, const float* patch, const int* xy, const float* theta, uint8_t* out, int B, int H,
+                    int W, int ph, int pw, int geometry, cudaStream_t stream);
+
 // ---- layout / elementwise (elementwise.cu) --------------------------------------------------------------
 // px [B,6,H,W] -> per-tower im2col rows [B*np, kpad] (k = c*P*P + ky*P + kx, zero padded to kpad)
 int im2col_patches(const bf16* px, bf16* a_dino, bf16* a_sig, int B, int H, int W, int P, int kpad, cudaStream_t s);

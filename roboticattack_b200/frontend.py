@@ -24,6 +24,15 @@ def _as_uint8_batch(images, device):
     return t.to(device).contiguous()
 
 
+def fixed_affine(angle, shx, shy):
+    """theta = (S . R)[:2] in float32 for a fixed rotation (degrees) and shear (appply_random_transform.py:26-41,69-75)."""
+    t = np.radians(angle)
+    c, s = np.cos(t), np.sin(t)
+    R = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]], dtype=np.float32)
+    S = np.array([[1, shx, 0], [shy, 1, 0], [0, 0, 1]], dtype=np.float32)
+    return np.ascontiguousarray(np.dot(S, R)[:2, :], dtype=np.float32)
+
+
 class _FrontendFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, patch, obs, xy, theta, mode, norm):
@@ -90,3 +99,18 @@ class RandomPatchTransform:
 
     def im_process(self, images, mean=None, std=None):
         return self._run(images, None, mean, std, _lib.FE_NONE, False)
+
+    def simulation_random_patch(self, image, patch, geometry=False, colorjitter=False, angle=1, shx=0.1, shy=0.1, position=(0, 0)):
+        """Eval-time paste (appply_random_transform.py:43-78): ``image`` uint8 ndarray [H,W,3] -> uint8 ndarray [H,W,3] with the
+        patch quantised to uint8 and pasted at the FIXED ``position`` = (x, y), warped by the FIXED (angle, shx, shy) when
+        ``geometry``.  ``colorjitter`` is accepted and ignored, as in the reference.  Runs ``vla_patch_sim_paste`` on the GPU."""
+        img = torch.from_numpy(np.ascontiguousarray(image, dtype=np.uint8))[None].to(self.device)
+        _, H, W, _ = img.shape
+        p = patch.detach().to(self.device, torch.float32).contiguous()
+        xy = torch.tensor([[int(position[0]), int(position[1])]], dtype=torch.int32, device=self.device)
+        theta = torch.from_numpy(fixed_affine(angle, shx, shy)[None]).to(self.device)
+        out = torch.empty_like(img)
+        _lib.check(_lib.lib().vla_patch_sim_paste(_lib.ptr(img), _lib.ptr(p), _lib.ptr(xy), _lib.ptr(theta), _lib.ptr(out), 1, H, W,
+                                                  p.shape[1], p.shape[2], int(bool(geometry)), _lib.cur_stream()),
+                   "vla_patch_sim_paste")
+        return out[0].cpu().numpy()

@@ -74,3 +74,55 @@ def test_synthetic_batch_layout():
 def test_flop_model_matches_survey():
     f = flops_per_sample(openvla_7b(), 33)
     assert abs(f["iter"] / 1e9 - 8380.8) < 0.5 and abs(f["f_lin"] / 1e9 - 4136.17) < 0.1
+
+
+def test_resume_reproduces_uninterrupted_run(tmp_path):
+    """a run restarted from <save_dir>/last/attack_state.pt (patch, Adam moments, step counters and the three
+    host RNG streams) ends with the same patch, bit for bit, as the uninterrupted run (CPU oracle engine standing in for the GPU)."""
+    import os
+    import random
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from roboticattack_b200.attacker import UADAAttacker
+    from roboticattack_b200.config import tiny
+    from roboticattack_b200.synthetic import synthetic_batch
+    from roboticattack_b200.weights import random_state_dict
+    cfg = tiny(img=28, llm_layers=1, vit_depth=2)
+    sd = random_state_dict(cfg, seed=0, dtype=torch.float32, init="test")
+    batches = []
+    for i in range(4):
+        b = synthetic_batch(cfg, 2, 14, seed=50 + i)
+        batches.append({"pixel_values": b["obs"], "input_ids": b["input_ids"], "attention_mask": b["attention_mask"], "labels": b["labels"]})
+    kw = dict(num_iter=4, patch_size=[3, 8, 8], lr=2e-3, maskidx=[0, 1], warmup=1, geometry=True, innerLoop=2)
+
+    def make(save_dir, resume=None):
+        a = UADAAttacker(sd, save_dir=save_dir, optimizer="adamW", cfg=cfg, device="cpu", engine_factory=OracleEngine, resume=resume)
+        a.val_every = 1
+        return a
+
+    def seed():
+        random.seed(42)
+        np.random.seed(42)
+        torch.manual_seed(42)
+
+    seed()
+    full = make(str(tmp_path / "full")).patchattack_unconstrained(batches, None, **kw)
+    seed()
+    part_dir = str(tmp_path / "part")
+
+    class Preempted(Exception):
+        pass
+
+    def crashing_loader():            # the job dies while fetching the third batch
+        yield batches[0]
+        yield batches[1]
+        raise Preempted()
+
+    with pytest.raises(Preempted):
+        make(part_dir).patchattack_unconstrained(crashing_loader(), None, **kw)
+    assert os.path.exists(os.path.join(part_dir, "last", "patch.pt")) and os.path.exists(os.path.join(part_dir, "last", "attack_state.pt"))
+    random.seed(1), np.random.seed(1), torch.manual_seed(1)      # a restarted process has unrelated RNG state
+    resumed = make(str(tmp_path / "resumed"), resume=os.path.join(part_dir, "last")).patchattack_unconstrained(batches[2:], None, **kw)
+    assert torch.equal(full, resumed)
+    assert not torch.equal(full, torch.load(os.path.join(part_dir, "last", "patch.pt")))

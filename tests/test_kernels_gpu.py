@@ -454,3 +454,28 @@ def test_patch_update_vs_oracle(kind, clip):
     if kind == "adamw":
         torch.testing.assert_close(md.cpu(), opt.m, rtol=1e-4, atol=1e-8)      # fma vs mul+add on cancelling terms
         torch.testing.assert_close(vd.cpu(), opt.v, rtol=1e-4, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------ eval-time paste
+@pytest.mark.parametrize("tag", ["s64_plain", "s64_geo", "s224_plain", "s224_geo", "s224_geo_default"])
+def test_simulation_random_patch_vs_reference(tag):
+    """RandomPatchTransform.simulation_random_patch (vla_patch_sim_paste) against the reference's own output.  Integer result:
+    exact without the warp; with it, the bilinear blend is truncated to uint8, so a 1-ulp difference of the fp32 blend may
+    flip a value by one (and a canvas value within an ulp of 0 may flip image <-> canvas): <= 0.2 % of the bytes may differ,
+    by at most 1 unless the pixel sits on the patch border."""
+    import os
+    from roboticattack_b200.frontend import RandomPatchTransform
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_sim.npz"))
+    geo, angle, shx, shy, x, y = g[f"{tag}_args"]
+    t = RandomPatchTransform("cuda:0")
+    out = t.simulation_random_patch(g[f"{tag}_img"], torch.from_numpy(g[f"{tag}_patch"]), geometry=bool(geo), angle=angle, shx=shx,
+                                    shy=shy, position=(int(x), int(y)))
+    ref = g[f"{tag}_out"]
+    assert out.dtype == np.uint8 and out.shape == ref.shape
+    if not geo:
+        assert np.array_equal(out, ref)
+        return
+    diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    frac = (diff > 0).mean()
+    assert frac <= 2e-3, f"{frac:.4%} of the bytes differ"
+    assert (diff > 1).mean() <= 2e-4, "differences beyond one level only on isolated border pixels"

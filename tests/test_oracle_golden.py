@@ -132,3 +132,20 @@ def test_adamw_rule_matches_definition():
     # first step: m = 0.1 g, v = 0.001 g^2, step = lr*sqrt(0.001)/0.1
     expect = p0 - 2e-3 * (0.001 ** 0.5) / 0.1 * (0.1 * g) / ((0.001 * g * g).sqrt() + 1e-6)
     torch.testing.assert_close(p, expect, rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ eval-time paste
+SIM_CASES = ["s64_plain", "s64_geo", "s224_plain", "s224_geo", "s224_geo_default"]
+
+
+@pytest.mark.parametrize("tag", SIM_CASES)
+def test_simulation_paste_matches_reference(tag):
+    """oracle.frontend.simulation_paste == the reference's own simulation_random_patch (tests/golden/make_golden_sim.py)."""
+    import os
+    from oracle import frontend as ofe
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_sim.npz"))
+    geo, angle, shx, shy, x, y = g[f"{tag}_args"]
+    out = ofe.simulation_paste(g[f"{tag}_img"], torch.from_numpy(g[f"{tag}_patch"]), bool(geo), angle, shx, shy, (int(x), int(y)))
+    assert out.dtype == np.uint8 and out.shape == g[f"{tag}_out"].shape
+    assert np.array_equal(out, g[f"{tag}_out"])
+    assert (out != g[f"{tag}_img"]).any(), "the patch must be visible"
