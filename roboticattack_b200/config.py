@@ -135,4 +135,7 @@ def flops_per_sample(cfg: OpenVLAConfig, text_len: int, supervised_rows: int = 8
     head = 2 * supervised_rows * hd * cfg.llm.vocab
     f_lin = dl + sl + proj + llm_lin + head
     f_att = da + sa + llm_att
-    return {"f_lin": f_lin, "f_att": f_att, "fwd": f_lin + f_att, "iter": 2 * f_lin + 3 * f_att}
+    # what the engine executes: the last decoder layer's o_proj + MLP run on the supervised rows only (engine.cu, exact)
+    saved = 2 * (L - supervised_rows) * (hd * hd + 3 * hd * cfg.llm.ffn)
+    return {"f_lin": f_lin, "f_att": f_att, "fwd": f_lin + f_att, "iter": 2 * f_lin + 3 * f_att,
+            "iter_executed": 2 * (f_lin - saved) + 3 * f_att}
