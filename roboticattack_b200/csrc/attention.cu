@@ -605,7 +605,7 @@ int g_attn_impl = -1;
 static int attn_impl() {
   if (g_attn_impl < 0) {
     const char* e = getenv("VLA_ATTN_IMPL");
-    g_attn_impl = e ? (atoi(e) & 3) : 2;
+    g_attn_impl = e ? (atoi(e) & 7) : 2;
   }
   return g_attn_impl;
 }
@@ -613,7 +613,8 @@ static int attn_impl() {
 int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                   cudaStream_t s) {
   VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
-  if ((attn_impl() & 1) && attention_tc_supported(N, hd))
+  if ((attn_impl() & 1) && attention_fwd_tc2_supported(N, hd)) return attention_fwd_tc2(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
+  if ((attn_impl() & 4) && attention_tc_supported(N, hd))   // the earlier one-shot kernel (kept for comparison)
     return attention_fwd_tc(qkv, o, lse, kv_len, B, N, H, hd, causal, 1.f / sqrtf(static_cast<float>(hd)), s);
   if (hd <= 64) return launch_fwd<64>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   if (hd <= 80) return launch_fwd<80>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);

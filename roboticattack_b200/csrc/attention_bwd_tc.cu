@@ -386,6 +386,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const uint32_t sPt = sPD + r * 128;   // MODE_DKV only
     const int D = H * a.hd;
     int g = 0, n_it = 0;
+    bool store_pending = false;
+    auto drain_store = [&]() {
+      if (store_pending) {
+        if (threadIdx.x == 0) tma_store_wait_read();
+        softmax_bar();
+        store_pending = false;
+      }
+    };
     Item it;
     for (int i = 0; get_item(i, it); ++i) {
       const int srow = it.t0 + r;                     // query (MODE_DQ) or key (MODE_DKV) index of this thread's row
@@ -408,6 +416,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         STAMP(MODE, threadIdx.x == 0, 4 + 2 * g);
         tc_fence_after();
         if (MODE == MODE_DKV) mbar_wait(bar_full(slot), (g / RING) & 1);   // acquire the producer's lse / delta stores
+        if (s == 0) drain_store();
         if (half * 32 < ncols) {
           if (warp_active) {
             uint32_t sv[32], dv[32];
@@ -493,6 +502,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         tc_fence_after();
       }
       STAMP(MODE, threadIdx.x == 0 && i == 0, 60);
+      drain_store();   // (items without steps reach the staging writes directly)
       constexpr int NOUT = (MODE == MODE_DKV) ? 2 : 1;
       constexpr bool SEQ = NOUT * SM::STAT_BYTES > SM::PD_BYTES;   // stage the two results one after the other
 #pragma unroll
@@ -577,9 +587,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                     tma_store_4d(&map_dqkv, stg + p * (TILE * 128) + rb * 8192, p * 64, head_out, it.t0 + rb * 64, it.b);
             }
             tma_store_commit();
-            tma_store_wait_read();
+            if (oi != NOUT - 1) tma_store_wait_read();
           }
-          softmax_bar();   // staging area (= P / dS buffers) reusable
+          // The staging area (= P / dS buffers) is reusable once the store has read it.  Between two results of one item
+          // that wait is taken here; after the last result it is deferred to the next item's first step (drain_store),
+          // by which time the store has long finished, so the epilogue does not stall on it.
+          if (oi != NOUT - 1) softmax_bar();
+          else store_pending = true;
         }
       }
       STAMP(MODE, threadIdx.x == 0 && i == 0, 61);

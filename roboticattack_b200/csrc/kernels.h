@@ -69,6 +69,10 @@ int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B
 bool attention_tc_supported(int N, int hd);
 int attention_fwd_tc(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                      float scale, cudaStream_t s);
+// persistent streaming tcgen05 forward (attention_fwd_tc2.cu): head dims 64 / 72 / 128, any N
+bool attention_fwd_tc2_supported(int N, int hd);
+int attention_fwd_tc2(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
+                      cudaStream_t s);
 // tcgen05 backward (attention_bwd_tc.cu): head dims 64 / 72 / 128, any N; same contract as attention_bwd.
 bool attention_bwd_tc_supported(int N, int hd);
 int attention_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,

@@ -179,7 +179,7 @@ def test_rmsnorm(M, d):
                                                     (1, 1, 1, 64, 1, False), (2, 700, 2, 128, 1, True),
                                                     (2, 257, 2, 72, 1, True), (1, 97, 3, 72, 0, False)])
 def test_attention(B, N, H, hd, causal, ragged, impl):
-    """impl 0 = legacy mma.sync kernels; 3 = tcgen05 forward (hd 64 / 128, N <= 320) + tcgen05 backward (hd 64 / 72 / 128)."""
+    """impl 0 = legacy mma.sync kernels; 3 = persistent tcgen05 forward + backward (hd 64 / 72 / 128, any N)."""
     _lib.check(L.vla_attention_set_impl(impl))
     try:
         _attention_case(B, N, H, hd, causal, ragged)
