@@ -94,30 +94,44 @@ __device__ __forceinline__ unsigned long long gtime() {
 #endif
 
 // ---------------------------------------------------------------------------------------------------------
-// delta[b, h, n] = sum_c dO[b, n, h, c] * O[b, n, h, c]   (one warp per (row, head); fp32)
+// delta[b, h, n] = sum_c dO[b, n, h, c] * O[b, n, h, c]   (fp32).  One CTA per row (b, n): warp w takes heads w, w + 8, ...
+// (32-bit index math only; all of a warp's loads are issued before the reductions), lane l takes 4 columns.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
-                                                         float* __restrict__ delta, int B, int N, int H, int hd) {
+                                                         float* __restrict__ delta, int N, int H, int hd) {
   pdl_trigger();
   pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int64_t w = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);   // (b * N + n) * H + h
-  if (w >= static_cast<int64_t>(B) * N * H) return;
-  const int h = static_cast<int>(w % H);
-  const int64_t row = w / H;
-  const bf16* op = o + row * H * hd + h * hd;
-  const bf16* dp = dout + row * H * hd + h * hd;
-  float sum = 0.f;
-  for (int c = lane * 4; c < hd; c += 128) {
-    const uint2 a = __ldg(reinterpret_cast<const uint2*>(op + c));
-    const uint2 d = __ldg(reinterpret_cast<const uint2*>(dp + c));
-    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y);
-    sum += (a0.x * d0.x + a0.y * d0.y) + (a1.x * d1.x + a1.y * d1.y);
-  }
-  sum = warp_sum(sum);
-  if (lane == 0) {
-    const int b = static_cast<int>(row / N), n = static_cast<int>(row % N);
-    delta[(static_cast<int64_t>(b) * H + h) * N + n] = sum;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x;                 // b * N + n
+  const int b = row / N, n = row - b * N;
+  const size_t base = static_cast<size_t>(row) * H * hd;
+  constexpr int MAXH = 4;                     // heads per warp and pass
+  for (int h0 = warp; h0 < H; h0 += 8 * MAXH) {
+    uint2 av[MAXH][2], dv[MAXH][2];
+#pragma unroll
+    for (int i = 0; i < MAXH; ++i) {
+      const int h = h0 + 8 * i;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = lane * 4 + j * 128;
+        const bool ok = h < H && c < hd;
+        av[i][j] = ok ? __ldg(reinterpret_cast<const uint2*>(o + base + h * hd + c)) : make_uint2(0u, 0u);
+        dv[i][j] = ok ? __ldg(reinterpret_cast<const uint2*>(dout + base + h * hd + c)) : make_uint2(0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXH; ++i) {
+      const int h = h0 + 8 * i;
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float2 a0 = unpack_bf16x2(av[i][j].x), a1 = unpack_bf16x2(av[i][j].y);
+        const float2 d0 = unpack_bf16x2(dv[i][j].x), d1 = unpack_bf16x2(dv[i][j].y);
+        sum += (a0.x * d0.x + a0.y * d0.y) + (a1.x * d1.x + a1.y * d1.y);
+      }
+      sum = warp_sum(sum);
+      if (lane == 0 && h < H) delta[(static_cast<size_t>(b) * H + h) * N + n] = sum;
+    }
   }
 }
 
@@ -646,8 +660,8 @@ int launch_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float*
   a.ntiles = ceil_div(N, TILE);
   a.nitems = a.ntiles * B * H;
   a.scale = 1.f / sqrtf(static_cast<float>(hd));
-  const int64_t nwarps = static_cast<int64_t>(B) * N * H;
-  VLA_CHECK_CUDA(vla_launch(attn_delta_kernel, dim3(static_cast<unsigned>((nwarps + 7) / 8)), dim3(256), 0, s, o, dout, delta, B, N, H, hd));
+  VLA_REQUIRE(hd <= 256, "attention_bwd_tc: head dim %d too large for the delta kernel", hd);
+  VLA_CHECK_CUDA(vla_launch(attn_delta_kernel, dim3(static_cast<unsigned>(B * N)), dim3(256), 0, s, o, dout, delta, N, H, hd));
   const int grid = a.nitems < g_num_sms_attn ? a.nitems : g_num_sms_attn;
   VLA_CHECK_CUDA(vla_launch(attn_bwd_tc_kernel<HD, KS, MODE_DQ>, dim3(grid), dim3(BWD_THREADS), static_cast<size_t>(BwdSmem<HD, MODE_DQ>::TOTAL),
                             s, map_qkv, map_do, map_dqkv, a));
