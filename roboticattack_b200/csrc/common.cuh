@@ -71,11 +71,15 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // ---------------------------------------------------------------------------------------------
 // Round to bf16 and back.  The packed conversion (F2FP on the ALU pipe) + a mask replaces the scalar F2F conversion, which
 // issues at a quarter of the rate: rounding is the most frequent op of the fused epilogues.  RNE, NaN -> NaN.
+#ifdef VLA_RBF_F2F
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+#else
 __device__ __forceinline__ float rbf(float x) {
   uint32_t p;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(x), "f"(0.f));   // x -> upper half
   return __uint_as_float(p & 0xFFFF0000u);
 }
+#endif
 __device__ __forceinline__ float b2f(bf16 x) { return __bfloat162float(x); }
 __device__ __forceinline__ bf16 f2b(float x) { return __float2bfloat16_rn(x); }
 

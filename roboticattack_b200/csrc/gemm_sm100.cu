@@ -139,23 +139,30 @@ __device__ __forceinline__ const uint4* side_ptr(const GemmArgs& g, int row_in, 
   if (row_in >= g.M || col0 + 32 > g.N) return nullptr;
   const int row = e.out_group ? (row_in / e.out_group) * e.out_stride + e.out_offset + row_in % e.out_group : row_in;
   if (e.aux_mode == 1) return reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + col0);
+  if (e.aux_mode == 2)   // saved gate|up pre-activations, interleaved [gate 64 | up 64]: gate chunk here, up chunk 64 elements on
+    return reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + static_cast<int64_t>(col0 / 64) * 128 + (col0 % 64));
   if (e.aux_mode == 0 && e.resid) {
     const int rrow = e.resid_mod ? row_in % e.resid_mod : row;
     return reinterpret_cast<const uint4*>(e.resid + static_cast<int64_t>(rrow) * e.ldr + col0);
   }
   return nullptr;
 }
-__device__ __forceinline__ void load_side(const uint4* p, uint4 (&buf)[4]) {
+// buf[0..3] = the chunk's 64 bytes; buf[4..7] = the "up" half of the SwiGLU pre-activations (aux_mode 2 only)
+__device__ __forceinline__ void load_side(const uint4* p, bool second, uint4 (&buf)[8]) {
   if (p != nullptr) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) buf[q] = p[q];
+    if (second) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) buf[4 + q] = p[8 + q];   // + 64 bf16
+    }
   }
 }
 
 // One row x 32 columns of the accumulator -> global, with the fused epilogue.  `side` = this chunk's prefetched side operand
 // (valid when side_ptr() of the chunk is non-null).
 __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const uint32_t (&acc)[32], int row_in, int col0,
-                                                     const uint4 (&side)[4]) {
+                                                     const uint4 (&side)[8]) {
   const GemmEpilogue& e = g.epi;
   const int row = e.out_group ? (row_in / e.out_group) * e.out_stride + e.out_offset + row_in % e.out_group : row_in;
   const int rrow = e.resid_mod ? row_in % e.resid_mod : row;
@@ -179,12 +186,11 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
   }
   if (e.aux_mode == 2) {   // SwiGLU backward on the interleaved [gate 64 | up 64] layout
     const int64_t gcol = static_cast<int64_t>(col0 / 64) * 128 + (col0 % 64);
-    const bf16* gp = e.aux + static_cast<int64_t>(row) * e.ldaux + gcol;
     bf16* dgp = static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + gcol;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint4 gu4 = *reinterpret_cast<const uint4*>(gp + q * 8);
-      const uint4 uu4 = *reinterpret_cast<const uint4*>(gp + 64 + q * 8);
+      const uint4 gu4 = side[q];        // prefetched one chunk ahead (load_side)
+      const uint4 uu4 = side[4 + q];
       const uint32_t gw[4] = {gu4.x, gu4.y, gu4.z, gu4.w}, uw[4] = {uu4.x, uu4.y, uu4.z, uu4.w};
       uint32_t og[4], ou[4];
 #pragma unroll
@@ -519,8 +525,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (row < g.M) epilogue_store_pair(g, va, vb, row, col_a);
         }
       } else {
-        uint4 side_cur[4], side_nxt[4];
-        load_side(side_ptr(g, row, n_blk * BLOCK_N + half * 32), side_nxt);   // first chunk: overlaps the wait for the MMAs
+        uint4 side_cur[8], side_nxt[8];
+        const bool side2 = g.epi.aux_mode == 2;
+        load_side(side_ptr(g, row, n_blk * BLOCK_N + half * 32), side2, side_nxt);   // first chunk: overlaps the wait for the MMAs
         if (!waited) {
           mbar_wait(tfull_bar(acc), acc_phase);
           tc_fence_after();
@@ -530,8 +537,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const int col0 = n_blk * BLOCK_N + c * 32;
           if (col0 >= g.N) break;  // warp-uniform
 #pragma unroll
-          for (int q = 0; q < 4; ++q) side_cur[q] = side_nxt[q];
-          if (c + 2 < BLOCK_N / 32) load_side(side_ptr(g, row, col0 + 64), side_nxt);
+          for (int q = 0; q < 8; ++q) side_cur[q] = side_nxt[q];
+          if (c + 2 < BLOCK_N / 32) load_side(side_ptr(g, row, col0 + 64), side2, side_nxt);
           uint32_t v[32];
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();
