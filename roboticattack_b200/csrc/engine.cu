@@ -480,7 +480,7 @@ int vit_backward(vla_engine* e, int t, Transients& tr, cudaStream_t s) {
       CK(scale_cols(dx, k.ls2, tr.c, Mv, d, s));
       g = tr.c;
     }
-    if (v.mlp % 32 == 0) {
+    if (v.mlp % 8 == 0) {
       GemmEpilogue ep;   // GELU backward fused into the fc2^T GEMM epilogue
       ep.aux_mode = 1;
       ep.aux = a.fc1_pre[i];

@@ -136,9 +136,11 @@ struct GemmCfg {
 // fetches it one chunk ahead (side_ptr + load_side), so the latency hides behind the MMAs / the previous chunk.
 __device__ __forceinline__ const uint4* side_ptr(const GemmArgs& g, int row_in, int col0) {
   const GemmEpilogue& e = g.epi;
-  if (row_in >= g.M || col0 + 32 > g.N) return nullptr;
+  if (row_in >= g.M || col0 >= g.N) return nullptr;
   const int row = e.out_group ? (row_in / e.out_group) * e.out_stride + e.out_offset + row_in % e.out_group : row_in;
+  // GELU backward: N % 8 == 0 is enough (SigLIP's 4304-wide MLP); load_side fetches only the 16-byte groups inside N
   if (e.aux_mode == 1) return reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + col0);
+  if (col0 + 32 > g.N) return nullptr;
   if (e.aux_mode == 2)   // saved gate|up pre-activations, interleaved [gate 64 | up 64]: gate chunk here, up chunk 64 elements on
     return reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + static_cast<int64_t>(col0 / 64) * 128 + (col0 % 64));
   if (e.aux_mode == 0 && e.resid) {
@@ -148,10 +150,11 @@ __device__ __forceinline__ const uint4* side_ptr(const GemmArgs& g, int row_in, 
   return nullptr;
 }
 // buf[0..3] = the chunk's 64 bytes; buf[4..7] = the "up" half of the SwiGLU pre-activations (aux_mode 2 only)
-__device__ __forceinline__ void load_side(const uint4* p, bool second, uint4 (&buf)[8]) {
+__device__ __forceinline__ void load_side(const uint4* p, bool second, int nq, uint4 (&buf)[8]) {
   if (p != nullptr) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) buf[q] = p[q];
+    for (int q = 0; q < 4; ++q)
+      if (q < nq) buf[q] = p[q];
     if (second) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) buf[4 + q] = p[8 + q];   // + 64 bf16
@@ -171,6 +174,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
     uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
+      if (col0 + q * 8 + 8 > g.N) break;   // ragged last chunk (N % 8 == 0)
       const uint4 u = side[q];
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
       uint32_t o[4];
@@ -527,7 +531,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       } else {
         uint4 side_cur[8], side_nxt[8];
         const bool side2 = g.epi.aux_mode == 2;
-        load_side(side_ptr(g, row, n_blk * BLOCK_N + half * 32), side2, side_nxt);   // first chunk: overlaps the wait for the MMAs
+        auto side_nq = [&](int col) { return min(4, (g.N - col) / 8); };   // 16-byte groups of the chunk inside N
+        load_side(side_ptr(g, row, n_blk * BLOCK_N + half * 32), side2, side_nq(n_blk * BLOCK_N + half * 32), side_nxt);   // overlaps the wait for the MMAs
         if (!waited) {
           mbar_wait(tfull_bar(acc), acc_phase);
           tc_fence_after();
@@ -538,7 +543,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (col0 >= g.N) break;  // warp-uniform
 #pragma unroll
           for (int q = 0; q < 8; ++q) side_cur[q] = side_nxt[q];
-          if (c + 2 < BLOCK_N / 32) load_side(side_ptr(g, row, col0 + 64), side2, side_nxt);
+          if (c + 2 < BLOCK_N / 32) load_side(side_ptr(g, row, col0 + 64), side2, side_nq(col0 + 64), side_nxt);
           uint32_t v[32];
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();
@@ -681,7 +686,8 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
               "gemm: operands must be 16-byte aligned");
   VLA_REQUIRE(!epi.resid || epi.ldr % 8 == 0, "gemm: residual ld must be a multiple of 8");
   VLA_REQUIRE(!epi.pair_mode || N % 128 == 0, "gemm: pair-mode epilogues need N %% 128 == 0 (got %d)", N);
-  VLA_REQUIRE(!epi.aux_mode || (N % 32 == 0 && epi.aux && epi.ldaux % 8 == 0), "gemm: aux-mode epilogues need N %% 32 == 0 and an aux tensor");
+  VLA_REQUIRE(!epi.aux_mode || (N % (epi.aux_mode == 1 ? 8 : 32) == 0 && epi.aux && epi.ldaux % 8 == 0),
+              "gemm: aux-mode epilogues need N %% 32 == 0 (GELU backward: N %% 8 == 0) and an aux tensor");
   VLA_REQUIRE(epi.pair_mode != 1 || (epi.rope_cos && epi.rope_sin && epi.rope_L > 0 && epi.rope_cols % 128 == 0), "gemm: bad RoPE epilogue");
   VLA_REQUIRE(epi.pair_mode != 2 || (epi.act_out && epi.ld_act % 8 == 0), "gemm: bad SwiGLU epilogue");
   if (g_num_sms == 0) {
