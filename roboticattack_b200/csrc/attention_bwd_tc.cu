@@ -662,7 +662,8 @@ int launch_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float*
   a.scale = 1.f / sqrtf(static_cast<float>(hd));
   VLA_REQUIRE(hd <= 256, "attention_bwd_tc: head dim %d too large for the delta kernel", hd);
   VLA_CHECK_CUDA(vla_launch(attn_delta_kernel, dim3(static_cast<unsigned>(B * N)), dim3(256), 0, s, o, dout, delta, N, H, hd));
-  const int grid = a.nitems < g_num_sms_attn ? a.nitems : g_num_sms_attn;
+  const int sms = (g_vla_sm_limit > 0 && g_vla_sm_limit < g_num_sms_attn) ? g_vla_sm_limit : g_num_sms_attn;
+  const int grid = a.nitems < sms ? a.nitems : sms;
   VLA_CHECK_CUDA(vla_launch(attn_bwd_tc_kernel<HD, KS, MODE_DQ>, dim3(grid), dim3(BWD_THREADS), static_cast<size_t>(BwdSmem<HD, MODE_DQ>::TOTAL),
                             s, map_qkv, map_do, map_dqkv, a));
   VLA_CHECK_CUDA(vla_launch(attn_bwd_tc_kernel<HD, KS, MODE_DKV>, dim3(grid), dim3(BWD_THREADS),

@@ -443,7 +443,8 @@ int launch_fwd_tc2(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int 
   a.ntiles = ceil_div(N, TILE);
   a.nitems = a.ntiles * B * H;
   a.scale = 1.f / sqrtf(static_cast<float>(hd));
-  const int grid = a.nitems < g_num_sms_fwd ? a.nitems : g_num_sms_fwd;
+  const int sms = (g_vla_sm_limit > 0 && g_vla_sm_limit < g_num_sms_fwd) ? g_vla_sm_limit : g_num_sms_fwd;
+  const int grid = a.nitems < sms ? a.nitems : sms;
   VLA_CHECK_CUDA(vla_launch(attn_fwd_tc2_kernel<HD, KS>, dim3(grid), dim3(FWD_THREADS), static_cast<size_t>(SM::TOTAL), s, map_qkv, map_o, a));
   ++g_vla_launch_count;
   return 0;

@@ -108,6 +108,9 @@ struct vla_engine {
   // Last decoder layer on the supervised rows only (see vla_fwd_bwd): only those rows of its output reach the loss, so
   // everything after its attention (o_proj, MLP and their backward) runs on R gathered rows instead of B*L.
   bool prune_last = true;
+  // two-stream vision towers: each tower's persistent kernels take half of the SMs.  Measured SLOWER (front + ViT forward 8.2 vs
+  // 7.1 ms: the towers are unbalanced, so the longer one finishes on half a machine) -> off by default, VLA_SM_SPLIT=1 enables.
+  bool split_sms = false;
   bf16 *ll_xs = nullptr, *ll_as = nullptr, *ll_xm = nullptr, *ll_norm = nullptr, *ll_gu = nullptr, *ll_act = nullptr,
        *ll_dgu = nullptr, *ll_dnorm = nullptr, *ll_dxm = nullptr, *ll_dattn = nullptr;
   float* ll_rstd2 = nullptr;
@@ -587,6 +590,8 @@ extern "C" int vla_engine_set_buffers(vla_engine* e, void* weight_arena, size_t 
     e->single_stream = ss && atoi(ss) != 0;
     const char* fs = getenv("VLA_FUSE_SWIGLU_BWD");
     e->fuse_swiglu_bwd = !(fs && atoi(fs) == 0);
+    const char* sp = getenv("VLA_SM_SPLIT");
+    e->split_sms = sp && atoi(sp) != 0;
     const char* pl = getenv("VLA_PRUNE_LAST");
     e->prune_last = !(pl && atoi(pl) == 0);
   }
@@ -807,14 +812,23 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
     VLA_CHECK_CUDA(cudaEventRecord(e->ev_fork, s));
     VLA_CHECK_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
   }
+  int num_sms = 0, cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, cur_dev);
+  const int tower_sms = (two_streams && e->split_sms && num_sms >= 8) ? (num_sms / 2) & ~1 : 0;
   int col_off = 0;
+  g_vla_sm_limit = tower_sms;
   for (int t = 0; t < 2; ++t) {
     cudaStream_t st = t == 0 ? s : s1;
-    CK(vit_forward(e, t, e->tr[two_streams ? t : 0], st));
+    if (int rc = vit_forward(e, t, e->tr[two_streams ? t : 0], st)) {
+      g_vla_sm_limit = 0;
+      return rc;
+    }
     const VitDims& v = e->vit[t];
     CK(copy_rows(e->va[t].x[v.used], v.dim, v.ntok, v.npre, e->feats + col_off, vd, P, 0, B, P, v.dim, st));
     col_off += v.dim;
   }
+  g_vla_sm_limit = 0;
   if (two_streams) {
     VLA_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
     VLA_CHECK_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
@@ -1004,7 +1018,10 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
     Transients& tr = e->tr[two_streams ? t : 0];
     VLA_CHECK_CUDA(cudaMemsetAsync(tr.a, 0, static_cast<size_t>(Mv) * v.dim * sizeof(bf16), st));
     CK(copy_rows(e->feats + col_off, vd, P, 0, tr.a, v.dim, v.ntok, v.npre, B, P, v.dim, st));
-    CK(vit_backward(e, t, tr, st));
+    g_vla_sm_limit = tower_sms;
+    const int rc_b = vit_backward(e, t, tr, st);
+    g_vla_sm_limit = 0;
+    if (rc_b) return rc_b;
     col_off += v.dim;
   }
   if (two_streams) {

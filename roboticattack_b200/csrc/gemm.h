@@ -50,5 +50,11 @@ struct GemmEpilogue {
 int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
                  const GemmEpilogue& epi, cudaStream_t stream);
 
+// Persistent kernels (GEMM, tcgen05 attention) size their grids to min(work, SMs).  While the two independent vision towers
+// run on two streams the engine sets this limit to half the SMs, so that one tower's persistent kernel leaves the other
+// half of the machine to the other tower (otherwise a 1-CTA-per-SM kernel of ~200 KB shared memory serialises them) and
+// the 1.x-wave ViT shapes lose less to wave quantisation.  0 = no limit.
+extern int g_vla_sm_limit;
+
 // number of GEMM kernel launches since process start (for bench.py's gpu_launches accounting)
 extern long long g_vla_launch_count;

@@ -21,6 +21,7 @@
 #include "tma_desc.h"
 
 long long g_vla_launch_count = 0;
+int g_vla_sm_limit = 0;
 
 // Optional per-launch timing of the GEMM kernel (bench.py's roofline leg): CUDA events recorded on the launch
 // stream around every GEMM launch while enabled; summed after a synchronise.
@@ -589,7 +590,8 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g,
     configured = true;
   }
   const int tiles = g.num_m_blocks * g.num_n_blocks;
-  const int units = g_num_sms / CTAS;   // persistent: one CTA (or CTA pair) per SM (pair)
+  const int sms = (g_vla_sm_limit > 0 && g_vla_sm_limit < g_num_sms) ? g_vla_sm_limit : g_num_sms;
+  const int units = sms / CTAS;   // persistent: one CTA (or CTA pair) per SM (pair)
   const int grid = (tiles < units ? tiles : units) * CTAS;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
@@ -704,7 +706,8 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
     ctas = g_forced_ctas;
     block_n = g_forced_n;
   } else {
-    const uint64_t key = (static_cast<uint64_t>(M) << 42) ^ (static_cast<uint64_t>(N) << 21) ^ static_cast<uint64_t>(K);
+    const uint64_t key = (static_cast<uint64_t>(M) << 42) ^ (static_cast<uint64_t>(N) << 21) ^ static_cast<uint64_t>(K) ^
+                         (g_vla_sm_limit > 0 ? (1ull << 62) : 0ull);   // the best variant depends on the SM budget
     auto it = g_tuned.find(key);
     if (it != g_tuned.end()) {
       ctas = it->second.ctas;
@@ -743,7 +746,8 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
         double best = 1e300;
         for (const Variant& v : kVariants) {
           const long tiles = static_cast<long>(ceil_div(M, BLOCK_M * v.ctas)) * ceil_div(N, v.block_n);
-          const long waves = (tiles + g_num_sms / v.ctas - 1) / (g_num_sms / v.ctas);
+          const int sms = (g_vla_sm_limit > 0 && g_vla_sm_limit < g_num_sms) ? g_vla_sm_limit : g_num_sms;
+          const long waves = (tiles + sms / v.ctas - 1) / (sms / v.ctas);
           const double t = static_cast<double>(waves) * v.block_n / v.eff;
           if (t < best) {
             best = t;
