@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(NORM_THREADS) layernorm_bwd_kernel(const bf16*
       s2 += g[it][k] * xh[it][k];
     }
   });
+  // the residual-stream gradient is fetched before the block reductions so that its latency hides behind them
+  uint4 rv[MAX_VEC];
+  if (dres) for_each_vec(d8, [&](int it, int v) { rv[it] = *reinterpret_cast<const uint4*>(dres + row * d + v * 8); });
   const float m1 = block_sum(s1, red) / d;
   const float m2 = block_sum(s2, red) / d;
   for_each_vec(d8, [&](int it, int v) {
@@ -106,10 +109,13 @@ __global__ void __launch_bounds__(NORM_THREADS) layernorm_bwd_kernel(const bf16*
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = rstd * (g[it][k] - m1 - xh[it][k] * m2);
     if (dres) {
-      float r[8];
-      load8(dres + row * d + v * 8, r);
+      const uint32_t w4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = r[k] + rbf(o[k]);
+      for (int t = 0; t < 4; ++t) {
+        const float2 r = unpack_bf16x2(w4[t]);
+        o[2 * t] = r.x + rbf(o[2 * t]);
+        o[2 * t + 1] = r.y + rbf(o[2 * t + 1]);
+      }
     }
     store8(dx + row * d + v * 8, o);
   });
@@ -163,6 +169,8 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(const bf16* _
       s += g[it][k] * xv[it][k];
     }
   });
+  uint4 rv[MAX_VEC];   // residual-stream gradient, fetched before the block reduction (latency hidden behind it)
+  if (dres) for_each_vec(d8, [&](int it, int v) { rv[it] = *reinterpret_cast<const uint4*>(dres + row * d + v * 8); });
   const float mgx = block_sum(s, red) / d;
   const float r3 = rstd * rstd * rstd;
   for_each_vec(d8, [&](int it, int v) {
@@ -170,10 +178,13 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(const bf16* _
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = rstd * g[it][k] - xv[it][k] * r3 * mgx;
     if (dres) {
-      float r[8];
-      load8(dres + row * d + v * 8, r);
+      const uint32_t w4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = r[k] + rbf(o[k]);
+      for (int t = 0; t < 4; ++t) {
+        const float2 r = unpack_bf16x2(w4[t]);
+        o[2 * t] = r.x + rbf(o[2 * t]);
+        o[2 * t + 1] = r.y + rbf(o[2 * t + 1]);
+      }
     }
     store8(dx + row * d + v * 8, o);
   });

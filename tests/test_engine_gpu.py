@@ -213,3 +213,36 @@ def test_last_layer_row_pruning_is_exact(tiny_setup, loss_kind, monkeypatch):
     assert torch.equal(outs[0][1][:_lib.S_GRAD_MEAN], outs[1][1][:_lib.S_GRAD_MEAN])
     assert torch.equal(outs[0][2], outs[1][2])
     assert outs[0][0].abs().sum() > 0
+
+
+def test_greedy_action_decode_vs_oracle(tiny_setup):
+    """ActionPolicy.generate_action_tokens (predict_action of modeling_prismatic.py:506-536 on the engine, one forward-only
+    pass per token) against the oracle's greedy decode in fp32: same tokens wherever the oracle's decision margin is above
+    bf16 noise; a tie-level disagreement ends the comparison (later tokens are conditioned on different prefixes)."""
+    from oracle import policy as opol
+    from roboticattack_b200.policy import ActionPolicy
+    cfg, sd, eng, B, T = tiny_setup
+    batch = synthetic_batch(cfg, B, T, seed=9)
+    prompt = batch["input_ids"][:, :T - 8].clone()          # BOS + prompt + 29871
+    n = 7
+    ref, margin = opol.greedy_action_tokens(sd, cfg, batch["obs"], prompt, n, NORM_MEAN, NORM_STD, torch.float32)
+    got = torch.from_numpy(ActionPolicy(eng).generate_action_tokens(batch["obs"], prompt, n))
+    eng.ensure_plan(B, T)                                    # restore the fixture's plan
+    checked = 0
+    for b in range(B):
+        for k in range(n):
+            if got[b, k] != ref[b, k]:
+                assert margin[b, k] < 0.05, f"sample {b} token {k}: engine {got[b, k]} oracle {ref[b, k]} margin {margin[b, k]:.3f}"
+                break
+            checked += 1
+    assert checked >= B * n // 2, f"only {checked} decisions could be compared"
+
+    # reference API: un-normalisation with dataset statistics (modeling_prismatic.py:527-534)
+    stats = {"bridge_orig": {"action": {"q01": [-1.0] * 7, "q99": [3.0] * 7, "mask": [True] * 6 + [False]}}}
+    pol = ActionPolicy(eng, stats)
+    act = pol.predict_action(batch["obs"][0].numpy(), prompt[:1], unnorm_key="bridge_orig")
+    eng.ensure_plan(B, T)
+    from roboticattack_b200 import labels as lab
+    norm = lab.decode_token_ids_to_actions(got[0].numpy())
+    expect = np.where(np.array([True] * 6 + [False]), 0.5 * (norm + 1) * 4.0 - 1.0, norm)
+    np.testing.assert_allclose(act, expect, rtol=0, atol=1e-12)
