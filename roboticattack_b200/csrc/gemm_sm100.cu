@@ -97,7 +97,25 @@ struct GemmArgs {
   int64_t ldc;
   void* out;
   GemmEpilogue epi;
+  int epi_sleep_ns;   // back-off between polls of the epilogue warps' wait for the accumulator (0 = plain try_wait loop)
 };
+
+// Wait of the 8 epilogue warps for the MMAs of their tile (most of a tile's duration): optional nanosleep back-off between
+// polls so that 256 threads do not compete with the producer / MMA warps for issue slots and power.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, int sleep_ns) {
+  if (sleep_ns <= 0) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    if (++spins > (1u << 24)) {
+      printf("mbar_wait_backoff timeout: block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO).
 // Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
@@ -513,7 +531,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
       const bool waited = g.epi.pair_mode != 0;
       if (waited) {
-        mbar_wait(tfull_bar(acc), acc_phase);
+        mbar_wait_backoff(tfull_bar(acc), acc_phase, g.epi_sleep_ns);
         tc_fence_after();
       }
       if (g.epi.pair_mode) {
@@ -535,7 +553,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         auto side_nq = [&](int col) { return min(4, (g.N - col) / 8); };   // 16-byte groups of the chunk inside N
         load_side(side_ptr(g, row, n_blk * BLOCK_N + half * 32), side2, side_nq(n_blk * BLOCK_N + half * 32), side_nxt);   // overlaps the wait for the MMAs
         if (!waited) {
-          mbar_wait(tfull_bar(acc), acc_phase);
+          mbar_wait_backoff(tfull_bar(acc), acc_phase, g.epi_sleep_ns);
           tc_fence_after();
         }
 #pragma unroll 1
@@ -652,6 +670,12 @@ int launch_variant(int ctas, int block_n, const bf16* A, int64_t lda, const bf16
   g.ldc = ldc;
   g.out = out;
   g.epi = epi;
+  static int sleep_ns = -1;
+  if (sleep_ns < 0) {
+    const char* e = getenv("VLA_EPI_SLEEP_NS");
+    sleep_ns = e ? atoi(e) : 0;
+  }
+  g.epi_sleep_ns = sleep_ns;
   CUtensorMap ma, mbm;
   if (int rc = get_tmap(A, lda, M, K, BLOCK_M, &ma)) return rc;
   if (int rc = get_tmap(W, ldw, N, K, block_n / ctas, &mbm)) return rc;
