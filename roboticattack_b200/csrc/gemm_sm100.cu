@@ -168,16 +168,24 @@ __device__ __forceinline__ const uint4* side_ptr(const GemmArgs& g, int row_in, 
   }
   return nullptr;
 }
-// buf[0..3] = the chunk's 64 bytes; buf[4..7] = the "up" half of the SwiGLU pre-activations (aux_mode 2 only)
-__device__ __forceinline__ void load_side(const uint4* p, bool second, int nq, uint4 (&buf)[8]) {
+// buf[0..3] = the chunk's 64 bytes of the side operand; buf[4..7] = the "up" half of the SwiGLU pre-activations (aux_mode 2)
+// or, in the plain epilogue modes, the chunk's 32 bias values (also an L2-latency load when L1 is carved down to ~30 KB).
+__device__ __forceinline__ void load_side(const GemmArgs& g, const uint4* p, int col, uint4 (&buf)[8]) {
+  const GemmEpilogue& e = g.epi;
   if (p != nullptr) {
+    const int nq = min(4, (g.N - col) / 8);   // 16-byte groups of the chunk inside N
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       if (q < nq) buf[q] = p[q];
-    if (second) {
+    if (e.aux_mode == 2) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) buf[4 + q] = p[8 + q];   // + 64 bf16
     }
+  }
+  if (e.aux_mode == 0 && e.bias != nullptr && col + 32 <= g.N) {
+    const uint4* bp = reinterpret_cast<const uint4*>(e.bias + col);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) buf[4 + q] = __ldg(bp + q);
   }
 }
 
@@ -255,10 +263,9 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
 
   if (full) {
     if (e.bias) {
-      const uint4* bp = reinterpret_cast<const uint4*>(e.bias + col0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint4 u = __ldg(bp + q);
+        const uint4 u = side[4 + q];   // prefetched with the side operand (load_side)
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -549,9 +556,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       } else {
         uint4 side_cur[8], side_nxt[8];
-        const bool side2 = g.epi.aux_mode == 2;
-        auto side_nq = [&](int col) { return min(4, (g.N - col) / 8); };   // 16-byte groups of the chunk inside N
-        load_side(side_ptr(g, row, n_blk * BLOCK_N + half * 32), side2, side_nq(n_blk * BLOCK_N + half * 32), side_nxt);   // overlaps the wait for the MMAs
+        load_side(g, side_ptr(g, row, n_blk * BLOCK_N + half * 32), n_blk * BLOCK_N + half * 32, side_nxt);   // overlaps the wait for the MMAs
         if (!waited) {
           mbar_wait_backoff(tfull_bar(acc), acc_phase, g.epi_sleep_ns);
           tc_fence_after();
@@ -562,7 +567,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (col0 >= g.N) break;  // warp-uniform
 #pragma unroll
           for (int q = 0; q < 8; ++q) side_cur[q] = side_nxt[q];
-          if (c + 2 < BLOCK_N / 32) load_side(side_ptr(g, row, col0 + 64), side2, side_nq(col0 + 64), side_nxt);
+          if (c + 2 < BLOCK_N / 32) load_side(g, side_ptr(g, row, col0 + 64), col0 + 64, side_nxt);
           uint32_t v[32];
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();
