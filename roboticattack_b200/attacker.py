@@ -198,6 +198,25 @@ class _AttackerBase(object):
             torch.save(self.host.state_dict(outer_iter, sched_step), os.path.join(d, self.STATE_FILE))
         return d
 
+    def _dump_val_images(self, d, extra=None):
+        """``<dir>/val_related_data/<o>.png``: the last validation batch with the patch applied, de-normalised from the DINOv2
+        channels (UADA.py:262-270, UPA.py:252-260, TMA.py:351-361), plus optional tensors (TMA: decoded actions).  The
+        reference converts with ``ToPILImage`` (``mul(255).byte()``, which wraps values a rounding error above 1.0); the
+        values are clamped to [0, 1] here."""
+        eng = self.host.engine
+        if eng is None or not hasattr(eng, "tap"):
+            return
+        from PIL import Image
+        vd = os.path.join(d, "val_related_data")
+        os.makedirs(vd, exist_ok=True)
+        img = self.host.cfg.img
+        px = eng.tap("px").view(-1, 6, img, img)[:, 0:3].float().cpu()
+        px = self.randomPatchTransform.denormalize(px, self.mean[0], self.std[0]).clamp_(0, 1)
+        for o in range(px.shape[0]):
+            Image.fromarray(px[o].mul(255).byte().permute(1, 2, 0).numpy()).save(os.path.join(vd, f"{o}.png"))
+        for name, t in (extra or {}).items():
+            torch.save(t, os.path.join(vd, name))
+
     def _maybe_resume(self):
         """-> (first outer iteration to run, scheduler step).  (0, 0) without ``resume``."""
         if not self.resume:
@@ -304,8 +323,8 @@ class UADAAttacker(_AttackerBase):
         self._log(args, log, i)
         if avg_mse < self.MSE_Distance_best:
             self.MSE_Distance_best = avg_mse
-            self._save_patch(h.patch, str(i))
-        self._save_patch(h.patch, "last", outer_iter=i, sched_step=getattr(self, "_sched_step", 0))
+            self._dump_val_images(self._save_patch(h.patch, str(i)))
+        self._dump_val_images(self._save_patch(h.patch, "last", outer_iter=i, sched_step=getattr(self, "_sched_step", 0)))
         self.val_CE_loss.append(avg_ce)
         self.val_MSE_Distance.append(avg_mse)
         self.val_UAD.append(avg_uad)
@@ -333,6 +352,9 @@ class UPAAttacker(_AttackerBase):
                                   reverse_direction=True, args=None):
         h = self.host
         self.train_CE_loss, self.val_CE_loss = [], []
+        self.avg_reserve_loss, self.avg_angle_loss, self.avg_distance_loss = [], [], []
+        self.reverse_direction_loss = 1e8
+        val_it = iter(val_dataloader) if val_dataloader is not None else None
         h.init_patch(patch_size)
         if guide:
             loss = LossSpec(_lib.LOSS_CE, ce_scale=1.0)
@@ -368,9 +390,38 @@ class UPAAttacker(_AttackerBase):
             self.loss_buffer.append(log["TRAIN_attack_loss(CE)"])
             self._log(args, log, i)
             if i % self.val_every == 0:
-                self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
+                if val_dataloader is not None and reverse_direction and not guide:
+                    val_it = self._validate(i, val_it, val_dataloader, fe_mode, loss, sched_step, args)
+                else:
+                    self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
                 self._dump(train_CE_loss=self.train_CE_loss)
         return h.patch.detach().cpu()
+
+    def _validate(self, i, val_it, val_dataloader, fe_mode, loss, sched_step, args):
+        """UPA.py:193-275: 100 forward-only batches; sums of the per-batch reverse-direction loss / angle term / distance term
+        divided by the SAMPLE count (as the reference does); the patch with the lowest reverse-direction loss is kept."""
+        h = self.host
+        n, s_loss, s_ang, s_dist = 0, 0.0, 0.0, 0.0
+        for _ in range(self.val_batches):
+            data, val_it = self._next(val_it, val_dataloader)
+            data = dict(data)
+            n += data["labels"].shape[0]
+            sc, _ = h.evaluate(data, fe_mode, loss)
+            s_loss += sc[_lib.S_LOSS].item()
+            s_ang += sc[_lib.S_AUX0].item()
+            s_dist += sc[_lib.S_AUX1].item()
+        avg_loss, avg_ang, avg_dist = s_loss / n, s_ang / n, s_dist / n
+        self._log(args, {"reverse_direction_loss": avg_loss, "avg_angle_loss": avg_ang, "avg_distance_loss": avg_dist}, i)
+        if avg_loss < self.reverse_direction_loss:
+            self.reverse_direction_loss = avg_loss
+            self._dump_val_images(self._save_patch(h.patch, str(i)))
+        self._dump_val_images(self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step))
+        self.avg_reserve_loss.append(avg_loss)
+        self.avg_angle_loss.append(avg_ang)
+        self.avg_distance_loss.append(avg_dist)
+        self._dump(val_CE_loss=self.val_CE_loss, avg_angle_loss=self.avg_angle_loss, avg_distance_loss=self.avg_distance_loss,
+                   avg_reserve_loss=self.avg_reserve_loss)
+        return val_it
 
 
 class TMAAttacker(_AttackerBase):
@@ -386,6 +437,9 @@ class TMAAttacker(_AttackerBase):
                                   filterGripTrainTo1=False, geometry=False, colorjitter=False, innerLoop=1, args=None):
         h = self.host
         self.train_CE_loss, self.train_inner_avg_loss, self.train_inner_relatived_distance = [], [], []
+        self.val_CE_loss, self.val_L1_loss, self.val_ASR, self.val_inner_relatived_distance = [], [], [], []
+        self.min_val_avg_L1_loss = 1e8
+        val_it = iter(val_dataloader) if val_dataloader is not None else None
         h.init_patch(patch_size)
         target = lab.tma_target(target_action, maskidx)
         loss = LossSpec(_lib.LOSS_CE, ce_scale=1.0 / accumulate_steps)
@@ -415,9 +469,85 @@ class TMAAttacker(_AttackerBase):
             self.loss_buffer.append(log["TRAIN_attack_loss(CE)"])
             self._log(args, log, i)
             if i % self.val_every == 0:
-                self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
-                self._dump(train_CE_loss=self.train_CE_loss, train_inner_avg_loss=self.train_inner_avg_loss)
+                if val_dataloader is not None:
+                    val_it = self._validate(i, val_it, val_dataloader, target, maskidx, fe_mode, sched_step, args)
+                else:
+                    self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
+                self._dump(train_CE_loss=self.train_CE_loss, train_inner_avg_loss=self.train_inner_avg_loss,
+                           train_inner_relatived_distance=self.train_inner_relatived_distance)
         return h.patch.detach().cpu()
+
+    def _validate(self, i, val_it, val_dataloader, target, maskidx, fe_mode, sched_step, args):
+        """TMA.py:202-383: 100 forward-only batches with the labels replaced by the target; CE, L1 between the decoded
+        greedy prediction and the target, ASR (all attacked DoF hit exactly), relative distance to the target; sums divided
+        by the sample count as in the reference; the patch with the lowest L1 is kept.  For the gripper-only attack
+        (maskidx == [6]) the reference first drops the samples whose CLEAN prediction of the gripper token is wrong and
+        reports the 0->other / 1->other / other->0 rates (calculate_01_ASR); both are reproduced."""
+        h = self.host
+        grip = len(maskidx) == 1 and maskidx[0] == 6
+        ce_loss = LossSpec(_lib.LOSS_CE, ce_scale=1.0)
+        n, s_ce, s_l1, s_rd, hits = 0, 0.0, 0.0, 0.0, 0
+        c01 = [0, 0, 0, 0, 0, 0]
+        pr = gt = torch.zeros(0)
+        for _ in range(self.val_batches):
+            data, val_it = self._next(val_it, val_dataloader)
+            data = dict(data)
+            real = data["labels"]
+            if grip:
+                _, clean_pred = h.evaluate(data, _lib.FE_NONE, ce_loss)                 # im_process: no patch
+                sup = real[:, 1:][real[:, 1:] != IGNORE_INDEX].view(real.shape[0], -1)  # [B, 8] = 7 actions + EOS
+                keep = [b for b in range(real.shape[0]) if int(clean_pred.view(real.shape[0], -1)[b, 6]) == int(sup[b, 6])]
+                if not keep:
+                    continue
+                data = {k: ([v[b] for b in keep] if isinstance(v, list) else v[keep]) for k, v in data.items()
+                        if k in ("pixel_values", "input_ids", "attention_mask", "labels")}
+                real = data["labels"]
+            B = real.shape[0]
+            n += B
+            data["labels"] = lab.tma_labels(real, target)
+            sc, pred = h.evaluate(data, fe_mode, ce_loss)
+            pr, gt = _decoded_pairs(pred, data["labels"])
+            s_ce += sc[_lib.S_CE].item()
+            s_l1 += torch.nn.functional.l1_loss(pr, gt).item() if pr.numel() else 0.0
+            s_rd += float(lab.relative_distance(pr, gt).mean()) if pr.numel() else 0.0
+            k = max(1, len(maskidx) - (1 if 7 in maskidx else 0))
+            hits += int((pr.view(B, k) == gt.view(B, k)).all(dim=1).sum()) if pr.numel() else 0
+            if grip:
+                p_ids = pred.view(B, -1)[:, 0]
+                g_ids = real[:, 1:][real[:, 1:] != IGNORE_INDEX].view(B, -1)[:, 6]
+                for b in range(B):
+                    g_, p_ = int(g_ids[b]), int(p_ids[b])
+                    if g_ == 31872:
+                        c01[1] += 1
+                        c01[0] += p_ != 31872
+                    elif g_ == 31744:
+                        c01[3] += 1
+                        c01[2] += p_ != 31744
+                    else:
+                        c01[5] += 1
+                        c01[4] += p_ == 31872
+        n = max(n, 1)
+        avg_ce, avg_l1, asr, avg_rd = s_ce / n, s_l1 / n, hits / n, s_rd / n
+        log = {"VAL_avg_CE_loss": avg_ce, "VAL_avg_L1_loss": avg_l1}
+        if grip:
+            log.update({"VAL_ASR(pred0-AllCorrect)": asr, "ASR_02other": c01[0] / c01[1] if c01[1] else 0,
+                        "ASR_12other": c01[2] / c01[3] if c01[3] else 0, "ASR_other20": c01[4] / c01[5] if c01[5] else 0,
+                        "ALL_ASR_6": (c01[0] + c01[2]) / (c01[1] + c01[3]) if (c01[1] + c01[3]) else 0})
+        else:
+            log.update({"VAL_ASR": asr, "VAL_inner_relatived_distance": avg_rd})
+        self._log(args, log, i)
+        extra = {"continuous_actions_pred.pt": pr, "continuous_actions_gt.pt": gt}
+        if avg_l1 < self.min_val_avg_L1_loss:
+            self.min_val_avg_L1_loss = avg_l1
+            self._dump_val_images(self._save_patch(h.patch, str(i)), extra)
+        self._dump_val_images(self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step), extra)
+        self.val_CE_loss.append(avg_ce)
+        self.val_L1_loss.append(avg_l1)
+        self.val_ASR.append(asr)
+        self.val_inner_relatived_distance.append(avg_rd)
+        self._dump(val_CE_loss=self.val_CE_loss, val_L1_loss=self.val_L1_loss, val_ASR=self.val_ASR,
+                   val_inner_relatived_distance=self.val_inner_relatived_distance)
+        return val_it
 
 
 class UADADDPAttacker(_AttackerBase):

@@ -59,6 +59,42 @@ def test_attacker_api_runs(model, tmp_path, kind):
     assert saved.shape == (3, 12, 12) and saved.dtype == torch.float32
     assert len(att.train_CE_loss) >= 3 and all(np.isfinite(att.train_CE_loss))
     assert att.host.opt_step == 6          # 3 outer x 2 inner AdamW steps
+    # validation side effects of the reference (UADA.py:193-292, UPA.py:193-275, TMA.py:202-383): images of the last
+    # validation batch with the patch, metric lists as .pkl, restart state next to patch.pt
+    vd = os.path.join(tmp_path, "last", "val_related_data")
+    from PIL import Image
+    im = Image.open(os.path.join(vd, "0.png"))
+    assert im.size == (cfg.img, cfg.img) and os.path.exists(os.path.join(vd, "1.png"))
+    assert os.path.exists(os.path.join(tmp_path, "last", "attack_state.pt"))
+    assert os.path.exists(os.path.join(tmp_path, "0", "patch.pt")), "the first validation always improves on the initial best"
+    pk = {"UADA": ["val_MSE_Distance", "val_UAD"], "UPA": ["avg_reserve_loss", "avg_angle_loss"], "TMA": ["val_L1_loss", "val_ASR"]}[kind]
+    import pickle
+    for name in pk:
+        with open(os.path.join(tmp_path, f"{name}.pkl"), "rb") as f:
+            vals = pickle.load(f)
+        assert len(vals) == 1 and np.isfinite(vals[0]), (name, vals)
+    if kind == "TMA":
+        assert os.path.exists(os.path.join(vd, "continuous_actions_pred.pt"))
+        assert 0.0 <= att.val_ASR[0] <= 1.0
+
+
+def test_tma_gripper_validation_filters_on_clean_prediction(model, tmp_path):
+    """maskidx == [6]: samples whose CLEAN gripper prediction is wrong are dropped before the attacked forward, and the
+    0->other / 1->other / other->0 rates are logged (TMA.py:223-250,298-306,318-336)."""
+    from roboticattack_b200.white_patch.TMA import OpenVLAAttacker
+    cfg, sd = model
+    random.seed(2)
+    np.random.seed(2)
+    torch.manual_seed(2)
+    att = OpenVLAAttacker(sd, None, save_dir=str(tmp_path), optimizer="adamW", cfg=cfg)
+    att.val_batches = 2
+    logs = []
+    att._log = lambda args, data, step: logs.append(data)
+    data = loader(cfg, 2, 3, 16, 400, as_pil=True)
+    att.patchattack_unconstrained(data, data, num_iter=1, patch_size=[3, 8, 8], alpha=2e-3, maskidx=[6], geometry=False,
+                                  innerLoop=1, args=ARGS)
+    val = [d for d in logs if "VAL_avg_CE_loss" in d]
+    assert len(val) == 1 and "ALL_ASR_6" in val[0] and np.isfinite(val[0]["VAL_avg_L1_loss"])
 
 
 def test_tma_pgd_and_accumulate(model, tmp_path):
