@@ -568,6 +568,7 @@ class UADADDPAttacker(_AttackerBase):
         self.maskidx, self.innerLoop, self.geometry, self.use_wandb, self.MSE_weights = maskidx, innerLoop, geometry, use_wandb, MSE_weights
         self.val_every, self.val_batches = 200, 100
         self.val_CE_loss, self.val_MSE_Distance, self.val_UAD = [], [], []
+        self.MSE_Distance_best = 10000
 
     def setup(self, rank, world_size):
         import torch.distributed as dist
@@ -605,7 +606,43 @@ class UADADDPAttacker(_AttackerBase):
             log = {"TRAIN_attack_loss(CE)": pack[0].item(), "TRAIN_attack_loss (MSE_Distance)": pack[1].item(),
                    "TRAIN_UAD": pack[2].item(), "TRAIN_patch_gradient": pack[3].item(), "TRAIN_LR": cur_lr}
             logs.append(log)
-            if rank == 0 and i % self.val_every == 0 and self.save_dir:
-                self._save_patch(h.patch, "last", outer_iter=i, sched_step=i + 1)
+            if i % self.val_every == 0:
+                val_dataloader = val_dataloader or (self.dataloaders[1] if self.dataloaders and len(self.dataloaders) > 1 else None)
+                if val_dataloader is not None:
+                    self._validate(i, rank, world_size, val_dataloader, fe_mode, loss)
+                elif rank == 0 and self.save_dir:
+                    self._save_patch(h.patch, "last", outer_iter=i, sched_step=i + 1)
         self.train_logs = logs
         return h.patch.detach().cpu()
+
+    def _validate(self, i, rank, world_size, val_dataloader, fe_mode, loss):
+        """UADA_ddp.py:232-325: every rank runs ``val_batches`` forward-only batches of its validation shard, the per-batch
+        MSE distance / UAD / CE are averaged over BATCHES (not samples, unlike UADA.py), averaged over ranks, and rank 0 keeps
+        the patch with the lowest distance (+ the images of its last validation batch) and refreshes ``last``."""
+        import torch.distributed as dist
+        h = self.host
+        s = torch.zeros(3, dtype=torch.float64)
+        nb = 0
+        for j, data in enumerate(val_dataloader):
+            if j == self.val_batches:
+                break
+            data = dict(data)
+            data["labels"] = self.mask_labels(data["labels"].clone(), self.maskidx)
+            sc, _ = h.evaluate(data, fe_mode, loss)
+            s += torch.tensor([sc[_lib.S_LOSS].item(), sc[_lib.S_UAD].item(), sc[_lib.S_CE].item()], dtype=torch.float64)
+            nb += 1
+        avg = (s / max(nb, 1)).to(torch.float32).to(h.device)
+        if world_size > 1:
+            dist.all_reduce(avg, op=dist.ReduceOp.SUM)
+            avg /= world_size
+        mse, uad, ce = (float(v) for v in avg.cpu())
+        if rank == 0:
+            if self.save_dir:
+                if mse < self.MSE_Distance_best:
+                    self.MSE_Distance_best = mse
+                    self._dump_val_images(self._save_patch(h.patch, str(i)))
+                self._save_patch(h.patch, "last", outer_iter=i, sched_step=i + 1)
+            self.val_CE_loss.append(ce)
+            self.val_MSE_Distance.append(mse)
+            self.val_UAD.append(uad)
+            self.val_logs = getattr(self, "val_logs", []) + [{"VAL_MSE_Distance": mse, "VAL_UAD": uad, "step": i}]

@@ -28,6 +28,28 @@ def shard_batches(rank):
     return out
 
 
+def _worker_val(rank, world, port, outdir):
+    """Same loop with the per-rank validation pass (UADA_ddp.py:232-325) every outer iteration."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from roboticattack_b200.attacker import UADADDPAttacker
+    torch.set_num_threads(2)
+    cfg = tiny(**CFG)
+    sd = random_state_dict(cfg, seed=0, dtype=torch.float32, init="test")
+    random.seed(42)
+    np.random.seed(42)
+    torch.manual_seed(42 + rank)
+    att = UADADDPAttacker(sd, save_dir=os.path.join(outdir, "run"), patch_size=[3, P_HW, P_HW], lr=LR, bs=B_PER_RANK, warmup=WARMUP,
+                          num_iter=2, maskidx=[0, 1, 2], innerLoop=1, geometry=True, use_wandb=False, MSE_weights=5, cfg=cfg,
+                          device="cpu", engine_factory=OracleEngine, backend="gloo")
+    att.val_every, att.val_batches = 1, 2
+    patch = att.attack(rank, world, train_dataloader=shard_batches(rank), val_dataloader=shard_batches(rank + 10))
+    torch.save({"patch": patch, "val": (att.val_CE_loss, att.val_MSE_Distance, att.val_UAD)}, os.path.join(outdir, f"rank{rank}.pt"))
+    torch.distributed.destroy_process_group()
+
+
 def _worker(rank, world, port, outdir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import sys
@@ -105,3 +127,19 @@ def test_ddp_world2_matches_serial_semantics():
     assert (ref - torch.rand(3, P_HW, P_HW, generator=torch.Generator().manual_seed(42))).abs().max() > 0
     # the packed metric reduction: CE / loss / UAD are means over ranks, identical on both
     assert outs[0]["logs"] == outs[1]["logs"] and len(outs[0]["logs"]) == OUTER
+
+
+def test_ddp_world2_validation():
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker_val, args=(world, port, d), nprocs=world, join=True)
+        outs = [torch.load(os.path.join(d, f"rank{r}.pt")) for r in range(world)]
+        assert torch.equal(outs[0]["patch"], outs[1]["patch"]), "validation must not desynchronise the ranks' RNG streams"
+        ce, mse, uad = outs[0]["val"]
+        assert len(ce) == len(mse) == len(uad) == 2 and all(np.isfinite(v) for v in ce + mse + uad)
+        assert outs[1]["val"] == ([], [], []), "only rank 0 records the reduced validation metrics"
+        assert os.path.exists(os.path.join(d, "run", "last", "patch.pt")) and os.path.exists(os.path.join(d, "run", "0", "patch.pt"))
+        assert os.path.exists(os.path.join(d, "run", "last", "attack_state.pt"))
