@@ -243,6 +243,28 @@ class _AttackerBase(object):
                 pass
 
     @staticmethod
+    def filter_train(data):
+        """``filter_train`` of the reference (UADA.py:311-341, UPA.py / TMA.py alike), used for the gripper-only attack with
+        ``filterGripTrainTo1``: keep the samples whose gripper label is 31744 ("1") when there are 2..7 of them, a random
+        8 of them (``random.sample``: consumes the Python RNG stream, as in the reference) when there are more than 8, and
+        the batch unchanged otherwise (0, 1 or exactly 8 hits fall through every branch of the reference)."""
+        labels = data["labels"]
+        sup = labels[labels > lab.ACTION_TOKEN_BEGIN_IDX].view(-1, 7)
+        one_index = [i for i in range(sup.shape[0]) if int(sup[i, 6]) == 31744]
+        if 1 < len(one_index) < 8:
+            chosen = one_index
+        elif len(one_index) > 8:
+            chosen = random.sample(one_index, k=8)
+        else:
+            return data
+        out = dict(data)
+        for k in ("labels", "attention_mask", "input_ids"):
+            out[k] = data[k][chosen, :]
+        pv = data["pixel_values"]
+        out["pixel_values"] = [pv[i] for i in chosen] if isinstance(pv, (list, tuple)) else pv[chosen]
+        return out
+
+    @staticmethod
     def _next(iterator, loader):
         try:
             return next(iterator), iterator
@@ -274,6 +296,8 @@ class UADAAttacker(_AttackerBase):
         for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
             data = dict(data)
+            if filterGripTrainTo1 and len(maskidx) == 1 and maskidx[0] == 6:
+                data = self.filter_train(data)
             data["labels"] = self.mask_labels(data["labels"].clone(), maskidx)
             cur_lr = lr * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else lr
             scalars, pred = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind)
@@ -371,6 +395,8 @@ class UPAAttacker(_AttackerBase):
         for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
             data = dict(data)
+            if filterGripTrainTo1 and len(maskidx) == 1 and maskidx[0] == 6:
+                data = self.filter_train(data)
             labels = data["labels"].clone()
             if not reverse_direction:
                 labels = self.mask_labels(labels, maskidx)
@@ -452,6 +478,8 @@ class TMAAttacker(_AttackerBase):
         for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
             data = dict(data)
+            if filterGripTrainTo1 and len(maskidx) == 1 and maskidx[0] == 6:
+                data = self.filter_train(data)
             data["labels"] = lab.tma_labels(data["labels"], target)
             stepping = (i + 1) % accumulate_steps == 0
             cur_lr = alpha * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else alpha

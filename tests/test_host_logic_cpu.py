@@ -126,3 +126,30 @@ def test_resume_reproduces_uninterrupted_run(tmp_path):
     resumed = make(str(tmp_path / "resumed"), resume=os.path.join(part_dir, "last")).patchattack_unconstrained(batches[2:], None, **kw)
     assert torch.equal(full, resumed)
     assert not torch.equal(full, torch.load(os.path.join(part_dir, "last", "patch.pt")))
+
+
+def test_filter_train_matches_reference_branches():
+    """filterGripTrainTo1 (UADA.py:311-341): 2..7 gripper-closed samples -> keep them; > 8 -> random.sample of 8; else unchanged."""
+    import random
+    from roboticattack_b200.attacker import _AttackerBase
+
+    def batch(grips):
+        B, T = len(grips), 12
+        labels = torch.full((B, T), -100, dtype=torch.int64)
+        for b, g in enumerate(grips):
+            labels[b, T - 8:T - 1] = torch.tensor([31800] * 6 + [31744 if g else 31872])
+            labels[b, T - 1] = 2
+        return {"labels": labels, "input_ids": torch.arange(B * T).view(B, T), "attention_mask": torch.ones(B, T, dtype=torch.bool),
+                "pixel_values": [f"img{b}" for b in range(B)]}
+
+    d = batch([1, 0, 1, 1, 0])
+    f = _AttackerBase.filter_train(d)
+    assert f["pixel_values"] == ["img0", "img2", "img3"] and f["labels"].shape[0] == 3 and torch.equal(f["input_ids"], d["input_ids"][[0, 2, 3]])
+    for grips in ([0, 0, 0], [1, 0, 0], [1] * 8):            # 0, 1 or exactly 8 hits: every branch of the reference falls through
+        d = batch(grips)
+        assert _AttackerBase.filter_train(d) is d
+    d = batch([1] * 11 + [0])
+    random.seed(5)
+    f = _AttackerBase.filter_train(d)
+    random.seed(5)
+    assert f["pixel_values"] == [f"img{i}" for i in random.sample(list(range(11)), k=8)]
