@@ -72,6 +72,34 @@ class RandomPatchTransform:
     def denormalize(self, images, mean, std):
         return images * std[None, :, None, None] + mean[None, :, None, None]
 
+    # helpers kept under the reference's names (appply_random_transform.py:26-41,80-102); the engine itself never calls them
+    def rotation_matrix(self, theta):
+        theta = np.radians(theta)
+        c, s = np.cos(theta), np.sin(theta)
+        return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]], dtype=np.float32)
+
+    def shear_matrix(self, shx, shy):
+        return np.array([[1, shx, 0], [shy, 1, 0], [0, 0, 1]], dtype=np.float32)
+
+    def combined_transform_matrix(self):
+        """Same RNG protocol as the reference: u < 0.2 -> identity, else angle, shx, shy in that order."""
+        if np.random.rand() < 0.2:
+            return torch.eye(3, dtype=torch.float32)
+        angle = np.random.uniform(-self.angle, self.angle)
+        shx = np.random.uniform(-self.shx, self.shx)
+        shy = np.random.uniform(-self.shy, self.shy)
+        return torch.tensor(np.dot(self.shear_matrix(shx, shy), self.rotation_matrix(angle)))
+
+    def apply_affine_transform(self, image, transform_matrix):
+        """Generic [C,H,W] warp (bilinear, border padding, align_corners=False) with torch ops; the attack path uses the fused
+        CUDA front end instead."""
+        import torch.nn.functional as F
+        if image.ndim == 4:
+            image = image.squeeze(0)
+        aff = torch.as_tensor(transform_matrix, dtype=image.dtype, device=image.device)[:2, :].unsqueeze(0)
+        grid = F.affine_grid(aff, image.unsqueeze(0).size(), align_corners=False)
+        return F.grid_sample(image.unsqueeze(0), grid, align_corners=False, padding_mode="border")
+
     def _run(self, images, patch, mean, std, mode, geometry):
         obs = _as_uint8_batch(images, self.device)
         B, H, W, _ = obs.shape
