@@ -73,6 +73,10 @@ int attention_fwd_tc(const bf16* qkv, bf16* o, float* lse, const int* kv_len, in
 bool attention_fwd_tc2_supported(int N, int hd);
 int attention_fwd_tc2(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                       cudaStream_t s);
+// persistent tcgen05 forward with the whole score tile resident in TMEM (attention_fwd_tc3.cu): N <= 320
+bool attention_fwd_tc3_supported(int N, int hd);
+int attention_fwd_tc3(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
+                      cudaStream_t s);
 // tcgen05 backward (attention_bwd_tc.cu): head dims 64 / 72 / 128, any N; same contract as attention_bwd.
 bool attention_bwd_tc_supported(int N, int hd);
 int attention_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,

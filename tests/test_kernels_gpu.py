@@ -184,7 +184,7 @@ def test_attention(B, N, H, hd, causal, ragged, impl):
     try:
         _attention_case(B, N, H, hd, causal, ragged)
     finally:
-        _lib.check(L.vla_attention_set_impl(2))
+        _lib.check(L.vla_attention_set_impl(3))
 
 
 def _attention_case(B, N, H, hd, causal, ragged):
@@ -262,7 +262,7 @@ def test_attention_bwd_fused_rope(B, N, H, ragged, impl):
         for i, nm in enumerate("qkv"):
             close(dqkv[:, i * D:(i + 1) * D], gref[:, i * D:(i + 1) * D], 8.0, f"attn+rope d{nm}")
     finally:
-        _lib.check(L.vla_attention_set_impl(2))
+        _lib.check(L.vla_attention_set_impl(3))
 
 
 def test_attention_bwd_reproducible():
@@ -275,7 +275,7 @@ def test_attention_bwd_reproducible():
     o = torch.zeros(B * N, D, device="cuda", dtype=torch.bfloat16)
     lse = torch.empty(B, H, N, device="cuda")
     delta = torch.empty(B, H, N, device="cuda")
-    _lib.check(L.vla_attention_set_impl(2))
+    _lib.check(L.vla_attention_set_impl(3))
     _lib.check(L.vla_attention_fwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(lse), None, B, N, H, hd, 1, _lib.cur_stream()))
     outs = []
     for _ in range(2):
