@@ -30,16 +30,16 @@ for (B, N, H, hd, causal) in [(8, 288, 32, 128, 1), (8, 261, 16, 64, 0), (8, 256
         tf, tb = t(f), t(bwd)
         print(f"N={N} H={H} hd={hd} causal={causal} impl={impl}: fwd {tf:.1f} us ({fl/tf/1e6:.0f} TFLOP/s)  bwd {tb:.1f} us ({2.5*fl/tb/1e6:.0f} TFLOP/s)")
 
-# optional in-kernel timeline (build with VLA_NVCC_EXTRA=-DVLA_ATTN_TIMING): globaltimer stamps of CTA (0, 0)
+# optional in-kernel timeline of the backward (build with VLA_NVCC_EXTRA=-DVLA_ATTN_TIMING): %globaltimer stamps of CTA 0
 import ctypes
-if hasattr(L, "vla_attn_dbg_read") or True:
-    try:
-        fn = L.vla_attn_dbg_read
-        buf = (ctypes.c_ulonglong * 128)()
-        fn(buf)
-        for mode in (0, 1):
-            st = [buf[mode * 64 + i] for i in range(64)]
-            t0 = st[0]
-            print("mode", mode, " ".join(f"{i}:{(v - t0)}" for i, v in enumerate(st) if v))
-    except AttributeError:
-        pass
+try:
+    fn = L.vla_attn_dbg_read
+except AttributeError:
+    fn = None
+if fn is not None:
+    buf = (ctypes.c_ulonglong * 128)()
+    fn(buf)
+    for mode in (0, 1):
+        st = [buf[mode * 64 + i] for i in range(64)]
+        t0 = st[0]
+        print("mode", mode, " ".join(f"{i}:{(v - t0)}" for i, v in enumerate(st) if v))
