@@ -476,13 +476,12 @@ int vit_backward(vla_engine* e, int t, Transients& tr, cudaStream_t s) {
   bf16* dx = tr.a;       // gradient wrt x[i+1]
   bf16* dxm = tr.b;      // gradient wrt x_mid[i]
   GemmEpilogue plain;
+  // LayerScale backward (dx o gamma, the A operand of the branch's first backward GEMM) is emitted by the LayerNorm backward
+  // that produces dx; only the very first one needs its own launch.
+  if (v.layerscale) CK(scale_cols(dx, w.blk[v.used - 1].ls2, tr.c, Mv, d, s));
   for (int i = v.used - 1; i >= 0; --i) {
     const VitBlockW& k = w.blk[i];
-    const bf16* g = dx;
-    if (v.layerscale) {
-      CK(scale_cols(dx, k.ls2, tr.c, Mv, d, s));
-      g = tr.c;
-    }
+    const bf16* g = v.layerscale ? tr.c : dx;
     if (v.mlp % 8 == 0) {
       GemmEpilogue ep;   // GELU backward fused into the fc2^T GEMM epilogue
       ep.aux_mode = 1;
@@ -494,17 +493,16 @@ int vit_backward(vla_engine* e, int t, Transients& tr, cudaStream_t s) {
       CK(gelu_bwd(tr.wide, a.fc1_pre[i], tr.wide, Mv * v.mlp, s));
     }
     CK(G(tr.wide, v.mlp, k.fc1_t, v.mlp, tr.norm, d, Mv, d, v.mlp, plain, s));
-    CK(layernorm_bwd(tr.norm, a.x_mid[i], k.n2w, a.mean2[i], a.rstd2[i], dx, dxm, Mv, d, s));
-    g = dxm;
-    if (v.layerscale) {
-      CK(scale_cols(dxm, k.ls1, tr.c, Mv, d, s));
-      g = tr.c;
-    }
+    CK(layernorm_bwd(tr.norm, a.x_mid[i], k.n2w, a.mean2[i], a.rstd2[i], dx, dxm, Mv, d, s, v.layerscale ? k.ls1 : nullptr,
+                     v.layerscale ? tr.c : nullptr));
+    g = v.layerscale ? tr.c : dxm;
     CK(G(g, d, k.proj_t, d, tr.d, d, Mv, d, d, plain, s));
     CK(attention_bwd(a.qkv[i], a.attn_o[i], tr.d, a.lse[i], tr.delta, tr.qkv, nullptr, B, v.ntok, v.heads, v.hd, 0, nullptr,
                      nullptr, 0, s));
     CK(G(tr.qkv, 3 * d, k.qkv_t, 3 * d, tr.norm, d, Mv, d, 3 * d, plain, s));
-    CK(layernorm_bwd(tr.norm, a.x[i], k.n1w, a.mean1[i], a.rstd1[i], dxm, dx, Mv, d, s));
+    const bool more = v.layerscale && i > 0;
+    CK(layernorm_bwd(tr.norm, a.x[i], k.n1w, a.mean1[i], a.rstd1[i], dxm, dx, Mv, d, s, more ? w.blk[i - 1].ls2 : nullptr,
+                     more ? tr.c : nullptr));
   }
   // patch-token rows of d x[0] -> d conv output [B*np, d] -> d im2col rows [B*np, kpad]
   CK(copy_rows(dx, d, v.ntok, v.npre, tr.c, d, e->np, 0, B, e->np, d, s));

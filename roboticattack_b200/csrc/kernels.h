@@ -53,8 +53,9 @@ int scatter_rows(const bf16* src, const int* rows, bf16* dst, int R, int d, cuda
 int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* mean, float* rstd, int64_t M, int d,
                   float eps, cudaStream_t s);
 // dx_out = bf16(dres + bf16(layernorm_bwd(dy)))   (dres may be null)
+// optional second output: scaled = bf16(dx * gamma2[col]) (timm LayerScale backward of the branch dx enters next)
 int layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* mean, const float* rstd, const bf16* dres,
-                  bf16* dx, int64_t M, int d, cudaStream_t s);
+                  bf16* dx, int64_t M, int d, cudaStream_t s, const bf16* gamma2 = nullptr, bf16* scaled = nullptr);
 int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int64_t M, int d, float eps, cudaStream_t s);
 int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx, int64_t M,
                 int d, cudaStream_t s);

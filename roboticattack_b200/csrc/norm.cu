@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(NORM_THREADS) layernorm_fwd_kernel(const bf16*
 __global__ void __launch_bounds__(NORM_THREADS) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                                       const bf16* __restrict__ w, const float* __restrict__ mean_in,
                                                                       const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
-                                                                      bf16* __restrict__ dx, int d) {
+                                                                      bf16* __restrict__ dx, int d, const bf16* __restrict__ gamma2,
+                                                                      bf16* __restrict__ scaled) {
   __shared__ float red[32];
   pdl_trigger();
   pdl_wait();
@@ -118,6 +119,13 @@ __global__ void __launch_bounds__(NORM_THREADS) layernorm_bwd_kernel(const bf16*
       }
     }
     store8(dx + row * d + v * 8, o);
+    if (scaled) {   // the LayerScale backward of the branch this gradient enters next: bf16(bf16(dx) * gamma), fused here
+      float gv[8], sc[8];
+      load8(gamma2 + v * 8, gv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sc[k] = rbf(o[k]) * gv[k];
+      store8(scaled + row * d + v * 8, sc);
+    }
   });
 }
 
@@ -206,9 +214,11 @@ int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* m
   return 0;
 }
 int layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* mean, const float* rstd, const bf16* dres,
-                  bf16* dx, int64_t M, int d, cudaStream_t s) {
+                  bf16* dx, int64_t M, int d, cudaStream_t s, const bf16* gamma2, bf16* scaled) {
   if (int rc = check_dims(M, d, "layernorm_bwd")) return rc;
-  VLA_CHECK_CUDA(vla_launch(layernorm_bwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, dy, x, w, mean, rstd, dres, dx, d));
+  VLA_REQUIRE((gamma2 == nullptr) == (scaled == nullptr), "layernorm_bwd: gamma2 and scaled go together");
+  VLA_CHECK_CUDA(vla_launch(layernorm_bwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, dy, x, w, mean, rstd, dres, dx, d,
+                            gamma2, scaled));
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
