@@ -432,7 +432,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         if (MODE == MODE_DKV) mbar_wait(bar_full(slot), (g / RING) & 1);   // acquire the producer's lse / delta stores
         if (s == 0) drain_store();
         if (half * 32 < ncols) {
-          if (warp_active) {
+          // a 32 x 32 block entirely above the causal diagonal (or behind the key padding): P = dS = 0 without touching TMEM
+          bool chunk_masked;
+          if (MODE == MODE_DQ) chunk_masked = (col0 >= klen) || (causal && col0 > warp_row0 + 31);
+          else chunk_masked = causal && warp_row0 > col0 + 31;
+          if (warp_active && !chunk_masked) {
             uint32_t sv[32], dv[32];
             tmem_ld_32x32(tmem + lane_addr + t * 128 + half * 32, sv);
             tmem_ld_32x32(tmem + lane_addr + t * 128 + 64 + half * 32, dv);
@@ -488,8 +492,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
               if (MODE == MODE_DKV) st_shared_v4(sPt + chunk, pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
             }
             STAMP(MODE, threadIdx.x == 0 && g == 2, 46);
-          } else if (s == 0) {
-            // rows outside the sequence: zero once per item (the tensor core reads all 128 rows of the A operand)
+          } else if (warp_active || s == 0) {
+            // masked block: zeros for this step; rows outside the sequence: zero once per item (the tensor core reads all
+            // 128 rows of the A operand)
             if (g >= 1) mbar_wait(bar_bdone((g - 1) & 1), ((g - 1) >> 1) & 1);
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {

@@ -306,7 +306,8 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       }
       for (int s = 0; s < it.nsteps; ++s) {
         const int col0 = s * STEP + half * 32;
-        if (half * 32 < step_cols(it, s) && warp_active) {
+        const bool chunk_masked = (col0 >= klen) || (causal && col0 > warp_row0 + 31);   // 32 x 32 block with no visible key
+        if (half * 32 < step_cols(it, s) && warp_active && !chunk_masked) {
           uint32_t sv[32];
           tmem_ld_32x32(tmem + lane_addr + s * STEP + half * 32, sv);
           tmem_ld_wait();
@@ -345,7 +346,8 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         // its barrier again: a warp without work in this step (rows outside the sequence, no columns) would otherwise run
         // ahead and arrive twice within one phase of bar_pdone, completing it before the working warps have written P.
         if (gp >= 2) mbar_wait(bar_bdone(buf), ((gp - 2) >> 1) & 1);
-        if (half * 32 < ncols && warp_active) {
+        const bool chunk_masked = (col0 >= klen) || (causal && col0 > warp_row0 + 31);
+        if (half * 32 < ncols && warp_active && !chunk_masked) {
           uint32_t sv[32];
           tmem_ld_32x32(tmem + lane_addr + s * STEP + half * 32, sv);
           tmem_ld_wait();
@@ -378,8 +380,9 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
             const uint32_t chunk = (static_cast<uint32_t>(half * 4 + q4) ^ static_cast<uint32_t>(r & 7)) << 4;
             st_shared_v4(sPr + chunk, pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
           }
-        } else if (s < 2 && !warp_active) {
-          // query rows outside the sequence: zero both P buffers once per item (the tensor core reads all 128 rows)
+        } else if ((s < 2 && !warp_active) || (warp_active && chunk_masked && half * 32 < ncols)) {
+          // a block with no visible key: P = 0 for this step; query rows outside the sequence: zero both P buffers once per
+          // item (the tensor core reads all 128 rows)
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             const uint32_t chunk = (static_cast<uint32_t>(half * 4 + q4) ^ static_cast<uint32_t>(r & 7)) << 4;
