@@ -120,8 +120,8 @@ int vla_attention_bwd_rope(const void* qkv, const void* o, const void* dout, con
                            void* dqkv, const int32_t* kv_len, int B, int N, int H, int hd, int causal,
                            const float* cos_tab, const float* sin_tab, int rope_L, void* stream);
 /* Kernel selection, bit mask: bit 0 = persistent tcgen05 forward (hd 64/72/128), bit 1 = persistent tcgen05 backward
- * (hd 64/72/128), bit 2 = the earlier one-shot tcgen05 forward (comparison).  Default 3; 0 = pipelined mma.sync kernels only
- * (also the fallback for other head dims).  Env VLA_ATTN_IMPL sets the default. */
+ * (hd 64/72/128).  Default 3; 0 = pipelined mma.sync kernels only (also the fallback for other head dims).
+ * Env VLA_ATTN_IMPL sets the default. */
 int vla_attention_set_impl(int impl);
 int vla_rope_inplace(void* qkv, const float* cos_tab, const float* sin_tab, int64_t M, int L, int H, int hd, int dir,
                      void* stream);

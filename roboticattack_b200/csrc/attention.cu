@@ -599,13 +599,13 @@ int launch_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* ls
 
 }  // namespace
 
-// bit 0: tcgen05 forward (attention_fwd_tc3 for N <= 320, else the streaming attention_fwd_tc2); bit 1: tcgen05 backward;
-// bit 2: the earlier one-shot tcgen05 forward (comparison only).  Default 3; VLA_ATTN_IMPL overrides it at first use.
+// bit 0: tcgen05 forward (attention_fwd_tc3 for N <= 320, else the streaming attention_fwd_tc2); bit 1: tcgen05 backward.
+// Default 3; VLA_ATTN_IMPL overrides it at first use.
 int g_attn_impl = -1;
 static int attn_impl() {
   if (g_attn_impl < 0) {
     const char* e = getenv("VLA_ATTN_IMPL");
-    g_attn_impl = e ? (atoi(e) & 7) : 3;
+    g_attn_impl = e ? (atoi(e) & 3) : 3;
   }
   return g_attn_impl;
 }
@@ -615,8 +615,6 @@ int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B
   VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
   if ((attn_impl() & 1) && attention_fwd_tc3_supported(N, hd)) return attention_fwd_tc3(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   if ((attn_impl() & 1) && attention_fwd_tc2_supported(N, hd)) return attention_fwd_tc2(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
-  if ((attn_impl() & 4) && attention_tc_supported(N, hd))   // the earlier one-shot kernel (kept for comparison)
-    return attention_fwd_tc(qkv, o, lse, kv_len, B, N, H, hd, causal, 1.f / sqrtf(static_cast<float>(hd)), s);
   if (hd <= 64) return launch_fwd<64>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   if (hd <= 80) return launch_fwd<80>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   return launch_fwd<128>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);

@@ -116,7 +116,7 @@ int vla_attention_bwd_rope(const void* qkv, const void* o, const void* dout, con
                        S(stream));
 }
 int vla_attention_set_impl(int impl) {
-  VLA_REQUIRE(impl >= 0 && impl <= 7, "vla_attention_set_impl: bit 0 = tcgen05 forward, bit 1 = tcgen05 backward (0 = legacy mma.sync only)");
+  VLA_REQUIRE(impl >= 0 && impl <= 3, "vla_attention_set_impl: bit 0 = tcgen05 forward, bit 1 = tcgen05 backward (0 = legacy mma.sync only)");
   g_attn_impl = impl;
   return 0;
 }

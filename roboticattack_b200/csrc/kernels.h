@@ -65,11 +65,6 @@ int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd,
 // causal != 0: key j visible to query i iff j <= i; kv_len (nullable) [B]: keys >= kv_len[b] are masked.
 int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                   cudaStream_t s);
-// tcgen05 implementations (attention_tc.cu): head dim 64 / 128, N <= 320.  attention_fwd / attention_bwd dispatch to them
-// when g_attn_impl != 0 and the shape is supported, else to the legacy mma.sync kernels.
-bool attention_tc_supported(int N, int hd);
-int attention_fwd_tc(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
-                     float scale, cudaStream_t s);
 // persistent streaming tcgen05 forward (attention_fwd_tc2.cu): head dims 64 / 72 / 128, any N
 bool attention_fwd_tc2_supported(int N, int hd);
 int attention_fwd_tc2(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
@@ -83,7 +78,7 @@ bool attention_bwd_tc_supported(int N, int hd);
 int attention_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                      const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
                      int rope_L, cudaStream_t s);
-extern int g_attn_impl;   // bit 0 = tcgen05 forward, bit 1 = tcgen05 backward where supported; -1 = unset (default 2 / env)
+extern int g_attn_impl;   // bit 0 = tcgen05 forward, bit 1 = tcgen05 backward where supported; -1 = unset (default 3 / env)
 // dqkv [B*N, 3*H*hd]; delta scratch [B, H, N] fp32
 // rope_cos / rope_sin (nullable; head dim 128 only): when given, d(q) and d(k) are returned with the rotary embedding's
 // backward already applied (gradients wrt the PRE-RoPE projections), i.e. rope_inplace(dqkv, ..., dir = -1) is fused.

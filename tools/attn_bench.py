@@ -23,7 +23,7 @@ for (B, N, H, hd, causal) in [(8, 288, 32, 128, 1), (8, 261, 16, 64, 0), (8, 256
     delta = torch.empty(B, H, N, device="cuda")
     dqkv = torch.empty_like(qkv)
     fl = 4.0 * B * H * N * N * hd * (0.5 if causal else 1.0)
-    for impl in (0, 3, 6):
+    for impl in (0, 3):
         L.vla_attention_set_impl(impl)
         f = lambda: _lib.check(L.vla_attention_fwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(lse), None, B, N, H, hd, causal, _lib.cur_stream()))
         bwd = lambda: _lib.check(L.vla_attention_bwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(do), _lib.ptr(lse), _lib.ptr(delta), _lib.ptr(dqkv), None, B, N, H, hd, causal, _lib.cur_stream()))
