@@ -145,6 +145,11 @@ struct GemmCfg {
   static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  // Ring slots released in pairs (one tcgen05.commit per two k-blocks): a tcgen05 instruction costs the issuing thread ~50 ns,
+  // which bounds the N = 128 CTA-pair variant (+10-20 % with 8 slots); with 4-6 slots the later release of the even slot
+  // costs more than the saved commit (measured), so only the 8-slot ring uses it.
+  static constexpr bool PAIR_RELEASE = STAGES >= 8;
+  static_assert(!PAIR_RELEASE || STAGES % 2 == 0, "paired slot release needs an even ring");
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 or 256: power of two >= 32
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
@@ -464,7 +469,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int row_a = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
         const int row_b = n_blk * BLOCK_N + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          // PAIR_RELEASE: slots are released two at a time on the odd slot's barrier (see GemmCfg)
+          if (!Cfg::PAIR_RELEASE || (stage & 1) == 0) mbar_wait(empty_bar(stage | (Cfg::PAIR_RELEASE ? 1 : 0)), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           if (CTAS == 1) {
             mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
@@ -512,7 +518,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               // advance 32 B (= UMMA_K bf16) inside the 128 B swizzle row: +2 in the (addr >> 4) field
               umma_bf16_ss<CTAS>(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit<CTAS>(empty_bar(stage));
+            if (!Cfg::PAIR_RELEASE || (stage & 1)) umma_commit<CTAS>(empty_bar(stage));
             if (kb == num_k_blocks - 1) umma_commit<CTAS>(tfull_bar(acc));
           }
           __syncwarp();
