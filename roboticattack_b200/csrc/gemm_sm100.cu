@@ -98,7 +98,39 @@ struct GemmArgs {
   void* out;
   GemmEpilogue epi;
   int epi_sleep_ns;   // back-off between polls of the epilogue warps' wait for the accumulator (0 = plain try_wait loop)
+  int wide;           // every epilogue tensor is 32-byte aligned with a 32-byte multiple row pitch: 256-bit global accesses
 };
+
+// 256-bit global accesses (sm_100: LDG/STG.256).  An epilogue thread owns 64 contiguous bytes of its row per chunk; with
+// 128-bit accesses every warp instruction touches half of 32 different sectors, with 256-bit ones it moves whole sectors
+// and the chunk takes half as many LSU instructions and L2 requests.
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+// 32 bytes of one row: one 256-bit store when the launch allows it, else two 128-bit ones
+__device__ __forceinline__ void store32(void* p, bool wide, const uint4& a, const uint4& b) {
+  if (wide) {
+    st_global_256(p, a, b);
+  } else {
+    reinterpret_cast<uint4*>(p)[0] = a;
+    reinterpret_cast<uint4*>(p)[1] = b;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* x) {
+  return make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+}
+// one row x 32 bf16 columns (64 bytes)
+__device__ __forceinline__ void store_row32(bf16* p, bool wide, const float (&x)[32]) {
+  store32(p, wide, pack8(x), pack8(x + 8));
+  store32(p + 16, wide, pack8(x + 16), pack8(x + 24));
+}
 
 // Wait of the 8 epilogue warps for the MMAs of their tile (most of a tile's duration): optional nanosleep back-off between
 // polls so that 256 threads do not compete with the producer / MMA warps for issue slots and power.
@@ -179,18 +211,33 @@ __device__ __forceinline__ void load_side(const GemmArgs& g, const uint4* p, int
   const GemmEpilogue& e = g.epi;
   if (p != nullptr) {
     const int nq = min(4, (g.N - col) / 8);   // 16-byte groups of the chunk inside N
+    if (g.wide && nq == 4) {
+      ld_global_256(p, buf[0], buf[1]);
+      ld_global_256(p + 2, buf[2], buf[3]);
+    } else {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (q < nq) buf[q] = p[q];
-    if (e.aux_mode == 2) {
+      for (int q = 0; q < 4; ++q)
+        if (q < nq) buf[q] = p[q];
+    }
+    if (e.aux_mode == 2) {   // + 64 bf16
+      if (g.wide) {
+        ld_global_256(p + 8, buf[4], buf[5]);
+        ld_global_256(p + 10, buf[6], buf[7]);
+      } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) buf[4 + q] = p[8 + q];   // + 64 bf16
+        for (int q = 0; q < 4; ++q) buf[4 + q] = p[8 + q];
+      }
     }
   }
   if (e.aux_mode == 0 && e.bias != nullptr && col + 32 <= g.N) {
     const uint4* bp = reinterpret_cast<const uint4*>(e.bias + col);
+    if (g.wide) {
+      ld_global_256(bp, buf[4], buf[5]);
+      ld_global_256(bp + 2, buf[6], buf[7]);
+    } else {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) buf[4 + q] = __ldg(bp + q);
+      for (int q = 0; q < 4; ++q) buf[4 + q] = __ldg(bp + q);
+    }
   }
 }
 
@@ -203,20 +250,30 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
   const int rrow = e.resid_mod ? row_in % e.resid_mod : row;
   const bool full = (col0 + 32 <= g.N);
   if (e.aux_mode == 1) {   // GELU backward: dpre = bf16(dy) * gelu'(pre)
-    uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0);
+    bf16* op = static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (col0 + q * 8 + 8 > g.N) break;   // ragged last chunk (N % 8 == 0)
-      const uint4 u = side[q];
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-      uint32_t o[4];
+    for (int h = 0; h < 2; ++h) {
+      uint4 o4[2];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 pre = unpack_bf16x2(w[t]);
-        const float d0 = rbf(__uint_as_float(acc[q * 8 + t * 2])), d1 = rbf(__uint_as_float(acc[q * 8 + t * 2 + 1]));
-        o[t] = pack_bf16x2(d0 * gelu_erf_grad(pre.x), d1 * gelu_erf_grad(pre.y));
+      for (int qq = 0; qq < 2; ++qq) {
+        const int q = h * 2 + qq;
+        const uint4 u = side[q];   // groups beyond a ragged N hold stale registers: computed, never stored
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 pre = unpack_bf16x2(w[t]);
+          const float d0 = rbf(__uint_as_float(acc[q * 8 + t * 2])), d1 = rbf(__uint_as_float(acc[q * 8 + t * 2 + 1]));
+          o[t] = pack_bf16x2(d0 * gelu_erf_grad(pre.x), d1 * gelu_erf_grad(pre.y));
+        }
+        o4[qq] = make_uint4(o[0], o[1], o[2], o[3]);
       }
-      op[q] = make_uint4(o[0], o[1], o[2], o[3]);
+      if (full) {
+        store32(op + h * 16, g.wide, o4[0], o4[1]);
+      } else {   // ragged last chunk (N % 8 == 0)
+        if (col0 + h * 16 + 8 <= g.N) reinterpret_cast<uint4*>(op + h * 16)[0] = o4[0];
+        if (col0 + h * 16 + 16 <= g.N) reinterpret_cast<uint4*>(op + h * 16)[1] = o4[1];
+      }
     }
     return;
   }
@@ -224,7 +281,11 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
     const int64_t gcol = static_cast<int64_t>(col0 / 64) * 128 + (col0 % 64);
     bf16* dgp = static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + gcol;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int h = 0; h < 2; ++h) {
+     uint4 og4[2], ou4[2];
+#pragma unroll
+     for (int qq = 0; qq < 2; ++qq) {
+      const int q = h * 2 + qq;
       const uint4 gu4 = side[q];        // prefetched one chunk ahead (load_side)
       const uint4 uu4 = side[4 + q];
       const uint32_t gw[4] = {gu4.x, gu4.y, gu4.z, gu4.w}, uw[4] = {uu4.x, uu4.y, uu4.z, uu4.w};
@@ -246,20 +307,26 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
         og[t] = pack_bf16x2(rg[0], rg[1]);
         ou[t] = pack_bf16x2(ru[0], ru[1]);
       }
-      *reinterpret_cast<uint4*>(dgp + q * 8) = make_uint4(og[0], og[1], og[2], og[3]);
-      *reinterpret_cast<uint4*>(dgp + 64 + q * 8) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+      og4[qq] = make_uint4(og[0], og[1], og[2], og[3]);
+      ou4[qq] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+     }
+     store32(dgp + h * 16, g.wide, og4[0], og4[1]);
+     store32(dgp + 64 + h * 16, g.wide, ou4[0], ou4[1]);
     }
     return;
   }
   if (full && !e.bias && !e.gamma && !e.resid && !e.act && !e.out_f32) {
     // plain GEMM (every input-gradient GEMM, q|k|v, gate|up): one packed cvt per pair, four 16-byte stores
-    uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0);
+    bf16* op = static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0;
+    uint4 o4[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      op[q] = make_uint4(pack_bf16x2(__uint_as_float(acc[q * 8]), __uint_as_float(acc[q * 8 + 1])),
+      o4[q] = make_uint4(pack_bf16x2(__uint_as_float(acc[q * 8]), __uint_as_float(acc[q * 8 + 1])),
                          pack_bf16x2(__uint_as_float(acc[q * 8 + 2]), __uint_as_float(acc[q * 8 + 3])),
                          pack_bf16x2(__uint_as_float(acc[q * 8 + 4]), __uint_as_float(acc[q * 8 + 5])),
                          pack_bf16x2(__uint_as_float(acc[q * 8 + 6]), __uint_as_float(acc[q * 8 + 7])));
+    store32(op, g.wide, o4[0], o4[1]);
+    store32(op + 16, g.wide, o4[2], o4[3]);
     return;
   }
   float x[32];
@@ -283,11 +350,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = rbf(x[j]);
     if (e.preact_out) {
-      uint4* pp = reinterpret_cast<uint4*>(e.preact_out + static_cast<int64_t>(row_in) * g.ldc + col0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        pp[q] = make_uint4(pack_bf16x2(x[q * 8], x[q * 8 + 1]), pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]),
-                           pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]));
+      store_row32(e.preact_out + static_cast<int64_t>(row_in) * g.ldc + col0, g.wide, x);
     }
     if (e.act == 1) {
       if (e.gamma || e.resid) {
@@ -326,15 +389,14 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
       }
     }
     if (e.out_f32) {
-      float4* op = reinterpret_cast<float4*>(static_cast<float*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) op[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
-    } else {
-      uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0);
+      float* op = static_cast<float*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        op[q] = make_uint4(pack_bf16x2(x[q * 8], x[q * 8 + 1]), pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]),
-                           pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]), pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]));
+        store32(op + q * 8, g.wide,
+                make_uint4(__float_as_uint(x[q * 8]), __float_as_uint(x[q * 8 + 1]), __float_as_uint(x[q * 8 + 2]), __float_as_uint(x[q * 8 + 3])),
+                make_uint4(__float_as_uint(x[q * 8 + 4]), __float_as_uint(x[q * 8 + 5]), __float_as_uint(x[q * 8 + 6]), __float_as_uint(x[q * 8 + 7])));
+    } else {
+      store_row32(static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0, g.wide, x);
     }
   } else {
     // ragged N edge: scalar path.  Fully unrolled with static indices: a dynamically indexed x[] would be placed in
@@ -386,22 +448,14 @@ __device__ __forceinline__ void epilogue_store_pair(const GemmArgs& g, const uin
       }
     }
   }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    reinterpret_cast<uint4*>(oa)[q] = make_uint4(pack_bf16x2(xa[q * 8], xa[q * 8 + 1]), pack_bf16x2(xa[q * 8 + 2], xa[q * 8 + 3]),
-                                                 pack_bf16x2(xa[q * 8 + 4], xa[q * 8 + 5]), pack_bf16x2(xa[q * 8 + 6], xa[q * 8 + 7]));
-    reinterpret_cast<uint4*>(ob)[q] = make_uint4(pack_bf16x2(xb[q * 8], xb[q * 8 + 1]), pack_bf16x2(xb[q * 8 + 2], xb[q * 8 + 3]),
-                                                 pack_bf16x2(xb[q * 8 + 4], xb[q * 8 + 5]), pack_bf16x2(xb[q * 8 + 6], xb[q * 8 + 7]));
-  }
+  store_row32(oa, g.wide, xa);
+  store_row32(ob, g.wide, xb);
   if (e.pair_mode == 2) {   // act = bf16(bf16(silu(gate)) * up), feature index = (group * 64) + offset inside the gate half
     bf16* ap = e.act_out + static_cast<int64_t>(row) * e.ld_act + (col_a / 128) * 64 + (col_a & 63);
     float y[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) y[j] = rbf(xa[j] * sigmoid_fast(xa[j])) * xb[j];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      reinterpret_cast<uint4*>(ap)[q] = make_uint4(pack_bf16x2(y[q * 8], y[q * 8 + 1]), pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]),
-                                                   pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]), pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]));
+    store_row32(ap, g.wide, y);
   }
 }
 
@@ -687,6 +741,15 @@ int launch_variant(int ctas, int block_n, const bf16* A, int64_t lda, const bf16
     sleep_ns = e ? atoi(e) : 0;
   }
   g.epi_sleep_ns = sleep_ns;
+  {
+    auto ok = [](const void* p, int64_t ld_elems, int elem) {
+      return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 31) == 0 && (ld_elems * elem) % 32 == 0);
+    };
+    static int no_wide = -1;
+    if (no_wide < 0) no_wide = getenv("VLA_GEMM_NO_WIDE") ? 1 : 0;   // A/B switch
+    g.wide = !no_wide && ok(out, ldc, epi.out_f32 ? 4 : 2) && ok(epi.resid, epi.ldr, 2) && ok(epi.aux, epi.ldaux, 2) &&
+             ok(epi.preact_out, ldc, 2) && ok(epi.act_out, epi.ld_act, 2) && ok(epi.bias, 16, 2);
+  }
   CUtensorMap ma, mbm;
   if (int rc = get_tmap(A, lda, M, K, BLOCK_M, &ma)) return rc;
   if (int rc = get_tmap(W, ldw, N, K, block_n / ctas, &mbm)) return rc;
