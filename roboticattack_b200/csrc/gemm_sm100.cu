@@ -437,14 +437,25 @@ __device__ __forceinline__ void epilogue_store_pair(const GemmArgs& g, const uin
     const float4* cp = reinterpret_cast<const float4*>(e.rope_cos + pos * 64 + (col_a & 63));
     const float4* sp = reinterpret_cast<const float4*>(e.rope_sin + pos * 64 + (col_a & 63));
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 c4 = __ldg(cp + q), s4 = __ldg(sp + q);
-      const float c[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+    for (int q = 0; q < 4; ++q) {   // the tables are fp32 [rope_L, 64]: 128 bytes of this lane's position per table and chunk
+      uint4 cu[2], su[2];
+      if (g.wide) {
+        ld_global_256(cp + 2 * q, cu[0], cu[1]);
+        ld_global_256(sp + 2 * q, su[0], su[1]);
+      } else {
+        cu[0] = __ldg(reinterpret_cast<const uint4*>(cp) + 2 * q);
+        cu[1] = __ldg(reinterpret_cast<const uint4*>(cp) + 2 * q + 1);
+        su[0] = __ldg(reinterpret_cast<const uint4*>(sp) + 2 * q);
+        su[1] = __ldg(reinterpret_cast<const uint4*>(sp) + 2 * q + 1);
+      }
+      const uint32_t cw[8] = {cu[0].x, cu[0].y, cu[0].z, cu[0].w, cu[1].x, cu[1].y, cu[1].z, cu[1].w};
+      const uint32_t sw[8] = {su[0].x, su[0].y, su[0].z, su[0].w, su[1].x, su[1].y, su[1].z, su[1].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float x1 = xa[q * 4 + k], x2 = xb[q * 4 + k];
-        xa[q * 4 + k] = rbf(x1 * c[k]) + rbf(-x2 * sn[k]);   // q*cos + rotate_half(q)*sin
-        xb[q * 4 + k] = rbf(x2 * c[k]) + rbf(x1 * sn[k]);
+      for (int k = 0; k < 8; ++k) {
+        const float c = __uint_as_float(cw[k]), sn = __uint_as_float(sw[k]);
+        const float x1 = xa[q * 8 + k], x2 = xb[q * 8 + k];
+        xa[q * 8 + k] = rbf(x1 * c) + rbf(-x2 * sn);   // q*cos + rotate_half(q)*sin
+        xb[q * 8 + k] = rbf(x2 * c) + rbf(x1 * sn);
       }
     }
   }
@@ -748,7 +759,8 @@ int launch_variant(int ctas, int block_n, const bf16* A, int64_t lda, const bf16
     static int no_wide = -1;
     if (no_wide < 0) no_wide = getenv("VLA_GEMM_NO_WIDE") ? 1 : 0;   // A/B switch
     g.wide = !no_wide && ok(out, ldc, epi.out_f32 ? 4 : 2) && ok(epi.resid, epi.ldr, 2) && ok(epi.aux, epi.ldaux, 2) &&
-             ok(epi.preact_out, ldc, 2) && ok(epi.act_out, epi.ld_act, 2) && ok(epi.bias, 16, 2);
+             ok(epi.preact_out, ldc, 2) && ok(epi.act_out, epi.ld_act, 2) && ok(epi.bias, 16, 2) &&
+             ok(epi.rope_cos, 8, 4) && ok(epi.rope_sin, 8, 4);
   }
   CUtensorMap ma, mbm;
   if (int rc = get_tmap(A, lda, M, K, BLOCK_M, &ma)) return rc;
