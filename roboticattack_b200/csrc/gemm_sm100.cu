@@ -101,6 +101,19 @@ struct GemmArgs {
   int wide;           // every epilogue tensor is 32-byte aligned with a 32-byte multiple row pitch: 256-bit global accesses
 };
 
+// The epilogue mode is a template parameter of the kernel: one kernel that branches over every mode at run time is ~9400
+// instructions (150 KB) of which a launch executes ~1600 scattered ones, and the epilogue warps then lose ~18 % of their
+// samples to instruction-fetch stalls (ncu stall_no_inst on the fc1+GELU shape).
+enum : int {
+  EPI_PLAIN = 0,       // bf16 store of whole 32-column chunks, nothing else (N % 32 == 0)
+  EPI_GENERAL = 1,     // bias / LayerScale / residual / fp32 output / saved pre-activation, ragged N
+  EPI_GELU = 2,        // EPI_GENERAL + GELU
+  EPI_GELU_BWD = 3,    // aux_mode 1
+  EPI_SWIGLU_BWD = 4,  // aux_mode 2
+  EPI_PAIR = 5,        // pair_mode 1 (RoPE) / 2 (SwiGLU forward)
+};
+template <int EPI> constexpr int kAuxMode = EPI == EPI_GELU_BWD ? 1 : (EPI == EPI_SWIGLU_BWD ? 2 : 0);
+
 // 256-bit global accesses (sm_100: LDG/STG.256).  An epilogue thread owns 64 contiguous bytes of its row per chunk; with
 // 128-bit accesses every warp instruction touches half of 32 different sectors, with 256-bit ones it moves whole sectors
 // and the chunk takes half as many LSU instructions and L2 requests.
@@ -190,16 +203,18 @@ struct GemmCfg {
 // The per-thread "side" operand of a chunk (64 contiguous bytes of this thread's row: the residual, or the saved
 // pre-activation of the GELU backward) is the only epilogue input with a full L2 / HBM latency; the epilogue loop
 // fetches it one chunk ahead (side_ptr + load_side), so the latency hides behind the MMAs / the previous chunk.
+template <int EPI>
 __device__ __forceinline__ const uint4* side_ptr(const GemmArgs& g, int row_in, int col0) {
   const GemmEpilogue& e = g.epi;
-  if (row_in >= g.M || col0 >= g.N) return nullptr;
+  constexpr int aux_mode = kAuxMode<EPI>;
+  if (EPI == EPI_PLAIN || row_in >= g.M || col0 >= g.N) return nullptr;
   const int row = e.out_group ? (row_in / e.out_group) * e.out_stride + e.out_offset + row_in % e.out_group : row_in;
   // GELU backward: N % 8 == 0 is enough (SigLIP's 4304-wide MLP); load_side fetches only the 16-byte groups inside N
-  if (e.aux_mode == 1) return reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + col0);
+  if (aux_mode == 1) return reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + col0);
   if (col0 + 32 > g.N) return nullptr;
-  if (e.aux_mode == 2)   // saved gate|up pre-activations, interleaved [gate 64 | up 64]: gate chunk here, up chunk 64 elements on
+  if (aux_mode == 2)   // saved gate|up pre-activations, interleaved [gate 64 | up 64]: gate chunk here, up chunk 64 elements on
     return reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + static_cast<int64_t>(col0 / 64) * 128 + (col0 % 64));
-  if (e.aux_mode == 0 && e.resid) {
+  if (aux_mode == 0 && e.resid) {
     const int rrow = e.resid_mod ? row_in % e.resid_mod : row;
     return reinterpret_cast<const uint4*>(e.resid + static_cast<int64_t>(rrow) * e.ldr + col0);
   }
@@ -207,8 +222,11 @@ __device__ __forceinline__ const uint4* side_ptr(const GemmArgs& g, int row_in, 
 }
 // buf[0..3] = the chunk's 64 bytes of the side operand; buf[4..7] = the "up" half of the SwiGLU pre-activations (aux_mode 2)
 // or, in the plain epilogue modes, the chunk's 32 bias values (also an L2-latency load when L1 is carved down to ~30 KB).
+template <int EPI>
 __device__ __forceinline__ void load_side(const GemmArgs& g, const uint4* p, int col, uint4 (&buf)[8]) {
   const GemmEpilogue& e = g.epi;
+  constexpr int aux_mode = kAuxMode<EPI>;
+  if (EPI == EPI_PLAIN) return;
   if (p != nullptr) {
     const int nq = min(4, (g.N - col) / 8);   // 16-byte groups of the chunk inside N
     if (g.wide && nq == 4) {
@@ -219,7 +237,7 @@ __device__ __forceinline__ void load_side(const GemmArgs& g, const uint4* p, int
       for (int q = 0; q < 4; ++q)
         if (q < nq) buf[q] = p[q];
     }
-    if (e.aux_mode == 2) {   // + 64 bf16
+    if (aux_mode == 2) {   // + 64 bf16
       if (g.wide) {
         ld_global_256(p + 8, buf[4], buf[5]);
         ld_global_256(p + 10, buf[6], buf[7]);
@@ -229,7 +247,7 @@ __device__ __forceinline__ void load_side(const GemmArgs& g, const uint4* p, int
       }
     }
   }
-  if (e.aux_mode == 0 && e.bias != nullptr && col + 32 <= g.N) {
+  if (aux_mode == 0 && e.bias != nullptr && col + 32 <= g.N) {
     const uint4* bp = reinterpret_cast<const uint4*>(e.bias + col);
     if (g.wide) {
       ld_global_256(bp, buf[4], buf[5]);
@@ -243,13 +261,16 @@ __device__ __forceinline__ void load_side(const GemmArgs& g, const uint4* p, int
 
 // One row x 32 columns of the accumulator -> global, with the fused epilogue.  `side` = this chunk's prefetched side operand
 // (valid when side_ptr() of the chunk is non-null).
+template <int EPI>
 __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const uint32_t (&acc)[32], int row_in, int col0,
                                                      const uint4 (&side)[8]) {
   const GemmEpilogue& e = g.epi;
+  constexpr int aux_mode = kAuxMode<EPI>;
+  constexpr bool kGelu = EPI == EPI_GELU;
   const int row = e.out_group ? (row_in / e.out_group) * e.out_stride + e.out_offset + row_in % e.out_group : row_in;
   const int rrow = e.resid_mod ? row_in % e.resid_mod : row;
   const bool full = (col0 + 32 <= g.N);
-  if (e.aux_mode == 1) {   // GELU backward: dpre = bf16(dy) * gelu'(pre)
+  if constexpr (aux_mode == 1) {   // GELU backward: dpre = bf16(dy) * gelu'(pre)
     bf16* op = static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -277,7 +298,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
     }
     return;
   }
-  if (e.aux_mode == 2) {   // SwiGLU backward on the interleaved [gate 64 | up 64] layout
+  if constexpr (aux_mode == 2) {   // SwiGLU backward on the interleaved [gate 64 | up 64] layout
     const int64_t gcol = static_cast<int64_t>(col0 / 64) * 128 + (col0 % 64);
     bf16* dgp = static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + gcol;
 #pragma unroll
@@ -315,8 +336,8 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
     }
     return;
   }
-  if (full && !e.bias && !e.gamma && !e.resid && !e.act && !e.out_f32) {
-    // plain GEMM (every input-gradient GEMM, q|k|v, gate|up): one packed cvt per pair, four 16-byte stores
+  if constexpr (EPI == EPI_PLAIN) {
+    // plain GEMM (every input-gradient GEMM, q|k|v, gate|up; the host dispatch guarantees whole chunks): one packed cvt per pair
     bf16* op = static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0;
     uint4 o4[4];
 #pragma unroll
@@ -352,7 +373,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
     if (e.preact_out) {
       store_row32(e.preact_out + static_cast<int64_t>(row_in) * g.ldc + col0, g.wide, x);
     }
-    if (e.act == 1) {
+    if (kGelu) {
       if (e.gamma || e.resid) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = rbf(gelu_erf(x[j]));
@@ -409,7 +430,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
       if (e.bias) v += b2f(e.bias[n]);
       v = rbf(v);
       if (e.preact_out) e.preact_out[static_cast<int64_t>(row_in) * g.ldc + n] = f2b(v);
-      if (e.act == 1) v = rbf(gelu_erf(v));
+      if (kGelu) v = rbf(gelu_erf(v));
       if (e.gamma) v = rbf(v * b2f(e.gamma[n]));
       if (e.resid) v = rbf(b2f(e.resid[static_cast<int64_t>(rrow) * e.ldr + n]) + v);
       if (e.out_f32)
@@ -470,7 +491,7 @@ __device__ __forceinline__ void epilogue_store_pair(const GemmArgs& g, const uin
   }
 }
 
-template <int BLOCK_N, int CTAS>
+template <int BLOCK_N, int CTAS, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmArgs g) {
@@ -607,12 +628,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int m_blk = tile % g.num_m_blocks, n_blk = tile / g.num_m_blocks;
       const int row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
-      const bool waited = g.epi.pair_mode != 0;
+      constexpr bool waited = EPI == EPI_PAIR;
       if (waited) {
         mbar_wait_backoff(tfull_bar(acc), acc_phase, g.epi_sleep_ns);
         tc_fence_after();
       }
-      if (g.epi.pair_mode) {
+      if constexpr (EPI == EPI_PAIR) {
         // chunks (4p + half) and (4p + half + 2) of every 128-column group: columns n and n + 64 in the same thread
 #pragma unroll 1
         for (int p = 0; p < BLOCK_N / 128; ++p) {
@@ -627,7 +648,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       } else {
         uint4 side_cur[8], side_nxt[8];
-        load_side(g, side_ptr(g, row, n_blk * BLOCK_N + half * 32), n_blk * BLOCK_N + half * 32, side_nxt);   // overlaps the wait for the MMAs
+        load_side<EPI>(g, side_ptr<EPI>(g, row, n_blk * BLOCK_N + half * 32), n_blk * BLOCK_N + half * 32, side_nxt);   // overlaps the wait for the MMAs
         if (!waited) {
           mbar_wait_backoff(tfull_bar(acc), acc_phase, g.epi_sleep_ns);
           tc_fence_after();
@@ -638,11 +659,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (col0 >= g.N) break;  // warp-uniform
 #pragma unroll
           for (int q = 0; q < 8; ++q) side_cur[q] = side_nxt[q];
-          if (c + 2 < BLOCK_N / 32) load_side(g, side_ptr(g, row, col0 + 64), col0 + 64, side_nxt);
+          if (c + 2 < BLOCK_N / 32) load_side<EPI>(g, side_ptr<EPI>(g, row, col0 + 64), col0 + 64, side_nxt);
           uint32_t v[32];
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();
-          if (row < g.M) epilogue_store_chunk(g, v, row, col0, side_cur);
+          if (row < g.M) epilogue_store_chunk<EPI>(g, v, row, col0, side_cur);
         }
       }
       tc_fence_before();
@@ -674,12 +695,12 @@ int get_tmap(const bf16* ptr, int64_t ld, int rows, int cols, int box_rows, CUte
 
 int g_num_sms = 0;
 
-template <int BLOCK_N, int CTAS>
-int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t stream) {
+template <int BLOCK_N, int CTAS, int EPI>
+int launch_gemm_epi(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CTAS>;
   static bool configured = false;
   if (!configured) {
-    VLA_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VLA_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, CTAS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     configured = true;
   }
@@ -713,7 +734,7 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g,
   attr[1].val.programmaticStreamSerializationAllowed = g_vla_pdl;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  VLA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BLOCK_N, CTAS>, ma, mb, g));
+  VLA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BLOCK_N, CTAS, EPI>, ma, mb, g));
   if (e1) {
     VLA_CHECK_CUDA(cudaEventRecord(e1, stream));
     g_prof.flops.push_back(2.0 * g.M * g.N * g.K);
@@ -735,6 +756,25 @@ constexpr Variant kVariants[] = {{2, 256, 0.92}, {2, 128, 0.80}, {1, 256, 0.76},
 }  // namespace
 
 namespace {
+int epilogue_kind(const GemmEpilogue& e, int N) {
+  if (e.pair_mode) return EPI_PAIR;
+  if (e.aux_mode == 1) return EPI_GELU_BWD;
+  if (e.aux_mode == 2) return EPI_SWIGLU_BWD;
+  if (e.act == 1) return EPI_GELU;
+  if (!e.bias && !e.gamma && !e.resid && !e.out_f32 && !e.preact_out && N % 32 == 0) return EPI_PLAIN;
+  return EPI_GENERAL;
+}
+template <int BLOCK_N, int CTAS>
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t stream) {
+  switch (epilogue_kind(g.epi, g.N)) {
+    case EPI_PLAIN: return launch_gemm_epi<BLOCK_N, CTAS, EPI_PLAIN>(ma, mb, g, stream);
+    case EPI_GELU: return launch_gemm_epi<BLOCK_N, CTAS, EPI_GELU>(ma, mb, g, stream);
+    case EPI_GELU_BWD: return launch_gemm_epi<BLOCK_N, CTAS, EPI_GELU_BWD>(ma, mb, g, stream);
+    case EPI_SWIGLU_BWD: return launch_gemm_epi<BLOCK_N, CTAS, EPI_SWIGLU_BWD>(ma, mb, g, stream);
+    case EPI_PAIR: return launch_gemm_epi<BLOCK_N, CTAS, EPI_PAIR>(ma, mb, g, stream);
+    default: return launch_gemm_epi<BLOCK_N, CTAS, EPI_GENERAL>(ma, mb, g, stream);
+  }
+}
 int launch_variant(int ctas, int block_n, const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc,
                    int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
   GemmArgs g;
