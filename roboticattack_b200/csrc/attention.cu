@@ -620,12 +620,16 @@ int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B
   return launch_fwd<128>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
 }
 
+// true when attention_bwd() can be called with o == NULL and `delta` already holding rowsum(dO * O) per (b, h, n)
+bool attention_bwd_takes_delta(int N, int hd) { return (attn_impl() & 2) && attention_bwd_tc_supported(N, hd); }
+
 int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                   const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
                   int rope_L, cudaStream_t s) {
   VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
   VLA_REQUIRE(rope_cos == nullptr || (hd == 128 && rope_sin != nullptr && rope_L > 0),
               "attention_bwd: the fused RoPE backward needs head dim 128 and both tables");
+  VLA_REQUIRE(o != nullptr || attention_bwd_takes_delta(N, hd), "attention_bwd: a precomputed delta (o == NULL) needs the tcgen05 backward");
   if ((attn_impl() & 2) && attention_bwd_tc_supported(N, hd))
     return attention_bwd_tc(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, rope_cos, rope_sin, rope_L, s);
   if (hd <= 64) return launch_bwd<64>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, nullptr, nullptr, 0, s);

@@ -666,14 +666,15 @@ int launch_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float*
   a.nitems = a.ntiles * B * H;
   a.scale = 1.f / sqrtf(static_cast<float>(hd));
   VLA_REQUIRE(hd <= 256, "attention_bwd_tc: head dim %d too large for the delta kernel", hd);
-  VLA_CHECK_CUDA(vla_launch(attn_delta_kernel, dim3(static_cast<unsigned>(B * N)), dim3(256), 0, s, o, dout, delta, N, H, hd));
+  // o == nullptr: delta was already written by the producer of dO (the delta epilogue of the o_proj backward GEMM)
+  if (o != nullptr) VLA_CHECK_CUDA(vla_launch(attn_delta_kernel, dim3(static_cast<unsigned>(B * N)), dim3(256), 0, s, o, dout, delta, N, H, hd));
   const int sms = (g_vla_sm_limit > 0 && g_vla_sm_limit < g_num_sms_attn) ? g_vla_sm_limit : g_num_sms_attn;
   const int grid = a.nitems < sms ? a.nitems : sms;
   VLA_CHECK_CUDA(vla_launch(attn_bwd_tc_kernel<HD, KS, MODE_DQ>, dim3(grid), dim3(BWD_THREADS), static_cast<size_t>(BwdSmem<HD, MODE_DQ>::TOTAL),
                             s, map_qkv, map_do, map_dqkv, a));
   VLA_CHECK_CUDA(vla_launch(attn_bwd_tc_kernel<HD, KS, MODE_DKV>, dim3(grid), dim3(BWD_THREADS),
                             static_cast<size_t>(BwdSmem<HD, MODE_DKV>::TOTAL), s, map_qkv, map_do, map_dqkv, a));
-  g_vla_launch_count += 3;
+  g_vla_launch_count += o != nullptr ? 3 : 2;
   return 0;
 }
 

@@ -962,6 +962,8 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
     VLA_CHECK_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(ML) * h * sizeof(bf16), s));
     CK(scatter_rows(e->hn, e->sup_rows, dx, R, h, s));
   }
+  const char* fd_env = getenv("VLA_FUSE_DELTA");   // read per step (A/B switch, tests)
+  const bool fuse_delta = fd_env == nullptr || atoi(fd_env) != 0;
   for (int l = l_first; l >= 0; --l) {
     const LlamaLayerW& w = e->lw[l];
     if (e->fuse_swiglu_bwd) {   // d(act) = dX . W_down, with the SwiGLU backward fused: writes d(gate|up) directly
@@ -976,10 +978,21 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
     }
     CK(G(e->tr[0].wide2, 2 * f, w.gu_t, 2 * f, e->tr[0].norm, h, ML, h, 2 * f, plain, s));
     CK(rmsnorm_bwd(e->tr[0].norm, la.x_mid[l], w.n2, la.rstd2[l], dx, dxm, ML, h, s));
-    CK(G(dxm, h, w.o_t, h, e->tr[0].d, h, ML, h, h, plain, s));
+    // hd == 128: delta = rowsum(dO * O) comes out of the o_proj backward GEMM's epilogue (no pass of its own over dO and O)
+    const bool fused_delta = fuse_delta && hd == 128 && attention_bwd_takes_delta(L, hd);
+    if (fused_delta) {
+      GemmEpilogue ep;
+      ep.aux = la.attn_o[l];
+      ep.ldaux = h;
+      ep.delta_out = e->tr[0].delta;
+      ep.delta_L = L;
+      CK(G(dxm, h, w.o_t, h, e->tr[0].d, h, ML, h, h, ep, s));
+    } else {
+      CK(G(dxm, h, w.o_t, h, e->tr[0].d, h, ML, h, h, plain, s));
+    }
     if (hd == 128) {   // RoPE backward fused into the attention backward's epilogues
-      CK(attention_bwd(la.qkv[l], la.attn_o[l], e->tr[0].d, la.lse[l], e->tr[0].delta, e->tr[0].qkv, e->kv_len, B, L, NH, hd, 1, e->rope_cos,
-                       e->rope_sin, L, s));
+      CK(attention_bwd(la.qkv[l], fused_delta ? nullptr : la.attn_o[l], e->tr[0].d, la.lse[l], e->tr[0].delta, e->tr[0].qkv, e->kv_len, B, L, NH,
+                       hd, 1, e->rope_cos, e->rope_sin, L, s));
     } else {
       CK(attention_bwd(la.qkv[l], la.attn_o[l], e->tr[0].d, la.lse[l], e->tr[0].delta, e->tr[0].qkv, e->kv_len, B, L, NH, hd, 1, nullptr, nullptr,
                        0, s));

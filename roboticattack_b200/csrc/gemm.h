@@ -44,6 +44,12 @@ struct GemmEpilogue {
   int rope_L = 0, rope_cols = 0;
   bf16* act_out = nullptr;
   int64_t ld_act = 0;
+  // delta_out != nullptr: the output is dO of an attention block with head dim 128 ([M = B * delta_L rows, N = H * 128]); the
+  //   epilogue also writes delta[b, h, n] = sum_c bf16(dO[b, n, h, c]) * O[b, n, h, c] (fp32, [B, H, delta_L], what the
+  //   attention backward needs) with O = aux (ld = ldaux).  An epilogue thread owns whole heads of its row, so the sum is
+  //   a plain serial reduction: no atomics, no extra pass over dO and O.  Plain epilogue otherwise; 256-wide tiles only.
+  float* delta_out = nullptr;
+  int delta_L = 0;
 };
 
 // Returns 0 on success. No allocation, no synchronisation; launches on `stream`.

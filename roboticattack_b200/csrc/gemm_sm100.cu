@@ -111,6 +111,7 @@ enum : int {
   EPI_GELU_BWD = 3,    // aux_mode 1
   EPI_SWIGLU_BWD = 4,  // aux_mode 2
   EPI_PAIR = 5,        // pair_mode 1 (RoPE) / 2 (SwiGLU forward)
+  EPI_DELTA = 6,       // plain + the attention backward's delta = rowsum(dO * O) per head (BLOCK_N = 256 only)
 };
 template <int EPI> constexpr int kAuxMode = EPI == EPI_GELU_BWD ? 1 : (EPI == EPI_SWIGLU_BWD ? 2 : 0);
 
@@ -208,6 +209,7 @@ __device__ __forceinline__ const uint4* side_ptr(const GemmArgs& g, int row_in, 
   const GemmEpilogue& e = g.epi;
   constexpr int aux_mode = kAuxMode<EPI>;
   if (EPI == EPI_PLAIN || row_in >= g.M || col0 >= g.N) return nullptr;
+  if (EPI == EPI_DELTA) return reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row_in) * e.ldaux + col0);   // O (N % 128 == 0)
   const int row = e.out_group ? (row_in / e.out_group) * e.out_stride + e.out_offset + row_in % e.out_group : row_in;
   // GELU backward: N % 8 == 0 is enough (SigLIP's 4304-wide MLP); load_side fetches only the 16-byte groups inside N
   if (aux_mode == 1) return reinterpret_cast<const uint4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + col0);
@@ -441,6 +443,31 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& g, const ui
   }
 }
 
+// EPI_DELTA: plain store of one row x 32 columns of dO, returns sum_j bf16(dO[j]) * O[j] over the chunk (side = O).
+__device__ __forceinline__ float epilogue_delta_chunk(const GemmArgs& g, const uint32_t (&acc)[32], int row, int col0,
+                                                      const uint4 (&side)[8]) {
+  bf16* op = static_cast<bf16*>(g.out) + static_cast<int64_t>(row) * g.ldc + col0;
+  float sum = 0.f;
+  uint4 o4[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t w[4] = {side[q].x, side[q].y, side[q].z, side[q].w};
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 ov = unpack_bf16x2(w[t]);
+      const float d0 = rbf(__uint_as_float(acc[q * 8 + t * 2])), d1 = rbf(__uint_as_float(acc[q * 8 + t * 2 + 1]));
+      sum = fmaf(d0, ov.x, sum);
+      sum = fmaf(d1, ov.y, sum);
+      o[t] = pack_bf16x2(d0, d1);
+    }
+    o4[q] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  store32(op, g.wide, o4[0], o4[1]);
+  store32(op + 16, g.wide, o4[2], o4[3]);
+  return sum;
+}
+
 // Two 32-column chunks (columns col_a.. and col_a + 64..) of one row: RoPE rotation or SwiGLU.
 __device__ __forceinline__ void epilogue_store_pair(const GemmArgs& g, const uint32_t (&va)[32], const uint32_t (&vb)[32],
                                                     int row, int col_a) {
@@ -646,6 +673,33 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           tmem_ld_wait();
           if (row < g.M) epilogue_store_pair(g, va, vb, row, col_a);
         }
+      } else if constexpr (EPI == EPI_DELTA) {
+        // the warp of column half `half` owns the head [half * 128, half * 128 + 128) of the 256-wide tile: 4 contiguous chunks
+        if constexpr (BLOCK_N == 256) {
+          const int head_col = n_blk * BLOCK_N + half * 128;
+          uint4 side_cur[8], side_nxt[8];
+          load_side<EPI>(g, side_ptr<EPI>(g, row, head_col), head_col, side_nxt);   // overlaps the wait for the MMAs
+          mbar_wait_backoff(tfull_bar(acc), acc_phase, g.epi_sleep_ns);
+          tc_fence_after();
+          if (head_col < g.N) {   // warp-uniform (N is a multiple of 128)
+            float dsum = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+              const int col0 = head_col + cc * 32;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) side_cur[q] = side_nxt[q];
+              if (cc + 1 < 4) load_side<EPI>(g, side_ptr<EPI>(g, row, col0 + 32), col0 + 32, side_nxt);
+              uint32_t v[32];
+              tmem_ld_32x32(taddr + static_cast<uint32_t>(half * 128 + cc * 32), v);
+              tmem_ld_wait();
+              if (row < g.M) dsum += epilogue_delta_chunk(g, v, row, col0, side_cur);
+            }
+            if (row < g.M) {
+              const int b = row / g.epi.delta_L, n = row - b * g.epi.delta_L;
+              g.epi.delta_out[(static_cast<int64_t>(b) * (g.N / 128) + head_col / 128) * g.epi.delta_L + n] = dsum;
+            }
+          }
+        }
       } else {
         uint4 side_cur[8], side_nxt[8];
         load_side<EPI>(g, side_ptr<EPI>(g, row, n_blk * BLOCK_N + half * 32), n_blk * BLOCK_N + half * 32, side_nxt);   // overlaps the wait for the MMAs
@@ -758,6 +812,7 @@ constexpr Variant kVariants[] = {{2, 256, 0.92}, {2, 128, 0.80}, {1, 256, 0.76},
 namespace {
 int epilogue_kind(const GemmEpilogue& e, int N) {
   if (e.pair_mode) return EPI_PAIR;
+  if (e.delta_out) return EPI_DELTA;
   if (e.aux_mode == 1) return EPI_GELU_BWD;
   if (e.aux_mode == 2) return EPI_SWIGLU_BWD;
   if (e.act == 1) return EPI_GELU;
@@ -772,6 +827,9 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g,
     case EPI_GELU_BWD: return launch_gemm_epi<BLOCK_N, CTAS, EPI_GELU_BWD>(ma, mb, g, stream);
     case EPI_SWIGLU_BWD: return launch_gemm_epi<BLOCK_N, CTAS, EPI_SWIGLU_BWD>(ma, mb, g, stream);
     case EPI_PAIR: return launch_gemm_epi<BLOCK_N, CTAS, EPI_PAIR>(ma, mb, g, stream);
+    case EPI_DELTA:
+      if constexpr (BLOCK_N == 256) return launch_gemm_epi<BLOCK_N, CTAS, EPI_DELTA>(ma, mb, g, stream);
+      else VLA_REQUIRE(false, "gemm: the delta epilogue needs a 256-wide tile");
     default: return launch_gemm_epi<BLOCK_N, CTAS, EPI_GENERAL>(ma, mb, g, stream);
   }
 }
@@ -842,6 +900,9 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
               "gemm: aux-mode epilogues need N %% 32 == 0 (GELU backward: N %% 8 == 0) and an aux tensor");
   VLA_REQUIRE(epi.pair_mode != 1 || (epi.rope_cos && epi.rope_sin && epi.rope_L > 0 && epi.rope_cols % 128 == 0), "gemm: bad RoPE epilogue");
   VLA_REQUIRE(epi.pair_mode != 2 || (epi.act_out && epi.ld_act % 8 == 0), "gemm: bad SwiGLU epilogue");
+  VLA_REQUIRE(!epi.delta_out || (N % 128 == 0 && epi.aux && epi.ldaux % 8 == 0 && epi.delta_L > 0 && M % epi.delta_L == 0 && !epi.aux_mode &&
+                                 !epi.pair_mode && !epi.bias && !epi.gamma && !epi.resid && !epi.act && !epi.out_f32 && !epi.out_group),
+              "gemm: bad delta epilogue (needs N %% 128 == 0, O in aux, M %% delta_L == 0 and no other epilogue option)");
   if (g_num_sms == 0) {
     int dev = 0;
     VLA_CHECK_CUDA(cudaGetDevice(&dev));
@@ -854,10 +915,11 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
   int ctas = 1, block_n = 256;
   if (g_forced_ctas) {
     ctas = g_forced_ctas;
-    block_n = g_forced_n;
+    block_n = epi.delta_out ? 256 : g_forced_n;
   } else {
     const uint64_t key = (static_cast<uint64_t>(M) << 42) ^ (static_cast<uint64_t>(N) << 21) ^ static_cast<uint64_t>(K) ^
-                         (g_vla_sm_limit > 0 ? (1ull << 62) : 0ull);   // the best variant depends on the SM budget
+                         (g_vla_sm_limit > 0 ? (1ull << 62) : 0ull) ^   // the best variant depends on the SM budget
+                         (epi.delta_out ? (1ull << 61) : 0ull);         // and the delta epilogue only has the 256-wide variants
     auto it = g_tuned.find(key);
     if (it != g_tuned.end()) {
       ctas = it->second.ctas;
@@ -874,6 +936,7 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
         VLA_CHECK_CUDA(cudaEventCreate(&e0));
         VLA_CHECK_CUDA(cudaEventCreate(&e1));
         for (const Variant& v : kVariants) {
+          if (epi.delta_out && v.block_n != 256) continue;
           float ms_min = 1e30f;
           for (int rep = 0; rep < 4; ++rep) {
             VLA_CHECK_CUDA(cudaEventRecord(e0, stream));
@@ -899,6 +962,7 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
       } else {
         double best = 1e300;
         for (const Variant& v : kVariants) {
+          if (epi.delta_out && v.block_n != 256) continue;
           const long tiles = static_cast<long>(ceil_div(M, BLOCK_M * v.ctas)) * ceil_div(N, v.block_n);
           const int sms = (g_vla_sm_limit > 0 && g_vla_sm_limit < g_num_sms) ? g_vla_sm_limit : g_num_sms;
           const long waves = (tiles + sms / v.ctas - 1) / (sms / v.ctas);

@@ -215,6 +215,43 @@ def test_last_layer_row_pruning_is_exact(tiny_setup, loss_kind, monkeypatch):
     assert outs[0][0].abs().sum() > 0
 
 
+def test_delta_from_gemm_epilogue_matches_delta_kernel(tiny_setup, monkeypatch):
+    """delta = rowsum(dO * O) of the Llama attention backward is produced by the o_proj backward GEMM's epilogue (head dim
+    128: an epilogue thread owns whole heads of its row).  Against the stand-alone delta kernel only the fp32 summation
+    order differs, so the patch gradient agrees to bf16 round-off of the few elements a last-bit change of delta can flip."""
+    cfg, sd, _, B, T = tiny_setup
+    batch = synthetic_batch(cfg, B, T, seed=78, ragged=True)
+    torch.manual_seed(2)
+    p = 10
+    patch = torch.rand(3, p, p).cuda()
+    from oracle import frontend as ofe
+    random.seed(4)
+    np.random.seed(4)
+    xy, theta = ofe.draw_placements(B, (cfg.img, cfg.img), (p, p), True)
+    outs = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("VLA_FUSE_DELTA", fuse)
+        monkeypatch.setenv("VLA_PRUNE_LAST", "0")      # both decoder layers take the fused path
+        eng = VLAEngine(cfg, B, T)
+        eng.load_state_dict(sd)
+        eng.set_batch(batch["obs"], batch["input_ids"], batch["attention_mask"], batch["labels"])
+        eng.set_placements(xy[None], theta[None])
+        dp = torch.zeros_like(patch)
+        sc = torch.zeros(_lib.NUM_SCALARS, device="cuda")
+        pred = torch.zeros(eng.num_supervised, dtype=torch.int32, device="cuda")
+        eng.fwd_bwd(patch, 0, _lib.FE_WARP, SPECS["uada"], dp, sc, pred)   # first call: the GEMM autotuner's dry runs
+        dp.zero_()
+        n0 = _lib.lib().vla_launch_count()
+        eng.fwd_bwd(patch, 0, _lib.FE_WARP, SPECS["uada"], dp, sc, pred)
+        torch.cuda.synchronize()
+        outs.append((dp.cpu(), sc.cpu(), _lib.lib().vla_launch_count() - n0))
+        del eng
+    assert torch.equal(outs[0][1][:_lib.S_GRAD_MEAN], outs[1][1][:_lib.S_GRAD_MEAN])   # the forward is untouched
+    assert outs[0][0].abs().sum() > 0
+    assert rel(outs[0][0], outs[1][0]) < 5e-3
+    assert outs[1][2] - outs[0][2] == cfg.llm.layers, "one delta launch less per decoder layer"
+
+
 def test_greedy_action_decode_vs_oracle(tiny_setup):
     """ActionPolicy.generate_action_tokens (predict_action of modeling_prismatic.py:506-536 on the engine, one forward-only
     pass per token) against the oracle's greedy decode in fp32: same tokens wherever the oracle's decision margin is above
