@@ -324,7 +324,7 @@ def engine_arm(args):
         _lib.check(lib.vla_profile_gemm_end(ctypes.byref(tm), ctypes.byref(fl), ctypes.byref(n)), "profile end")
         pk = peaks()
         traffic = None   # DRAM bytes of the GEMM launches of one step, from the committed ncu launch list of this command
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01n_gemm_dram_traffic.json")
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01o_gemm_dram_traffic.json")
         if os.path.exists(tpath) and world == 1:
             with open(tpath) as fh:
                 traffic = json.load(fh)["dram_bytes_per_step"]
@@ -332,7 +332,7 @@ def engine_arm(args):
         f = flops_per_sample(cfg, T, supervised_rows=4)             # maskidx 0,1,2 + EOS = 4 supervised rows per sample
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05, all launches of one step)", "achieved": round(ach, 1),
                 "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["bf16_sustained"], 4), "traffic": traffic,
-                "traffic_note": "dram__bytes_read+write summed over the GEMM launches of one step (ncu, caches flushed between launches; profiles/r01n_gemm_dram_traffic.json); algorithmic: 30 GB of weights + ~12 GB of activations",
+                "traffic_note": "dram__bytes_read+write summed over the GEMM launches of one step (ncu, caches flushed between launches; profiles/r01o_gemm_dram_traffic.json); algorithmic: 30 GB of weights + ~12 GB of activations",
                 "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
                 "gemm_launches_per_step": n.value, "gemm_ms_per_step": round(tm.value, 3),
                 "gemm_flops_per_step": fl.value, "algorithmic_flops_per_step": f["iter"] * B,
