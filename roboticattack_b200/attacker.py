@@ -73,7 +73,10 @@ class AttackEngineHost:
             src = self._vla
             if src is None:
                 raise _lib.VLAError("no weights: pass an HF model, a state dict or a loaded VLAEngine")
-            sd = src if isinstance(src, dict) else src.state_dict()
+            if isinstance(src, (str, os.PathLike)):   # the reference's `vla_path` (UADA_ddp.py:46): a torch.save'd state dict
+                sd = torch.load(src, map_location="cpu", weights_only=True, mmap=True)
+            else:
+                sd = src if isinstance(src, dict) else src.state_dict()
             self.engine.load_state_dict(sd, strict=False)
         self.engine.ensure_plan(B, T)
         return self.engine
@@ -605,6 +608,42 @@ class UADADDPAttacker(_AttackerBase):
         if self.host.device.type == "cuda":
             torch.cuda.set_device(self.host.device)
         self.host.rank, self.host.world_size = rank, world_size
+
+    def cleanup(self):
+        """UADA_ddp.py:134-136."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+
+    @classmethod
+    def run(cls, vla_path, dataset_name, save_dir, resize_patch, patch_size, lr, bs, warmup, num_iter, maskidx, innerLoop, geometry,
+            use_wandb, MSE_weights, world_size=None, **extra):
+        """UADA_ddp.py:327-336: one process per visible GPU, each constructing its own attacker.  ``vla_path`` is a file holding
+        the state dict (every rank loads it itself); ``dataset_name`` is a picklable callable ``(rank, world_size) ->
+        (train_loader, val_loader | None)`` standing in for the reference's RLDS dataset name (its TF loader is out of scope).
+        ``extra`` (cfg, backend, device, engine_factory, resume) goes to the constructor."""
+        import torch.multiprocessing as mp
+        world_size = world_size or torch.cuda.device_count()
+        instance_params = dict(vla=vla_path, dataloaders=dataset_name, save_dir=save_dir, resize_patch=resize_patch, patch_size=patch_size,
+                               lr=lr, bs=bs, warmup=warmup, num_iter=num_iter, maskidx=maskidx, innerLoop=innerLoop, geometry=geometry,
+                               use_wandb=use_wandb, MSE_weights=MSE_weights, **extra)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        mp.spawn(cls._attack_entry, args=(instance_params, world_size), nprocs=world_size)
+
+    @staticmethod
+    def _attack_entry(rank, instance_params, world_size):
+        """UADA_ddp.py:338-344."""
+        import torch.distributed as dist
+        os.environ["LOCAL_RANK"] = str(rank)
+        params = dict(instance_params)
+        if not dist.is_initialized():
+            dist.init_process_group(params.get("backend", "nccl"), rank=rank, world_size=world_size)
+        if callable(params["dataloaders"]):
+            params["dataloaders"] = params["dataloaders"](rank, world_size)
+        instance = UADADDPAttacker(**params)
+        instance.attack(rank, world_size)
+        instance.cleanup()
 
     def attack(self, rank, world_size, train_dataloader=None, val_dataloader=None):
         import torch.distributed as dist

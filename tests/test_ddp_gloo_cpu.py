@@ -143,3 +143,37 @@ def test_ddp_world2_validation():
         assert outs[1]["val"] == ([], [], []), "only rank 0 records the reduced validation metrics"
         assert os.path.exists(os.path.join(d, "run", "last", "patch.pt")) and os.path.exists(os.path.join(d, "run", "0", "patch.pt"))
         assert os.path.exists(os.path.join(d, "run", "last", "attack_state.pt"))
+
+
+def _loaders(rank, world):
+    return shard_batches(rank), None
+
+
+def test_ddp_run_classmethod_spawns_ranks():
+    """``OpenVLAAttacker.run(...)`` of UADA_ddp.py:327-344: spawns one process per rank, each loads the weights from
+    ``vla_path`` and its own data shard, runs ``attack`` and tears the process group down; rank 0 leaves ``last/patch.pt``."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from roboticattack_b200.white_patch.UADA_ddp import OpenVLAAttacker
+    cfg = tiny(**CFG)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    old = {k: os.environ.get(k) for k in ("MASTER_ADDR", "MASTER_PORT")}
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "vla.pt")
+            torch.save(random_state_dict(cfg, seed=0, dtype=torch.float32, init="test"), path)
+            OpenVLAAttacker.run(path, _loaders, os.path.join(d, "run"), False, [3, P_HW, P_HW], LR, B_PER_RANK, WARMUP, 2, [0, 1, 2], 1, True,
+                                False, 5, world_size=2, cfg=cfg, device="cpu", engine_factory=OracleEngine, backend="gloo")
+            patch = torch.load(os.path.join(d, "run", "last", "patch.pt"), weights_only=True)
+            assert patch.shape == (3, P_HW, P_HW) and patch.dtype == torch.float32 and 0 <= patch.min() and patch.max() <= 1
+            assert os.path.exists(os.path.join(d, "run", "last", "attack_state.pt"))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
