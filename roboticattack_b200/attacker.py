@@ -236,6 +236,62 @@ class _AttackerBase(object):
             with open(os.path.join(self.save_dir, f"{name}.pkl"), "wb") as f:
                 pickle.dump(values, f)
 
+    # ---- the reference's helper methods, same names and argument meaning (they are not on the engine's hot path: inside
+    # patchattack_unconstrained the engine computes all of this on the device) -----------------------------------------
+    SAVE_INFO_LISTS: tuple = ()
+
+    def save_info(self, path):
+        """``<path>/<list>.pkl`` for every metric list of the attack (UADA.py:341-353, UPA.py:309-325, TMA.py:454-468)."""
+        os.makedirs(path, exist_ok=True)
+        for name in self.SAVE_INFO_LISTS:
+            with open(os.path.join(path, f"{name}.pkl"), "wb") as f:
+                pickle.dump(getattr(self, name, []), f)
+
+    def plot_loss(self):
+        """Loss curves as ``<save_dir>/loss.png`` (UADA.py:76-91); skipped with a note when matplotlib is not installed."""
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+        except ImportError:
+            print("plot_loss: matplotlib is not installed; the .pkl lists written by save_info() hold the same data")
+            return None
+        names = [n for n in self.SAVE_INFO_LISTS if len(getattr(self, n, []))]
+        fig, axes = plt.subplots(1, max(len(names), 1), figsize=(5 * max(len(names), 1), 4))
+        for ax, n in zip(np.atleast_1d(axes), names):
+            ax.plot(getattr(self, n))
+            ax.set_title(n)
+        out = os.path.join(self.save_dir or ".", "loss.png")
+        fig.savefig(out)
+        plt.close(fig)
+        return out
+
+    def modifiy_labels(self, labels, target_action={"0": 0, "1": 1, "2": 2, "3": 3, "4": 4, "5": 5, "6": 6, "7": 7, "8": 8}):
+        """Write ``target_action[k]`` at the k-th supervised position of every row, entries equal to -100 left alone
+        (UADA.py:295-307, TMA.py:385-396; the reference's spelling of the name is kept).  In place, returns ``labels``."""
+        first = (labels != IGNORE_INDEX).int().argmax(dim=1)
+        for key, value in target_action.items():
+            if value != IGNORE_INDEX:
+                labels[torch.arange(labels.shape[0]), first + int(key)] = value
+        return labels
+
+    def calculate_relative_distance(self, pred, gt, maskidx, relative_distance):
+        """Append ``|pred - gt| / max(1 - gt, gt + 1)`` of every (sample, DoF) to ``relative_distance[str(dof)]``
+        (UADA.py:354-369, UPA.py:327-342); ``pred`` / ``gt`` are flat continuous actions, ``len(maskidx)`` per sample."""
+        n = len(maskidx)
+        rd = lab.relative_distance(torch.as_tensor(pred, dtype=torch.float64).view(-1, n), torch.as_tensor(gt, dtype=torch.float64).view(-1, n))
+        for j, dof in enumerate(maskidx):
+            relative_distance[str(dof)].extend(rd[:, j].tolist())
+        return relative_distance
+
+    def cal_UAD(self, pred, gt):
+        """Untargeted action discrepancy of predicted vs ground-truth action TOKEN ids: mean of |a_pred - a_gt| over the distance
+        from a_gt to the far end of [-1, 1] (UADA.py:408-418)."""
+        a_gt = torch.tensor(lab.decode_token_ids_to_actions(torch.as_tensor(gt).detach().cpu().numpy()))
+        a_pr = torch.tensor(lab.decode_token_ids_to_actions(torch.as_tensor(pred).detach().cpu().numpy()))
+        far = torch.where(a_gt > 0, (a_gt + 1).abs(), (a_gt - 1).abs())
+        return ((a_pr - a_gt).abs() / far).mean()
+
     @staticmethod
     def _log(args, data, step):
         if args is not None and getattr(args, "wandb_project", "false") != "false":
@@ -279,6 +335,13 @@ class _AttackerBase(object):
 class UADAAttacker(_AttackerBase):
     """Untargeted action-discrepancy attack (UADA.py).  loss = mean((5e - 5t)^2) + 1/CE."""
     KIND = "UADA"
+    SAVE_INFO_LISTS = ("train_CE_loss", "train_MSE_distance_loss", "train_UAD", "val_CE_loss", "val_MSE_Distance", "val_UAD")
+
+    def weighted_loss(self, logits, labels, maskid=None):
+        """``(distance_loss, UAD)`` of UADA.py:381-406 on caller-supplied CUDA logits ``[B, L, V]`` and text labels ``[B, T]``
+        (CUDA loss-head kernel, differentiable w.r.t. the logits); ``maskid`` is unused, as in the reference."""
+        from .loss_heads import uada_weighted_loss
+        return uada_weighted_loss(logits, labels, 5.0)
 
     def patchattack_unconstrained(self, train_dataloader, val_dataloader, num_iter=5000, target_action=np.zeros(7),
                                   patch_size=[3, 50, 50], lr=1 / 255, accumulate_steps=1, maskidx=[], warmup=20,
@@ -370,8 +433,20 @@ class UPAAttacker(_AttackerBase):
         self.alpha, self.belta = alpha, belta
         self.val_batches = 100
 
+    SAVE_INFO_LISTS = ("val_CE_loss", "train_CE_loss", "avg_angle_loss", "avg_distance_loss", "avg_reserve_loss")
+
     def mask_labels(self, labels, maskidx):
         return lab.mask_labels_upa(labels, maskidx)
+
+    def change_target(self, gt):
+        """UPA.py:358-364 (``guide`` labels), in place."""
+        return lab.change_target(gt)
+
+    def weighted_loss(self, logits, labels):
+        """``(total_loss, angle_loss, distance_loss)`` of UPA.py:367-387 on caller-supplied CUDA logits (CUDA loss-head kernel,
+        differentiable w.r.t. the logits) with this attacker's ``alpha`` / ``belta``."""
+        from .loss_heads import upa_weighted_loss
+        return upa_weighted_loss(logits, labels, self.alpha, self.belta)
 
     def patchattack_unconstrained(self, train_dataloader, val_dataloader, num_iter=5000, target_action=np.zeros(7),
                                   patch_size=[3, 50, 50], lr=1 / 255, accumulate_steps=1, maskidx=[], warmup=20,
@@ -456,6 +531,21 @@ class UPAAttacker(_AttackerBase):
 class TMAAttacker(_AttackerBase):
     """Targeted manipulation attack (TMA.py): CE towards a target action on the DoF in ``maskidx``."""
     KIND = "TMA"
+    SAVE_INFO_LISTS = ("val_CE_loss", "val_L1_loss", "val_ASR", "val_inner_relatived_distance", "train_CE_loss", "train_inner_avg_loss",
+                       "train_inner_relatived_distance")
+
+    def calculate_01_ASR(self, pred, gt):
+        """Gripper flip counts on token ids (TMA.py:398-420): (0 -> other, #gt 0, 1 -> other, #gt 1, other -> 0, #gt other) with
+        31872 = the zero action and 31744 = +1."""
+        pred, gt = torch.as_tensor(pred).view(-1), torch.as_tensor(gt).view(-1)
+        is0, is1 = gt == 31872, gt == 31744
+        other = ~is0 & ~is1
+        return (int((is0 & (pred != 31872)).sum()), int(is0.sum()), int((is1 & (pred != 31744)).sum()), int(is1.sum()),
+                int((other & (pred == 31872)).sum()), int(other.sum()))
+
+    def calculate_relative_distance_target(self, pred, gt):
+        """Mean of ``|pred - gt| / max(1 - gt, gt + 1)`` over the entries (TMA.py:470-483)."""
+        return lab.relative_distance(torch.as_tensor(pred, dtype=torch.float64), torch.as_tensor(gt, dtype=torch.float64)).mean()
 
     def __init__(self, *a, **kw):
         super().__init__(*a, **kw)
@@ -608,6 +698,11 @@ class UADADDPAttacker(_AttackerBase):
         if self.host.device.type == "cuda":
             torch.cuda.set_device(self.host.device)
         self.host.rank, self.host.world_size = rank, world_size
+
+    def weighted_loss(self, logits, labels, maskid=None):
+        """``(distance_loss, UAD)`` of UADA_ddp.py:99-124 with this attacker's ``MSE_weights`` (CUDA loss-head kernel)."""
+        from .loss_heads import uada_weighted_loss
+        return uada_weighted_loss(logits, labels, float(self.MSE_weights))
 
     def cleanup(self):
         """UADA_ddp.py:134-136."""

@@ -1,4 +1,5 @@
 """Host-side logic of the product package, checked against the oracle and the golden vectors (CPU only)."""
+import os
 import random
 
 import numpy as np
@@ -153,3 +154,52 @@ def test_filter_train_matches_reference_branches():
     f = _AttackerBase.filter_train(d)
     random.seed(5)
     assert f["pixel_values"] == [f"img{i}" for i in random.sample(list(range(11)), k=8)]
+
+
+def test_reference_helper_methods(tmp_path):
+    """The reference's helper methods under their own names (UADA.py:295-418, UPA.py:309-364, TMA.py:385-483), checked
+    against the oracle / element-wise restatements of the reference loops."""
+    import pickle
+    from oracle import losses as ol
+    from roboticattack_b200.attacker import TMAAttacker, UADAAttacker, UPAAttacker
+    rng = np.random.default_rng(0)
+    uada = UADAAttacker(None, save_dir=str(tmp_path), optimizer="adamW", device="cpu")
+    tma = TMAAttacker(None, save_dir=str(tmp_path), optimizer="adamW", device="cpu")
+    upa = UPAAttacker(None, save_dir=str(tmp_path), optimizer="adamW", alpha=0.8, belta=0.2, device="cpu")
+
+    pred_ids, gt_ids = torch.from_numpy(rng.integers(31744, 32000, 21)), torch.from_numpy(rng.integers(31744, 32000, 21))
+    np.testing.assert_allclose(float(uada.cal_UAD(pred_ids, gt_ids)), float(ol.cal_uad(pred_ids, gt_ids)), rtol=1e-12)
+
+    pred, gt = torch.from_numpy(rng.uniform(-1, 1, 12)), torch.from_numpy(rng.uniform(-1, 1, 12))
+    maskidx = [0, 2, 5]
+    rd = uada.calculate_relative_distance(pred, gt, maskidx, {str(k): [] for k in maskidx})
+    p2, g2 = pred.view(4, 3), gt.view(4, 3)
+    for j, dof in enumerate(maskidx):        # the reference's scalar loop (UADA.py:357-368)
+        want = [float(abs(p2[i, j] - g2[i, j]) / max(1 - g2[i, j], g2[i, j] + 1)) for i in range(4)]
+        np.testing.assert_allclose(rd[str(dof)], want, rtol=1e-12)
+    np.testing.assert_allclose(float(tma.calculate_relative_distance_target(pred, gt)),
+                               np.mean([float(abs(p - g) / max(1 - g, g + 1)) for p, g in zip(pred, gt)]), rtol=1e-12)
+
+    gt_g = torch.tensor([31872, 31872, 31744, 31744, 31900, 31800, 31872])
+    pr_g = torch.tensor([31872, 31744, 31744, 31872, 31872, 31800, 31999])
+    assert tma.calculate_01_ASR(pr_g, gt_g) == (2, 3, 1, 2, 1, 2)
+
+    labels = torch.full((2, 10), -100, dtype=torch.int64)
+    labels[0, 3:] = torch.arange(31750, 31757)
+    labels[1, 2:9] = torch.arange(31760, 31767)
+    out = tma.modifiy_labels(labels.clone(), {"0": 31999, "1": -100, "6": 31744})
+    assert out[0, 3] == 31999 and out[0, 4] == 31751 and out[0, 9] == 31744
+    assert out[1, 2] == 31999 and out[1, 3] == 31761 and out[1, 8] == 31744 and (out[1, :2] == -100).all()
+
+    g = torch.tensor([[-100, 31872, 31900, 31800, 2]])
+    torch.manual_seed(0)
+    assert (upa.change_target(g.clone())[0, 1:] == 31999).all()     # the literal behaviour of UPA.py:358-364 (labels.change_target)
+
+    uada.train_CE_loss, uada.val_UAD = [1.0, 2.0], [0.5]
+    uada.train_MSE_distance_loss = uada.train_UAD = uada.val_CE_loss = uada.val_MSE_Distance = []
+    uada.save_info(str(tmp_path / "info"))
+    with open(tmp_path / "info" / "train_CE_loss.pkl", "rb") as f:
+        assert pickle.load(f) == [1.0, 2.0]
+    assert sorted(os.listdir(tmp_path / "info")) == sorted(f"{n}.pkl" for n in UADAAttacker.SAVE_INFO_LISTS)
+    with pytest.raises(Exception):
+        uada.weighted_loss(torch.zeros(1, 20, 32064), torch.full((1, 4), -100))   # CPU logits: no CPU fallback

@@ -479,3 +479,40 @@ def test_simulation_random_patch_vs_reference(tag):
     frac = (diff > 0).mean()
     assert frac <= 2e-3, f"{frac:.4%} of the bytes differ"
     assert (diff > 1).mean() <= 2e-4, "differences beyond one level only on isolated border pixels"
+
+
+def test_attacker_weighted_loss_methods_vs_oracle():
+    """``OpenVLAAttacker.weighted_loss`` under the reference's signatures (UADA.py:381, UADA_ddp.py:99, UPA.py:367): full
+    logits [B, L, V] + text labels in, loss (+ metrics) out, gradients back to the logits -- the CUDA loss-head kernel
+    against the oracle's autograd."""
+    from oracle import losses as ol
+    from roboticattack_b200.attacker import UADAAttacker, UADADDPAttacker, UPAAttacker
+    labels, logits, P, V = _loss_case()
+    lab_u = ol.mask_labels_uada(labels.clone(), [0, 2, 5])
+
+    def check(loss, ref_loss, lg, rg):
+        np.testing.assert_allclose(loss.item(), ref_loss.item(), rtol=2e-5)
+        loss.backward()
+        ref_loss.backward()
+        scale = rg.grad.abs().max().item()
+        assert scale > 0
+        assert (lg.grad.cpu() - rg.grad).abs().max().item() <= 1e-2 * scale      # dlogits are stored as bf16 by the kernel
+
+    for att, w in ((UADAAttacker(None, optimizer="adamW"), 5.0),
+                   (UADADDPAttacker(None, MSE_weights=3), 3.0)):
+        lg = logits.cuda().requires_grad_(True)
+        rg = logits.clone().requires_grad_(True)
+        loss, uad = att.weighted_loss(lg, lab_u.cuda(), None)
+        ref_loss, ref_uad = ol.weighted_loss_uada(rg, lab_u, w)
+        np.testing.assert_allclose(float(uad), float(ref_uad), rtol=1e-5)
+        check(loss, ref_loss, lg, rg)
+
+    upa = UPAAttacker(None, optimizer="adamW", alpha=0.8, belta=0.2)
+    lab_p = ol.mask_labels_upa(labels.clone(), [0, 1, 2])
+    lg = logits.cuda().requires_grad_(True)
+    rg = logits.clone().requires_grad_(True)
+    loss, ang, dist = upa.weighted_loss(lg, lab_p)
+    ref_loss, ref_ang, ref_dist = ol.weighted_loss_upa(rg, lab_p, 0.8, 0.2, P)
+    assert isinstance(ang, float) and isinstance(dist, float)
+    np.testing.assert_allclose([ang, dist], [ref_ang.item(), ref_dist.item()], rtol=2e-5)
+    check(loss, ref_loss, lg, rg)
