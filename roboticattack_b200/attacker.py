@@ -182,6 +182,7 @@ class _AttackerBase(object):
         if resize_patch:
             raise NotImplementedError("resize_patch=True is dead code in the reference (appply_random_transform.py:113-118)")
         self.host = AttackEngineHost(vla, cfg=cfg, device=device, engine_factory=engine_factory)
+        self.action_tokenizer = lab.ActionTokenizer(getattr(processor, "tokenizer", None))   # UADA.py:60
         self.mean = [torch.tensor(NORM_MEAN[0]), torch.tensor(NORM_MEAN[1])]
         self.std = [torch.tensor(NORM_STD[0]), torch.tensor(NORM_STD[1])]
         self.randomPatchTransform = RandomPatchTransform(device, resize_patch)   # reference attribute; used by eval scripts

@@ -28,6 +28,37 @@ def action_to_token_ids(action) -> np.ndarray:
     return VOCAB_TOKENIZER - np.digitize(action, _BINS)
 
 
+class ActionTokenizer:
+    """Interface of ``prismatic/vla/action_tokenizer.py:28-72`` on the two functions above: uniform bins over
+    [min_action, max_action], ids counted down from the end of the tokenizer vocabulary.  ``tokenizer`` may be None (the
+    attack engines only need ids): ``__call__`` then returns the token ids instead of the decoded string."""
+
+    def __init__(self, tokenizer=None, bins: int = 256, min_action: int = -1, max_action: int = 1):
+        self.tokenizer, self.n_bins, self.min_action, self.max_action = tokenizer, bins, min_action, max_action
+        self.bins = np.linspace(min_action, max_action, bins)
+        self.bin_centers = (self.bins[:-1] + self.bins[1:]) / 2.0
+        self._vocab = int(getattr(tokenizer, "vocab_size", VOCAB_TOKENIZER))
+        self.action_token_begin_idx = int(self._vocab - (bins + 1))
+
+    @property
+    def vocab_size(self) -> int:
+        return self.n_bins
+
+    def token_ids(self, action) -> np.ndarray:
+        action = np.clip(np.asarray(action, dtype=np.float64), a_min=float(self.min_action), a_max=float(self.max_action))
+        return self._vocab - np.digitize(action, self.bins)
+
+    def __call__(self, action):
+        ids = self.token_ids(action)
+        if self.tokenizer is None:
+            return ids
+        return self.tokenizer.decode(list(ids)) if ids.ndim == 1 else self.tokenizer.batch_decode(ids.tolist())
+
+    def decode_token_ids_to_actions(self, action_token_ids) -> np.ndarray:
+        d = self._vocab - np.asarray(action_token_ids)
+        return self.bin_centers[np.clip(d - 1, a_min=0, a_max=self.bin_centers.shape[0] - 1)]
+
+
 def _action_rows(labels):
     mask = labels > ACTION_TOKEN_BEGIN_IDX
     acts = labels[mask]

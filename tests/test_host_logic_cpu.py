@@ -203,3 +203,23 @@ def test_reference_helper_methods(tmp_path):
     assert sorted(os.listdir(tmp_path / "info")) == sorted(f"{n}.pkl" for n in UADAAttacker.SAVE_INFO_LISTS)
     with pytest.raises(Exception):
         uada.weighted_loss(torch.zeros(1, 20, 32064), torch.full((1, 4), -100))   # CPU logits: no CPU fallback
+
+
+def test_action_tokenizer_class(golden):
+    """``ActionTokenizer`` (prismatic/vla/action_tokenizer.py:28-72) with and without a tokenizer object."""
+    tok = lab.ActionTokenizer()
+    assert tok.action_token_begin_idx == 31743 and tok.vocab_size == 256
+    a = np.linspace(-1.2, 1.2, 41)
+    np.testing.assert_array_equal(tok(a), ol.encode_actions_to_token_ids(a))
+    ids = np.arange(31740, 32003)
+    np.testing.assert_array_equal(tok.decode_token_ids_to_actions(ids), ol.decode_token_ids_to_actions(ids))
+
+    class Tk:
+        vocab_size = 32000
+        def decode(self, ids):
+            return " ".join(str(int(i)) for i in ids)
+        def batch_decode(self, rows):
+            return [self.decode(r) for r in rows]
+    t2 = lab.ActionTokenizer(Tk())
+    assert t2(np.zeros(7)) == " ".join(["31872"] * 7)
+    assert t2(np.zeros((2, 3))) == ["31872 31872 31872"] * 2
