@@ -3,7 +3,7 @@ PyTorch attack iteration (per-image front-end loop, autograd, full-sequence lm_h
 clamp) run on cuda:0 in bf16 with torch's own kernels (cuBLAS, SDPA) -- the denominator for "x times the reference GPU
 path".  Two variants, as in the reference: weights frozen (UADA_ddp.py:50-51) and weights requiring grad (UADA.py never
 freezes them, so autograd also computes 7.5 B unused weight gradients).  Measurement tool only; not on the product path.
-usage: python tools/ref_gpu_path.py [--batch 8] [--iters 6]"""
+usage: python tests/ref_gpu_path.py [--batch 8] [--iters 6]"""
 import argparse
 import os
 import random

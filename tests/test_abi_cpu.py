@@ -76,3 +76,39 @@ def test_engine_refuses_cpu():
     from roboticattack_b200.engine import VLAEngine
     with pytest.raises(_lib.VLAError):
         VLAEngine(tiny(), 1, 16)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no module of the product package (nor bench.py outside its cpu_baseline /
+    --impl reference legs, nor the tools) may import it, directly or through another product module."""
+    import ast
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parent.parent
+
+    def imports(path):
+        out = []
+        for node in ast.walk(ast.parse(path.read_text())):
+            if isinstance(node, ast.Import):
+                out += [(a.name, node.lineno) for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.module:
+                out.append((node.module, node.lineno))
+        return out
+
+    for path in sorted((root / "roboticattack_b200").rglob("*.py")):
+        bad = [(m, ln) for m, ln in imports(path) if m == "oracle" or m.startswith("oracle.")]
+        assert not bad, f"{path.relative_to(root)} imports the oracle: {bad}"
+    # bench.py: only inside the two CPU legs
+    src = (root / "bench.py").read_text()
+    tree = ast.parse(src)
+    allowed = {"cpu_reference_rate", "run_reference_arm"}
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            mod = node.module if isinstance(node, ast.ImportFrom) else None
+            names = [a.name for a in node.names] if isinstance(node, ast.Import) else []
+            if (mod and (mod == "oracle" or mod.startswith("oracle."))) or any(n == "oracle" or n.startswith("oracle.") for n in names):
+                assert fn.name in allowed, f"bench.py:{node.lineno} imports the oracle inside {fn.name}()"
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    for node in top:
+        mod = node.module if isinstance(node, ast.ImportFrom) else None
+        names = [a.name for a in node.names] if isinstance(node, ast.Import) else []
+        assert not (mod and mod.startswith("oracle")) and not any(n.startswith("oracle") for n in names), "bench.py imports the oracle at module level"
