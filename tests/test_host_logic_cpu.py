@@ -223,3 +223,48 @@ def test_action_tokenizer_class(golden):
     t2 = lab.ActionTokenizer(Tk())
     assert t2(np.zeros(7)) == " ".join(["31872"] * 7)
     assert t2(np.zeros((2, 3))) == ["31872 31872 31872"] * 2
+
+
+@pytest.mark.parametrize("kind,opt", [("UADA", "adamW"), ("UPA", "adamW"), ("TMA", "adamW"), ("TMA", "pgd")])
+def test_attacker_loops_on_the_cpu_oracle_engine(tmp_path, kind, opt):
+    """Host side of the three attacks (outer loop, label preparation, schedule, validation, best-patch selection, side
+    effects: UADA.py:104-292, UPA.py:104-275, TMA.py:93-383) driven end to end with the CPU oracle engine standing in for
+    the CUDA engine -- the same flow tests/test_attackers_gpu.py runs on the GPU."""
+    import importlib
+    import pickle
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from roboticattack_b200.weights import random_state_dict
+    cfg = tiny(img=28, llm_layers=1, vit_depth=2)
+    sd = random_state_dict(cfg, seed=0, dtype=torch.float32, init="test")
+
+    def loader(n, seed):
+        out = []
+        for i in range(n):
+            b = synthetic_batch(cfg, 2, 14, seed=seed + i, ragged=(i % 2 == 1))
+            out.append({"pixel_values": b["obs"], "input_ids": b["input_ids"], "attention_mask": b["attention_mask"], "labels": b["labels"]})
+        return out
+
+    mod = importlib.import_module(f"roboticattack_b200.white_patch.{kind}")
+    random.seed(42), np.random.seed(42), torch.manual_seed(42)
+    kw = dict(alpha=0.8, belta=0.2) if kind == "UPA" else {}
+    att = mod.OpenVLAAttacker(sd, None, save_dir=str(tmp_path), optimizer=opt, resize_patch=False, cfg=cfg, device="cpu",
+                              engine_factory=OracleEngine, **kw)
+    att.val_batches = 2
+    common = dict(num_iter=2, target_action=np.zeros(7), patch_size=[3, 8, 8], accumulate_steps=1, maskidx=[0, 1, 2], warmup=1,
+                  filterGripTrainTo1=False, geometry=True, innerLoop=2, args=None)
+    step_arg = dict(alpha=2e-3) if kind == "TMA" else dict(lr=2e-3)
+    patch = att.patchattack_unconstrained(loader(2, 100), loader(2, 200), **step_arg, **common)
+    assert patch.shape == (3, 8, 8) and patch.dtype == torch.float32 and 0.0 <= patch.min() and patch.max() <= 1.0
+    saved = torch.load(os.path.join(tmp_path, "last", "patch.pt"), weights_only=True)
+    assert saved.shape == (3, 8, 8) and os.path.exists(os.path.join(tmp_path, "last", "attack_state.pt"))
+    assert os.path.exists(os.path.join(tmp_path, "0", "patch.pt")), "the first validation always improves on the initial best"
+    assert att.host.opt_step == 4 and len(att.train_CE_loss) >= 2 and all(np.isfinite(att.train_CE_loss))
+    names = {"UADA": ["val_MSE_Distance", "val_UAD"], "UPA": ["avg_reserve_loss", "avg_angle_loss"], "TMA": ["val_L1_loss", "val_ASR"]}[kind]
+    for name in names:
+        with open(os.path.join(tmp_path, f"{name}.pkl"), "rb") as f:
+            vals = pickle.load(f)
+        assert len(vals) == 1 and np.isfinite(vals[0]), (name, vals)
+    att.save_info(str(tmp_path / "info"))
+    assert sorted(os.listdir(tmp_path / "info")) == sorted(f"{n}.pkl" for n in att.SAVE_INFO_LISTS)
