@@ -620,6 +620,13 @@ int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B
   return launch_fwd<128>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
 }
 
+int attention_tile_shift(int N, int causal) {
+  const char* e = getenv("VLA_ATTN_SHIFT");   // read per call: A/B switch, tests
+  if (!causal || (e != nullptr && atoi(e) == 0)) return 0;
+  const int ntiles = (N + 127) / 128;
+  return ((ntiles * 128 - N) / 64) * 64;
+}
+
 // true when attention_bwd() can be called with o == NULL and `delta` already holding rowsum(dO * O) per (b, h, n)
 bool attention_bwd_takes_delta(int N, int hd) { return (attn_impl() & 2) && attention_bwd_tc_supported(N, hd); }
 

@@ -164,6 +164,7 @@ struct BwdArgs {
   const float* rope_cos;
   const float* rope_sin;
   int B, N, H, hd, causal, rope_L, ntiles, nitems;
+  int shift;   // MODE_DQ under the causal mask: query tile i covers rows [128 i - shift, +128) (see Fwd3Args::shift)
   float scale;
 };
 
@@ -242,7 +243,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     it.h = bh - it.b * H;
     // heavy tiles first: under the causal mask the LAST query tile sees the most keys, the FIRST key tile the most queries
     const int ti = (MODE == MODE_DQ && causal) ? (a.ntiles - 1 - y) : y;
-    it.t0 = ti * TILE;
+    it.t0 = ti * TILE - ((MODE == MODE_DQ) ? a.shift : 0);
     it.klen = a.kv_len ? min(a.kv_len[it.b], N) : N;
     if (MODE == MODE_DQ) {
       it.c_begin = 0;
@@ -270,11 +271,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       const int heady = (MODE == MODE_DQ) ? 2 * H + it.h : it.h;      // V_s | dO_s
       if (n_it > 0) mbar_wait(bar_xfree, (n_it - 1) & 1);
       if (lane == 0) {
-        mbar_arrive_expect_tx(bar_stat, 2 * SM::STAT_BYTES);
+        // a 64-row box in front of the sequence (shifted first query tile) is not loaded: its rows belong to inactive warps
+        mbar_arrive_expect_tx(bar_stat, it.t0 < 0 ? SM::STAT_BYTES : 2 * SM::STAT_BYTES);
 #pragma unroll
         for (int p = 0; p < SM::PANELS; ++p)
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
+            if (it.t0 + r * 64 < 0) continue;
             tma_load_4d(sX + p * (TILE * 128) + r * 8192, &map_qkv, bar_stat, p * 64, headX, it.t0 + r * 64, it.b);
             tma_load_4d(sY + p * (TILE * 128) + r * 8192, mapY, bar_stat, p * 64, headY, it.t0 + r * 64, it.b);
           }
@@ -413,9 +416,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       const int srow = it.t0 + r;                     // query (MODE_DQ) or key (MODE_DKV) index of this thread's row
       const int warp_row0 = it.t0 + quarter * 32;
       const int klen = it.klen;
-      const bool warp_active = warp_row0 < ((MODE == MODE_DQ) ? N : klen);
+      const bool warp_active = warp_row0 >= 0 && warp_row0 < ((MODE == MODE_DQ) ? N : klen);
       float lse2_r = INFINITY, delta_r = 0.f;
-      if (MODE == MODE_DQ && srow < N) {
+      if (MODE == MODE_DQ && srow >= 0 && srow < N) {
         const int64_t si = (static_cast<int64_t>(it.b) * H + it.h) * N + srow;
         const float l = __ldg(a.lse + si);
         delta_r = __ldg(a.delta + si);
@@ -541,7 +544,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 #pragma unroll
             for (int j = 0; j < 32; ++j) lo[j] = hi[j] = 0u;
           }
-          const int pos = srow % a.rope_L;
+          const int pos = max(srow, 0) % a.rope_L;   // rows in front of the sequence are never stored
           const float* cp = a.rope_cos + pos * 64 + half * 32;
           const float* sp = a.rope_sin + pos * 64 + half * 32;
 #pragma unroll
@@ -602,7 +605,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
               for (int p = 0; p < SM::PANELS; ++p)
 #pragma unroll
                 for (int rb = 0; rb < 2; ++rb)
-                  if (it.t0 + rb * 64 < N && p * 64 < a.hd)
+                  if (it.t0 + rb * 64 >= 0 && it.t0 + rb * 64 < N && p * 64 < a.hd)
                     tma_store_4d(&map_dqkv, stg + p * (TILE * 128) + rb * 8192, p * 64, head_out, it.t0 + rb * 64, it.b);
             }
             tma_store_commit();
@@ -664,6 +667,7 @@ int launch_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float*
   a.B = B, a.N = N, a.H = H, a.hd = hd, a.causal = causal, a.rope_L = rope_L > 0 ? rope_L : 1;
   a.ntiles = ceil_div(N, TILE);
   a.nitems = a.ntiles * B * H;
+  a.shift = attention_tile_shift(N, causal);
   a.scale = 1.f / sqrtf(static_cast<float>(hd));
   VLA_REQUIRE(hd <= 256, "attention_bwd_tc: head dim %d too large for the delta kernel", hd);
   // o == nullptr: delta was already written by the producer of dO (the delta epilogue of the o_proj backward GEMM)

@@ -109,6 +109,11 @@ struct Fwd3Args {
   float* lse;
   const int* kv_len;
   int B, N, H, hd, causal, ntiles, nitems;
+  // Causal mask: the ragged query tile goes to the FRONT of the sequence (tile i covers rows [128 i - shift, +128), shift =
+  // 0 or 64 <= 128 ntiles - N), where a tile sees the fewest keys -- at N = 288 the tiles are [-64, 64), [64, 192), [192, 320)
+  // with 1 + 3 + 5 key steps instead of [0, 128), [128, 256), [256, 384) with 2 + 4 + 5.  shift is a multiple of the 64-row
+  // TMA box and of the 32 rows of a warp, so a box / a warp is either entirely in front of the sequence or inside it.
+  int shift;
   float scale;
 };
 
@@ -183,7 +188,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     it.b = bh / H;
     it.h = bh - it.b * H;
     const int ti = causal ? (a.ntiles - 1 - y) : y;   // heavy first: under the causal mask the last query tile sees the most keys
-    it.t0 = ti * TILE;
+    it.t0 = ti * TILE - a.shift;
     it.klen = a.kv_len ? min(a.kv_len[it.b], N) : N;
     it.c_end = causal ? min(it.klen, it.t0 + TILE) : it.klen;
     it.nsteps = it.c_end > 0 ? (it.c_end + STEP - 1) / STEP : 0;
@@ -203,11 +208,14 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         mbar_wait(bar_kfree, (n_it - 1) & 1);
       }
       if (lane == 0) {
-        mbar_arrive_expect_tx(bar_q, SM::Q_BYTES);
+        // a 64-row box in front of the sequence (shifted first tile) is not loaded: its rows belong to inactive warps, whose
+        // scores are never read and whose P rows are zeroed
+        mbar_arrive_expect_tx(bar_q, it.t0 < 0 ? SM::Q_BYTES / 2 : SM::Q_BYTES);
 #pragma unroll
         for (int p = 0; p < SM::PANELS; ++p)
 #pragma unroll
-          for (int r = 0; r < 2; ++r) tma_load_4d(sQ + p * (TILE * 128) + r * 8192, &map_qkv, bar_q, p * 64, it.h, it.t0 + r * 64, it.b);
+          for (int r = 0; r < 2; ++r)
+            if (it.t0 + r * 64 >= 0) tma_load_4d(sQ + p * (TILE * 128) + r * 8192, &map_qkv, bar_q, p * 64, it.h, it.t0 + r * 64, it.b);
         mbar_arrive_expect_tx(bar_k, it.nsteps * SM::STREAM_BYTES);
         for (int s = 0; s < it.nsteps; ++s)
 #pragma unroll
@@ -296,7 +304,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       const int q = it.t0 + r;
       const int warp_row0 = it.t0 + quarter * 32;
       const int klen = it.klen;
-      const bool warp_active = warp_row0 < N;
+      const bool warp_active = warp_row0 >= 0 && warp_row0 < N;
       STAMP3(i * 8 + 0);
       // ---- pass 0: row maximum over all key steps ----
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -436,7 +444,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_outfree);
       }
-      if (half == 0 && q < N)
+      if (half == 0 && q >= 0 && q < N)
         a.lse[(static_cast<int64_t>(it.b) * H + it.h) * N + q] = (l > 0.f) ? (mref + log2f(l)) / LOG2E_F2 : -INFINITY;
       fence_proxy_async();
       softmax_bar();
@@ -445,7 +453,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         for (int p = 0; p < SM::PANELS; ++p)
 #pragma unroll
           for (int rb = 0; rb < 2; ++rb)
-            if (it.t0 + rb * 64 < N && p * 64 < a.hd)
+            if (it.t0 + rb * 64 >= 0 && it.t0 + rb * 64 < N && p * 64 < a.hd)
               tma_store_4d(&map_o, sPD + p * (TILE * 128) + rb * 8192, p * 64, it.h, it.t0 + rb * 64, it.b);
         tma_store_commit();
         tma_store_wait_read();
@@ -490,6 +498,7 @@ int launch_fwd_tc3(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int 
   a.B = B, a.N = N, a.H = H, a.hd = hd, a.causal = causal;
   a.ntiles = ceil_div(N, TILE);
   a.nitems = a.ntiles * B * H;
+  a.shift = attention_tile_shift(N, causal);
   a.scale = 1.f / sqrtf(static_cast<float>(hd));
   const int sms = (g_vla_sm_limit > 0 && g_vla_sm_limit < g_num_sms_fwd3) ? g_vla_sm_limit : g_num_sms_fwd3;
   const int grid = a.nitems < sms ? a.nitems : sms;

@@ -75,7 +75,10 @@ int attention_fwd_tc3(const bf16* qkv, bf16* o, float* lse, const int* kv_len, i
                       cudaStream_t s);
 // tcgen05 backward (attention_bwd_tc.cu): head dims 64 / 72 / 128, any N; same contract as attention_bwd.
 bool attention_bwd_tc_supported(int N, int hd);
-bool attention_bwd_takes_delta(int N, int hd);   // attention_bwd(o == NULL): delta precomputed by the producer of dO
+bool attention_bwd_takes_delta(int N, int hd);
+// rows by which the 128-row query tiles of the tcgen05 kernels are shifted towards the front under the causal mask (0 or 64;
+// env VLA_ATTN_SHIFT=0 disables): the ragged tile then sits where the mask leaves the fewest keys
+int attention_tile_shift(int N, int causal);   // attention_bwd(o == NULL): delta precomputed by the producer of dO
 int attention_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                      const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
                      int rope_L, cudaStream_t s);
