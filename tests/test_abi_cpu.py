@@ -100,7 +100,7 @@ def test_product_never_imports_the_oracle():
     # bench.py: only inside the two CPU legs
     src = (root / "bench.py").read_text()
     tree = ast.parse(src)
-    allowed = {"cpu_reference_rate", "run_reference_arm"}
+    allowed = {"cpu_reference_rate", "reference_arm"}
     for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
         for node in ast.walk(fn):
             mod = node.module if isinstance(node, ast.ImportFrom) else None
@@ -112,3 +112,27 @@ def test_product_never_imports_the_oracle():
         mod = node.module if isinstance(node, ast.ImportFrom) else None
         names = [a.name for a in node.names] if isinstance(node, ast.Import) else []
         assert not (mod and mod.startswith("oracle")) and not any(n.startswith("oracle") for n in names), "bench.py imports the oracle at module level"
+
+
+def test_bench_reference_arm_contract():
+    """``bench.py --impl reference`` (the reference's CPU path on the host cores) prints ONE JSON line with the keys of the
+    bench contract; run here on the toy model so that it takes seconds.  Under torchrun only rank 0 prints."""
+    import json
+    import os
+    import pathlib
+    import subprocess
+    import sys
+    root = pathlib.Path(__file__).resolve().parent.parent
+    cmd = [sys.executable, str(root / "bench.py"), "--impl", "reference", "--model", "tiny", "--steps", "1", "--warmup", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env={**os.environ, "RANK": "0"})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "attack_iters_per_sec" and d["higher_is_better"] is True
+    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1e-6 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env={**os.environ, "RANK": "1"})
+    assert other.returncode == 0 and other.stdout.strip() == ""
