@@ -7,6 +7,9 @@ timm is a third-party dependency absent from /root/reference and from this conta
 ``x = x + ls1(attn(norm1(x))); x = x + ls2(mlp(norm2(x)))`` with LayerNorm eps 1e-6, fused-qkv MHA through
 ``F.scaled_dot_product_attention`` and an erf-GELU MLP.  ``forward`` is monkey-patched to
 ``get_intermediate_layers(n={depth-2})``: the output of block depth-2, no final norm, prefix tokens stripped.
+
+Pinning: tests/test_oracle_golden.py checks this restatement against ``transformers.Dinov2WithRegistersModel`` and
+``transformers.SiglipVisionModel`` (independent implementations of the two model families) on shared random weights.
 """
 from __future__ import annotations
 

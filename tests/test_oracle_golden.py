@@ -149,3 +149,97 @@ def test_simulation_paste_matches_reference(tag):
     assert out.dtype == np.uint8 and out.shape == g[f"{tag}_out"].shape
     assert np.array_equal(out, g[f"{tag}_out"])
     assert (out != g[f"{tag}_img"]).any(), "the patch must be visible"
+
+
+def _rand_vit_sd(c, prefix, seed):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g) * 0.2   # noqa: E731
+    d, m = c.dim, c.mlp_hidden
+    sd = {prefix + "patch_embed.proj.weight": r(d, 3, c.patch, c.patch), prefix + "patch_embed.proj.bias": r(d),
+          prefix + "pos_embed": r(1, c.num_patches, d)}
+    if c.num_prefix:
+        sd[prefix + "cls_token"] = r(1, 1, d)
+        sd[prefix + "reg_token"] = r(1, c.num_prefix - 1, d)
+    for i in range(c.depth):
+        p = f"{prefix}blocks.{i}."
+        sd.update({p + "norm1.weight": 1 + r(d), p + "norm1.bias": r(d), p + "attn.qkv.weight": r(3 * d, d), p + "attn.qkv.bias": r(3 * d),
+                   p + "attn.proj.weight": r(d, d), p + "attn.proj.bias": r(d), p + "norm2.weight": 1 + r(d), p + "norm2.bias": r(d),
+                   p + "mlp.fc1.weight": r(m, d), p + "mlp.fc1.bias": r(m), p + "mlp.fc2.weight": r(d, m), p + "mlp.fc2.bias": r(d)})
+        if c.layerscale:
+            sd.update({p + "ls1.scale_factor": r(d), p + "ls2.scale_factor": r(d)})
+    return sd
+
+
+def test_vit_restatement_matches_hf_dinov2_with_registers():
+    """timm is absent from the container, so ``oracle/vit.py`` restates its ``VisionTransformer`` from the published algorithm.
+    Cross-check of the DINOv2-reg4 wiring (pre-LN blocks, fused q|k|v, LayerScale, eps 1e-6, [cls, reg x4, patches], cls
+    without position embedding, second-to-last block output) against an INDEPENDENT implementation of the same model
+    family: ``transformers.Dinov2WithRegistersModel`` with the same random weights."""
+    from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel
+    from oracle import vit as ovit
+    from roboticattack_b200.config import ViTConfig
+    c = ViTConfig(dim=64, depth=4, heads=2, mlp_hidden=256, num_prefix=5, layerscale=True, img=28, patch=14)
+    sd = _rand_vit_sd(c, "f.", 11)
+    hf = Dinov2WithRegistersModel(Dinov2WithRegistersConfig(hidden_size=64, num_hidden_layers=4, num_attention_heads=2, mlp_ratio=4,
+                                                            image_size=28, patch_size=14, num_register_tokens=4, layer_norm_eps=1e-6,
+                                                            hidden_act="gelu", attn_implementation="eager")).eval()
+    t = hf.state_dict()
+    t["embeddings.patch_embeddings.projection.weight"] = sd["f.patch_embed.proj.weight"]
+    t["embeddings.patch_embeddings.projection.bias"] = sd["f.patch_embed.proj.bias"]
+    t["embeddings.cls_token"] = sd["f.cls_token"]
+    t["embeddings.register_tokens"] = sd["f.reg_token"]
+    t["embeddings.position_embeddings"] = torch.cat([torch.zeros(1, 1, 64), sd["f.pos_embed"]], dim=1)   # no_embed_class=True
+    for i in range(c.depth):
+        p, h = f"f.blocks.{i}.", f"encoder.layer.{i}."
+        qw, kw, vw = sd[p + "attn.qkv.weight"].chunk(3, 0)
+        qb, kb, vb = sd[p + "attn.qkv.bias"].chunk(3, 0)
+        t.update({h + "norm1.weight": sd[p + "norm1.weight"], h + "norm1.bias": sd[p + "norm1.bias"],
+                  h + "attention.attention.query.weight": qw, h + "attention.attention.query.bias": qb,
+                  h + "attention.attention.key.weight": kw, h + "attention.attention.key.bias": kb,
+                  h + "attention.attention.value.weight": vw, h + "attention.attention.value.bias": vb,
+                  h + "attention.output.dense.weight": sd[p + "attn.proj.weight"], h + "attention.output.dense.bias": sd[p + "attn.proj.bias"],
+                  h + "layer_scale1.lambda1": sd[p + "ls1.scale_factor"], h + "layer_scale2.lambda1": sd[p + "ls2.scale_factor"],
+                  h + "norm2.weight": sd[p + "norm2.weight"], h + "norm2.bias": sd[p + "norm2.bias"],
+                  h + "mlp.fc1.weight": sd[p + "mlp.fc1.weight"], h + "mlp.fc1.bias": sd[p + "mlp.fc1.bias"],
+                  h + "mlp.fc2.weight": sd[p + "mlp.fc2.weight"], h + "mlp.fc2.bias": sd[p + "mlp.fc2.bias"]})
+    missing = hf.load_state_dict(t, strict=True)
+    img = torch.randn(2, 3, 28, 28, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = hf(pixel_values=img, output_hidden_states=True).hidden_states[c.depth - 1][:, c.num_prefix:]
+        got = ovit.vit_forward(sd, "f.", c, img)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_vit_restatement_matches_hf_siglip():
+    """Same cross-check for the SigLIP tower (no cls token, no LayerScale, learned position embedding on every token):
+    ``transformers.SiglipVisionModel`` with ``hidden_act="gelu"`` -- timm 0.9.10's model definition passes no activation, i.e.
+    the erf GELU that ``oracle/vit.py`` (and the engine) use."""
+    from transformers import SiglipVisionConfig, SiglipVisionModel
+    from oracle import vit as ovit
+    from roboticattack_b200.config import ViTConfig
+    c = ViTConfig(dim=72, depth=4, heads=2, mlp_hidden=264, num_prefix=0, layerscale=False, img=28, patch=14)
+    sd = _rand_vit_sd(c, "s.", 12)
+    hf = SiglipVisionModel(SiglipVisionConfig(hidden_size=72, intermediate_size=264, num_hidden_layers=4, num_attention_heads=2,
+                                              image_size=28, patch_size=14, layer_norm_eps=1e-6, hidden_act="gelu",
+                                              attn_implementation="eager")).eval()
+    t = hf.state_dict()
+    t["vision_model.embeddings.patch_embedding.weight"] = sd["s.patch_embed.proj.weight"]
+    t["vision_model.embeddings.patch_embedding.bias"] = sd["s.patch_embed.proj.bias"]
+    t["vision_model.embeddings.position_embedding.weight"] = sd["s.pos_embed"][0]
+    for i in range(c.depth):
+        p, h = f"s.blocks.{i}.", f"vision_model.encoder.layers.{i}."
+        qw, kw, vw = sd[p + "attn.qkv.weight"].chunk(3, 0)
+        qb, kb, vb = sd[p + "attn.qkv.bias"].chunk(3, 0)
+        t.update({h + "layer_norm1.weight": sd[p + "norm1.weight"], h + "layer_norm1.bias": sd[p + "norm1.bias"],
+                  h + "self_attn.q_proj.weight": qw, h + "self_attn.q_proj.bias": qb, h + "self_attn.k_proj.weight": kw,
+                  h + "self_attn.k_proj.bias": kb, h + "self_attn.v_proj.weight": vw, h + "self_attn.v_proj.bias": vb,
+                  h + "self_attn.out_proj.weight": sd[p + "attn.proj.weight"], h + "self_attn.out_proj.bias": sd[p + "attn.proj.bias"],
+                  h + "layer_norm2.weight": sd[p + "norm2.weight"], h + "layer_norm2.bias": sd[p + "norm2.bias"],
+                  h + "mlp.fc1.weight": sd[p + "mlp.fc1.weight"], h + "mlp.fc1.bias": sd[p + "mlp.fc1.bias"],
+                  h + "mlp.fc2.weight": sd[p + "mlp.fc2.weight"], h + "mlp.fc2.bias": sd[p + "mlp.fc2.bias"]})
+    hf.load_state_dict(t, strict=True)
+    img = torch.randn(2, 3, 28, 28, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        ref = hf(pixel_values=img, output_hidden_states=True).hidden_states[c.depth - 1]
+        got = ovit.vit_forward(sd, "s.", c, img)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
