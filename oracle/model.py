@@ -4,6 +4,10 @@ Follows ``prismatic/extern/hf/modeling_prismatic.py``: ``PrismaticVisionBackbone
 DINOv2 / SigLIP, concat features), ``PrismaticProjector.forward`` :146-158 (fused variant fc1-GELU-fc2-GELU-fc3),
 ``PrismaticForConditionalGeneration.forward`` :362-415 (embed, splice after BOS, mask / label splice, LLM call),
 weight init ``_init_weights`` :185-205.  Parameter names as in the HF checkpoint.
+
+Pinning: tests/test_oracle_golden.py::test_multimodal_forward_matches_reference_model_class compares ``forward`` (vision features,
+projector output, loss, logits) with the reference's own ``OpenVLAForActionPrediction.forward`` executed on the CPU
+(tests/golden/make_golden_glue.py -> tests/golden/reference_golden_glue.npz).  Test infrastructure: never imported by the product.
 """
 from __future__ import annotations
 

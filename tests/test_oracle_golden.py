@@ -243,3 +243,31 @@ def test_vit_restatement_matches_hf_siglip():
         ref = hf(pixel_values=img, output_hidden_states=True).hidden_states[c.depth - 1]
         got = ovit.vit_forward(sd, "s.", c, img)
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_multimodal_forward_matches_reference_model_class():
+    """``oracle.model.forward`` against the REFERENCE's own ``OpenVLAForActionPrediction.forward`` executed on the CPU
+    (tests/golden/make_golden_glue.py -> reference_golden_glue.npz): channel split and tower order, second-to-last-block
+    features, the LayerScale ``scale_factor`` patch, projector, [BOS | patches | text] splice of embeddings / mask / labels,
+    HF Llama with padding, fp32 logits and the shifted cross-entropy."""
+    import os
+    from oracle import model as om
+    from roboticattack_b200.config import LlamaConfig, OpenVLAConfig, ViTConfig
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_glue.npz"))
+    sd = {k[2:]: torch.from_numpy(gold[k].astype(np.float32)) for k in gold.files if k.startswith("w:")}
+    cfg = OpenVLAConfig(dino=ViTConfig(dim=32, depth=3, heads=2, mlp_hidden=128, num_prefix=5, layerscale=True, img=28),
+                        siglip=ViTConfig(dim=40, depth=4, heads=2, mlp_hidden=136, num_prefix=0, layerscale=False, img=28),
+                        llm=LlamaConfig(hidden=64, layers=2, heads=2, ffn=176, vocab=384), name="glue")
+    ids, mask = torch.from_numpy(gold["input_ids"]), torch.from_numpy(gold["attention_mask"])
+    labels, px = torch.from_numpy(gold["labels"]), torch.from_numpy(gold["pixel_values"])
+    feats = om.vision_backbone(sd, cfg, px)
+    torch.testing.assert_close(feats, torch.from_numpy(gold["vision_features"]), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(om.projector(sd, feats), torch.from_numpy(gold["projected"]), rtol=1e-5, atol=1e-5)
+    out = om.forward(sd, cfg, ids, mask, px, labels)
+    np.testing.assert_allclose(out.loss.item(), float(gold["loss"]), rtol=1e-6)
+    # rows at padded text positions depend on how the attention implementation treats fully padded keys; every position
+    # that can carry a label or be attended to is compared
+    P = cfg.num_patches
+    mm_mask = torch.cat([mask[:, :1], torch.ones(mask.shape[0], P, dtype=torch.bool), mask[:, 1:]], dim=1)
+    got, ref = out.logits.float(), torch.from_numpy(gold["logits"])
+    torch.testing.assert_close(got[mm_mask], ref[mm_mask], rtol=1e-4, atol=1e-4)
