@@ -163,6 +163,31 @@ def main():
     assert all(np.array_equal(arrays["w:" + k].astype(np.float32), v.detach().numpy()) for k, v in model.state_dict().items())
     arrays.update(input_ids=ids.numpy(), attention_mask=mask.numpy(), labels=labels.numpy(), pixel_values=px.numpy(),
                   loss=np.float64(out.loss.item()), logits=out.logits.numpy(), vision_features=feats.numpy(), projected=proj.numpy())
+    # ---- predict_action (modeling_prismatic.py:506-536): empty-token insertion, de-tokenisation with the full-size vocabulary
+    # (32064 - 64), un-normalisation with q01 / q99 / mask.  ``generate`` (a GenerationMixin method the 4.40-era class no
+    # longer inherits under transformers 5.x) is replaced by a stand-in that records its input and appends fixed token ids.
+    stats = {"toy": {"action": {"q01": [-0.5, -0.2, -1.0, -0.3, -0.1, -0.7, 0.0], "q99": [0.6, 0.9, 1.0, 0.2, 0.4, 0.3, 1.0],
+                                "mask": [True, True, True, True, True, True, False]}}}
+    text2 = dict(text, vocab_size=32064, pad_token_id=32000)
+    cfg2 = cp.OpenVLAConfig(vision_backbone_id="dinosiglip-vit-so-224px", llm_backbone_id="llama2-7b-pure", image_sizes=[IMG, IMG],
+                            text_config=text2, attn_implementation="eager", norm_stats=stats)
+    m2 = mp.OpenVLAForActionPrediction(cfg2).eval()
+    cases = np.array([[31872, 31744, 31999, 31745, 31900, 31800, 31744], [31998, 31873, 31871, 31760, 31999, 31744, 31872],
+                      [32000, 31743, 31500, 31872, 31872, 31872, 31999]], dtype=np.int64)   # the last row leaves the action range (clip)
+    prompts = [torch.tensor([[1, 500, 600, 29871]]), torch.tensor([[1, 500, 600, 700]]), torch.tensor([[1, 29871]])]
+    seen, acts = [], []
+    for toks, prompt in zip(cases, prompts):
+        def fake_generate(input_ids, max_new_tokens, **kw):
+            seen.append(input_ids.numpy().copy())
+            assert max_new_tokens == 7
+            return torch.cat([input_ids, torch.from_numpy(toks)[None]], dim=1)
+        m2.generate = fake_generate
+        acts.append(m2.predict_action(prompt, unnorm_key="toy"))
+    arrays.update(pa_tokens=cases, pa_actions=np.stack(acts), pa_q01=np.array(stats["toy"]["action"]["q01"]),
+                  pa_q99=np.array(stats["toy"]["action"]["q99"]), pa_mask=np.array(stats["toy"]["action"]["mask"]))
+    for i, (pr, sn) in enumerate(zip(prompts, seen)):
+        arrays[f"pa_prompt{i}"] = pr.numpy()
+        arrays[f"pa_generate_input{i}"] = sn
     np.savez_compressed(os.path.join(HERE, "reference_golden_glue.npz"), **arrays)
     print("wrote", len(arrays), "arrays; loss", out.loss.item(), "logits", tuple(out.logits.shape))
 

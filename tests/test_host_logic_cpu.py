@@ -268,3 +268,25 @@ def test_attacker_loops_on_the_cpu_oracle_engine(tmp_path, kind, opt):
         assert len(vals) == 1 and np.isfinite(vals[0]), (name, vals)
     att.save_info(str(tmp_path / "info"))
     assert sorted(os.listdir(tmp_path / "info")) == sorted(f"{n}.pkl" for n in att.SAVE_INFO_LISTS)
+
+
+def test_predict_action_postprocessing_matches_reference_method(monkeypatch):
+    """``ActionPolicy.predict_action`` (the product's host code) against the reference's own
+    ``OpenVLAForActionPrediction.predict_action`` run with a stand-in ``generate`` (tests/golden/make_golden_glue.py): the
+    empty token 29871 is appended when missing, ids map to bin centres through ``32000 - id`` with clipping, and the
+    result is un-normalised with q01 / q99 except where the mask is False."""
+    from roboticattack_b200.policy import ActionPolicy
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_glue.npz"))
+    stats = {"toy": {"action": {"q01": gold["pa_q01"].tolist(), "q99": gold["pa_q99"].tolist(), "mask": gold["pa_mask"].tolist()}}}
+    pol = ActionPolicy(engine=None, norm_stats=stats)
+    for i, toks in enumerate(gold["pa_tokens"]):
+        seen = {}
+
+        def fake(images_u8, input_ids, n_tokens=7, toks=toks, seen=seen):
+            seen["ids"], seen["n"] = input_ids.numpy().copy(), n_tokens
+            return toks[None]
+        monkeypatch.setattr(pol, "generate_action_tokens", fake)
+        act = pol.predict_action(np.zeros((28, 28, 3), dtype=np.uint8), torch.from_numpy(gold[f"pa_prompt{i}"]), unnorm_key="toy")
+        np.testing.assert_allclose(act, gold["pa_actions"][i], rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(seen["ids"], gold[f"pa_generate_input{i}"])
+        assert seen["n"] == 7
