@@ -290,3 +290,55 @@ def test_predict_action_postprocessing_matches_reference_method(monkeypatch):
         np.testing.assert_allclose(act, gold["pa_actions"][i], rtol=0, atol=1e-12)
         np.testing.assert_array_equal(seen["ids"], gold[f"pa_generate_input{i}"])
         assert seen["n"] == 7
+
+
+def test_uada_loop_tracks_the_reference_loop(tmp_path):
+    """The product's ``OpenVLAAttacker.patchattack_unconstrained`` (UADA host loop: label masking, host RNG protocol of the
+    placements through training AND the 1000-batch validation pass, cosine schedule, ``+ 1/CE``, AdamW step, clamp,
+    best / last patch files) against the REFERENCE's own loop run on the CPU with the reference's own model class and front
+    end (tests/golden/make_golden_loop.py -> reference_golden_loop.npz).  The product runs on the CPU oracle engine in bf16
+    like the reference model; what remains is bf16 round-off (the two sides order a few roundings differently)."""
+    import argparse
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from roboticattack_b200.attacker import UADAAttacker
+    from roboticattack_b200.config import LlamaConfig, OpenVLAConfig, ViTConfig
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_loop.npz"))
+
+    def big_matrix(rows, cols, a, b):       # embedding / lm_head by formula, as in the generator
+        i, j = torch.arange(rows)[:, None], torch.arange(cols)[None, :]
+        return (((i * a + j * b) % 257) - 128).float() / 4096.0
+
+    sd = {k[2:]: torch.from_numpy(g[k]).view(torch.bfloat16).float() for k in g.files if k.startswith("w:")}
+    sd["language_model.model.embed_tokens.weight"] = big_matrix(32064, 32, 131, 71)
+    sd["language_model.lm_head.weight"] = big_matrix(32064, 32, 89, 153)
+    cfg = OpenVLAConfig(dino=ViTConfig(dim=32, depth=3, heads=2, mlp_hidden=64, num_prefix=5, layerscale=True, img=28),
+                        siglip=ViTConfig(dim=40, depth=3, heads=2, mlp_hidden=72, num_prefix=0, layerscale=False, img=28),
+                        llm=LlamaConfig(hidden=32, layers=2, heads=2, ffn=64, vocab=32064), name="loop")
+
+    def loader(name, n):
+        return [{"pixel_values": torch.from_numpy(g[f"{name}{k}_obs"]), "input_ids": torch.from_numpy(g[f"{name}{k}_ids"]),
+                 "attention_mask": torch.from_numpy(g[f"{name}{k}_mask"]), "labels": torch.from_numpy(g[f"{name}{k}_labels"])}
+                for k in range(n)]
+
+    lr = 2e-3
+    att = UADAAttacker(sd, None, save_dir=str(tmp_path), optimizer="adamW", cfg=cfg, device="cpu",
+                       engine_factory=lambda c, B, T, device="cpu": OracleEngine(c, B, T, device, dtype=torch.bfloat16))
+    random.seed(42), np.random.seed(42), torch.manual_seed(42)
+    patch = att.patchattack_unconstrained(loader("train", 3), loader("val", 2), num_iter=3, target_action=np.zeros(7), patch_size=[3, 8, 8],
+                                          lr=lr, accumulate_steps=1, maskidx=[0, 1, 2], warmup=0, filterGripTrainTo1=False, geometry=True,
+                                          innerLoop=2, args=argparse.Namespace(wandb_project="false"))
+    np.testing.assert_allclose(att.train_CE_loss, g["train_CE_loss"], rtol=1e-3)
+    np.testing.assert_allclose(att.train_MSE_distance_loss, g["train_MSE_distance_loss"], rtol=1e-3)
+    np.testing.assert_allclose(att.train_UAD, g["train_UAD"], atol=0.08)            # argmax flips of near-ties under bf16 noise
+    # validation of outer iteration 0: 1000 batches, every one drawing placements from the host RNG
+    np.testing.assert_allclose(att.val_MSE_Distance, g["val_MSE_Distance"], rtol=1e-4)
+    np.testing.assert_allclose(att.val_CE_loss, g["val_CE_loss"], rtol=1e-4)
+    np.testing.assert_allclose(att.val_UAD, g["val_UAD"], atol=5e-3)
+    ref_final = torch.from_numpy(g["patches"][-1])
+    assert (patch - ref_final).abs().max().item() < lr and (patch - ref_final).abs().mean().item() < lr / 10
+    for sub, key in (("last", "saved_last"), ("0", "saved_best")):
+        saved = torch.load(os.path.join(tmp_path, sub, "patch.pt"), weights_only=True)
+        assert (saved - torch.from_numpy(g[key])).abs().max().item() < lr
+    assert (ref_final - torch.from_numpy(g["patches"][0])).abs().max().item() > 2 * lr, "the golden trajectory moves"
