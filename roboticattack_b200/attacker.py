@@ -141,7 +141,21 @@ class AttackEngineHost:
                                  grad_scale=1.0 / self.world_size, clip_l1=clip_l1, scalars=scalars[s])
                 if accumulate is not None:
                     accumulate.zero_()
-        return scalars.cpu(), pred.cpu()
+        return scalars.cpu(), self._full_vocab_pred(eng, R, pred).cpu()
+
+    def _full_vocab_pred(self, eng, R, pred):
+        """The reference's metrics take ``action_preds = logits.argmax(dim=2)`` over the FULL vocabulary (UADA.py:168,229;
+        TMA.py:150,274) and let ``decode_token_ids_to_actions`` clip whatever id comes out, whereas the loss-head kernel reports
+        the argmax inside the 256 action classes (what ``weighted_loss`` / UAD use).  The two differ whenever a non-action token
+        wins -- which an attack can provoke -- and TMA selects its best patch by an L1 built on these predictions, so the ids of
+        the action rows are taken from the engine's fp32 logits rows here (one [R, V] argmax per validation batch / outer
+        iteration; not on the per-inner-step path)."""
+        if not hasattr(eng, "tap"):
+            return pred
+        V = self.cfg.llm.vocab
+        logits = eng.tap("logits", dtype=torch.float32, max_elems=R * V).view(R, V)
+        full = logits.argmax(dim=1).to(torch.int32)
+        return torch.where(pred >= 0, full.to(pred.device), pred)
 
     def evaluate(self, batch, fe_mode, loss: LossSpec):
         """Forward-only pass (validation): scalars [8] and pred_ids [R] on the host."""
@@ -154,7 +168,7 @@ class AttackEngineHost:
         scalars = torch.zeros(_lib.NUM_SCALARS, device=self.device)
         pred = torch.full((R,), -1, dtype=torch.int32, device=self.device)
         eng.fwd_bwd(self.patch, 0, fe_mode, loss, self.grad, scalars, pred, forward_only=True)
-        return scalars.cpu(), pred.cpu()
+        return scalars.cpu(), self._full_vocab_pred(eng, R, pred).cpu()
 
 
 def _decoded_pairs(pred_ids: torch.Tensor, labels: torch.Tensor):
@@ -521,9 +535,12 @@ class UPAAttacker(_AttackerBase):
             self.reverse_direction_loss = avg_loss
             self._dump_val_images(self._save_patch(h.patch, str(i)))
         self._dump_val_images(self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step))
-        self.avg_reserve_loss.append(avg_loss)
-        self.avg_angle_loss.append(avg_ang)
-        self.avg_distance_loss.append(avg_dist)
+        # The reference appends the already averaged values divided by the sample count a second time (UPA.py:269-271); the
+        # .pkl lists reproduce that so that they hold the numbers the reference writes (the logged values and the best-patch
+        # selection above use the plain averages, as the reference's do).
+        self.avg_reserve_loss.append(avg_loss / n)
+        self.avg_angle_loss.append(avg_ang / n)
+        self.avg_distance_loss.append(avg_dist / n)
         self._dump(val_CE_loss=self.val_CE_loss, avg_angle_loss=self.avg_angle_loss, avg_distance_loss=self.avg_distance_loss,
                    avg_reserve_loss=self.avg_reserve_loss)
         return val_it

@@ -88,7 +88,8 @@ def batches(n, seed):
     return out
 
 
-def main():
+def main(kind="UADA"):
+    del STEPS[:], GRADS[:], PATCHES[:]
     cp, mp = glue.load_reference_model_module()
     glue.SPECS.update({"vit_large_patch14_reg4_dinov2.lvd142m": (32, 3, 2, 64, 5, True), "vit_so400m_patch14_siglip_224": (40, 3, 2, 72, 0, False)})
     text = dict(hidden_size=HIDDEN, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=2, vocab_size=VOCAB,
@@ -122,18 +123,30 @@ def main():
     tok = mg.load_file_module("ref_action_tokenizer", "prismatic/vla/action_tokenizer.py")
     import transformers
     transformers.AdamW = HFAdamW
-    uada = mg.load_attack_module("UADA.py", fe, tok)
+    uada = mg.load_attack_module(f"{kind}.py", fe, tok)
     uada.transformers.AdamW = HFAdamW
 
+    class RoundTripTokenizer:
+        """Stand-in for the Llama tokenizer (not available offline): ``decode`` then ``__call__`` returns [BOS, 29871 ('')] + the ids,
+        which is what the real tokenizer does with a string of action tokens (TMA.py:93 drops the first two)."""
+        vocab_size = 32000
+
+        def decode(self, ids):
+            return " ".join(str(int(i)) for i in ids)
+
+        def __call__(self, text):
+            return argparse.Namespace(input_ids=[1, 29871] + [int(t) for t in text.split()])
+
     class Proc:
-        tokenizer = mg.FakeTokenizer()
+        tokenizer = RoundTripTokenizer()
 
         class image_processor:
             apply_transform = None
 
     train, val = batches(N_TRAIN, 100), batches(N_VAL, 200)
     with tempfile.TemporaryDirectory() as d:
-        att = uada.OpenVLAAttacker(model, Proc(), save_dir=d, optimizer="adamW", resize_patch=False)
+        extra = dict(alpha=0.8, belta=0.2) if kind == "UPA" else {}
+        att = uada.OpenVLAAttacker(model, Proc(), save_dir=d, optimizer="adamW", resize_patch=False, **extra)
         att.plot_loss = lambda: None          # matplotlib / seaborn are not installed
         random.seed(42)
         np.random.seed(42)
@@ -153,25 +166,32 @@ def main():
                     yield {k: (v.clone() if torch.is_tensor(v) else v) for k, v in b.items() if k != "obs"}
 
         strip = Loader
+        step_arg = dict(alpha=LR) if kind == "TMA" else dict(lr=LR)
         att.patchattack_unconstrained(strip(train), strip(val), num_iter=NUM_ITER, target_action=np.zeros(7), patch_size=[3, P_HW, P_HW],
-                                      lr=LR, accumulate_steps=1, maskidx=MASKIDX, warmup=0, filterGripTrainTo1=False, geometry=True,
-                                      innerLoop=INNER, args=argparse.Namespace(wandb_project="false"))
+                                      accumulate_steps=1, maskidx=MASKIDX, warmup=0, filterGripTrainTo1=False,
+                                      geometry=(kind != "TMA"),   # TMA.py:137-141 passes colorjitter= to a method without it: only geometry=False runs
+                                      innerLoop=INNER, args=argparse.Namespace(wandb_project="false"), **step_arg)
         saved_last = torch.load(os.path.join(d, "last", "patch.pt"))
         saved_best = torch.load(os.path.join(d, "0", "patch.pt"))
-    out = dict(weights)
-    for name, bs in (("train", train), ("val", val)):
+    out = dict(weights) if kind == "UADA" else {}      # the three fixtures share the weights and batches of the UADA one
+    for name, bs in ((("train", train), ("val", val)) if kind == "UADA" else ()):
         for k, b in enumerate(bs):
             out[f"{name}{k}_obs"] = b["obs"]
             out[f"{name}{k}_ids"] = b["input_ids"].numpy()
             out[f"{name}{k}_mask"] = b["attention_mask"].numpy()
             out[f"{name}{k}_labels"] = b["labels"].numpy()
-    out.update(train_CE_loss=np.array(att.train_CE_loss), train_MSE_distance_loss=np.array(att.train_MSE_distance_loss),
-               train_UAD=np.array(att.train_UAD), val_CE_loss=np.array(att.val_CE_loss), val_MSE_Distance=np.array(att.val_MSE_Distance),
-               val_UAD=np.array(att.val_UAD), grads=torch.stack(GRADS).numpy(), patches=torch.stack(PATCHES).numpy(),
-               saved_last=saved_last.numpy(), saved_best=saved_best.numpy())
-    np.savez_compressed(os.path.join(HERE, "reference_golden_loop.npz"), **out)
-    print("steps", len(GRADS), "CE", att.train_CE_loss, "MSE", att.train_MSE_distance_loss, "val", att.val_MSE_Distance, att.val_UAD)
+    lists = {"UADA": ["train_CE_loss", "train_MSE_distance_loss", "train_UAD", "val_CE_loss", "val_MSE_Distance", "val_UAD"],
+             "UPA": ["train_CE_loss", "avg_angle_loss", "avg_distance_loss", "avg_reserve_loss"],
+             "TMA": ["train_CE_loss", "train_inner_avg_loss", "val_CE_loss", "val_L1_loss", "val_ASR"]}[kind]
+    for name in lists:
+        out[name] = np.array([float(v) for v in getattr(att, name)])
+    out.update(grads=torch.stack(GRADS).numpy(), patches=torch.stack(PATCHES).numpy(), saved_last=saved_last.numpy(),
+               saved_best=saved_best.numpy())
+    suffix = "" if kind == "UADA" else "_" + kind.lower()
+    np.savez_compressed(os.path.join(HERE, f"reference_golden_loop{suffix}.npz"), **out)
+    print(kind, "steps", len(GRADS), {n: out[n].tolist() for n in lists})
 
 
 if __name__ == "__main__":
-    main()
+    for k in (sys.argv[1:] or ["UADA", "UPA", "TMA"]):
+        main(k)

@@ -34,6 +34,7 @@ class OracleEngine:
         obs, ids, mask, labels = self.batch
         p = patch.detach().clone().requires_grad_(True)
         px = ofe.apply_patch_batch(obs, p, self.xy[step_idx], self.theta[step_idx], fe_mode, NORM_MEAN, NORM_STD)
+        self._px = px.detach()
         out = om.forward(self.sd, self.cfg, ids, mask, px.to(self.dtype), labels)
         logits = out.logits.float()
         aux0 = aux1 = uad = 0.0
@@ -53,6 +54,7 @@ class OracleEngine:
             dpatch.copy_(p.grad)
         sup = labels[:, 1:] != -100
         P = self.cfg.num_patches
+        self._sup_logits = logits[:, P:-1][sup].detach()          # [R, V], what VLAEngine.tap("logits") returns
         act = logits[:, P:-1][sup][:, 31744:32000].argmax(-1).int() + 31744
         tgt = labels[:, 1:][sup]
         pred_ids.copy_(torch.where(tgt > 2, act, torch.full_like(act, -1)))
@@ -62,6 +64,12 @@ class OracleEngine:
             scalars[_lib.S_AUX0] = aux0
             scalars[_lib.S_AUX1] = aux1
             scalars[_lib.S_UAD] = uad
+
+    def tap(self, what, dtype=torch.float32, max_elems=1 << 28):
+        if what == "px":                                           # normalised 6-channel front-end output of the last pass
+            return self._px.reshape(-1).to(dtype)
+        assert what == "logits", what
+        return self._sup_logits.reshape(-1).to(dtype)
 
     def patch_update(self, patch, grad, m, v, step, lr, kind=_lib.OPT_ADAMW, grad_scale=1.0, clip_l1=0.0, scalars=None,
                      betas=(0.9, 0.999), eps=1e-6):

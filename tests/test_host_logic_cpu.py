@@ -292,19 +292,25 @@ def test_predict_action_postprocessing_matches_reference_method(monkeypatch):
         assert seen["n"] == 7
 
 
-def test_uada_loop_tracks_the_reference_loop(tmp_path):
-    """The product's ``OpenVLAAttacker.patchattack_unconstrained`` (UADA host loop: label masking, host RNG protocol of the
-    placements through training AND the 1000-batch validation pass, cosine schedule, ``+ 1/CE``, AdamW step, clamp,
-    best / last patch files) against the REFERENCE's own loop run on the CPU with the reference's own model class and front
-    end (tests/golden/make_golden_loop.py -> reference_golden_loop.npz).  The product runs on the CPU oracle engine in bf16
-    like the reference model; what remains is bf16 round-off (the two sides order a few roundings differently)."""
+@pytest.mark.parametrize("kind", ["UADA", "UPA", "TMA"])
+def test_attack_loops_track_the_reference_loops(tmp_path, kind):
+    """The product's ``OpenVLAAttacker.patchattack_unconstrained`` (host loops of UADA / UPA / TMA: label preparation, host
+    RNG protocol of the placements through training AND the validation pass (1000 / 100 / 100 batches), cosine schedule, the
+    loss composition, AdamW step (+ UPA's L1 clip), clamp, validation metrics, best / last patch files) against the
+    REFERENCE's own loops (UADA.py:93-292, UPA.py:92-275, TMA.py:82-383) run on the CPU with the reference's own model class
+    and front end (tests/golden/make_golden_loop.py -> reference_golden_loop*.npz).  The product runs on the CPU oracle engine in
+    bf16 like the reference model; what remains is bf16 round-off (the two sides order a few roundings differently; Adam's
+    first steps are sign-like, so a single flipped sign moves a pixel by 2 lr).  TMA runs with geometry=False, the only
+    branch of the reference that executes (TMA.py:137-141 passes ``colorjitter=`` to a method that does not take it)."""
     import argparse
+    import importlib
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from oracle_engine import OracleEngine
-    from roboticattack_b200.attacker import UADAAttacker
     from roboticattack_b200.config import LlamaConfig, OpenVLAConfig, ViTConfig
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_loop.npz"))
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gdir, "reference_golden_loop.npz"))                       # weights + batches (+ the UADA trajectory)
+    gk = g if kind == "UADA" else np.load(os.path.join(gdir, f"reference_golden_loop_{kind.lower()}.npz"))
 
     def big_matrix(rows, cols, a, b):       # embedding / lm_head by formula, as in the generator
         i, j = torch.arange(rows)[:, None], torch.arange(cols)[None, :]
@@ -323,22 +329,29 @@ def test_uada_loop_tracks_the_reference_loop(tmp_path):
                 for k in range(n)]
 
     lr = 2e-3
-    att = UADAAttacker(sd, None, save_dir=str(tmp_path), optimizer="adamW", cfg=cfg, device="cpu",
-                       engine_factory=lambda c, B, T, device="cpu": OracleEngine(c, B, T, device, dtype=torch.bfloat16))
+    mod = importlib.import_module(f"roboticattack_b200.white_patch.{kind}")
+    kw = dict(alpha=0.8, belta=0.2) if kind == "UPA" else {}
+    att = mod.OpenVLAAttacker(sd, None, save_dir=str(tmp_path), optimizer="adamW", cfg=cfg, device="cpu",
+                              engine_factory=lambda c, B, T, device="cpu": OracleEngine(c, B, T, device, dtype=torch.bfloat16), **kw)
     random.seed(42), np.random.seed(42), torch.manual_seed(42)
+    step_arg = dict(alpha=lr) if kind == "TMA" else dict(lr=lr)
     patch = att.patchattack_unconstrained(loader("train", 3), loader("val", 2), num_iter=3, target_action=np.zeros(7), patch_size=[3, 8, 8],
-                                          lr=lr, accumulate_steps=1, maskidx=[0, 1, 2], warmup=0, filterGripTrainTo1=False, geometry=True,
-                                          innerLoop=2, args=argparse.Namespace(wandb_project="false"))
-    np.testing.assert_allclose(att.train_CE_loss, g["train_CE_loss"], rtol=1e-3)
-    np.testing.assert_allclose(att.train_MSE_distance_loss, g["train_MSE_distance_loss"], rtol=1e-3)
-    np.testing.assert_allclose(att.train_UAD, g["train_UAD"], atol=0.08)            # argmax flips of near-ties under bf16 noise
-    # validation of outer iteration 0: 1000 batches, every one drawing placements from the host RNG
-    np.testing.assert_allclose(att.val_MSE_Distance, g["val_MSE_Distance"], rtol=1e-4)
-    np.testing.assert_allclose(att.val_CE_loss, g["val_CE_loss"], rtol=1e-4)
-    np.testing.assert_allclose(att.val_UAD, g["val_UAD"], atol=5e-3)
-    ref_final = torch.from_numpy(g["patches"][-1])
-    assert (patch - ref_final).abs().max().item() < lr and (patch - ref_final).abs().mean().item() < lr / 10
+                                          accumulate_steps=1, maskidx=[0, 1, 2], warmup=0, filterGripTrainTo1=False,
+                                          geometry=(kind != "TMA"), innerLoop=2, args=argparse.Namespace(wandb_project="false"), **step_arg)
+    tol = {"train_UAD": dict(atol=0.08), "val_UAD": dict(atol=5e-3),       # argmax flips of near-ties under bf16 noise
+           "val_MSE_Distance": dict(rtol=1e-4), "val_CE_loss": dict(rtol=1e-4), "val_L1_loss": dict(rtol=1e-6), "val_ASR": dict(atol=0),
+           "avg_angle_loss": dict(rtol=2e-3), "avg_distance_loss": dict(rtol=2e-3), "avg_reserve_loss": dict(rtol=2e-3)}
+    checked = 0
+    for name in gk.files:
+        if name.startswith("w:") or name in ("grads", "patches", "saved_last", "saved_best") or name[:3] in ("tra", "val") and name[-4:] in ("_obs", "_ids") \
+                or name.endswith("_mask") or name.endswith("_labels"):
+            continue
+        np.testing.assert_allclose([float(v) for v in getattr(att, name)], gk[name], err_msg=name, **tol.get(name, dict(rtol=1e-3)))
+        checked += 1
+    assert checked >= 4
+    ref_final = torch.from_numpy(gk["patches"][-1])
+    assert (patch - ref_final).abs().max().item() < 2.5 * lr and (patch - ref_final).abs().mean().item() < lr / 10
     for sub, key in (("last", "saved_last"), ("0", "saved_best")):
         saved = torch.load(os.path.join(tmp_path, sub, "patch.pt"), weights_only=True)
-        assert (saved - torch.from_numpy(g[key])).abs().max().item() < lr
-    assert (ref_final - torch.from_numpy(g["patches"][0])).abs().max().item() > 2 * lr, "the golden trajectory moves"
+        assert (saved - torch.from_numpy(gk[key])).abs().max().item() < 2.5 * lr
+    assert (ref_final - torch.from_numpy(gk["patches"][0])).abs().max().item() > lr / 2, "the golden trajectory moves"
