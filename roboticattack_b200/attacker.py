@@ -597,6 +597,8 @@ class TMAAttacker(_AttackerBase):
             scalars, pred = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind, do_step=stepping, accumulate=acc)
             if self.optimizer == "adamW" and stepping:
                 sched_step += 1
+            # logging only: the reference averages this metric over the inner steps (TMA.py:161,177); reading the predictions of
+            # every inner step would put a device->host sync into the inner loop, so the last inner step's are used
             pr, gt = _decoded_pairs(pred, data["labels"])
             rd = lab.relative_distance(pr, gt).mean().item() if pr.numel() else 0.0
             log = {"TRAIN_attack_loss(CE)": scalars[-1, _lib.S_LOSS].item(),
