@@ -64,7 +64,7 @@ class HFAdamW(torch.optim.Optimizer):
                 PATCHES.append(p.detach().clone())
 
 
-STEPS, GRADS, PATCHES = [], [], []
+STEPS, GRADS, PATCHES, FINAL = [], [], [], []
 
 
 def batches(n, seed):
@@ -88,7 +88,7 @@ def batches(n, seed):
     return out
 
 
-def main(kind="UADA"):
+def main(kind="UADA", optimizer="adamW"):
     del STEPS[:], GRADS[:], PATCHES[:]
     cp, mp = glue.load_reference_model_module()
     glue.SPECS.update({"vit_large_patch14_reg4_dinov2.lvd142m": (32, 3, 2, 64, 5, True), "vit_so400m_patch14_siglip_224": (40, 3, 2, 72, 0, False)})
@@ -146,11 +146,19 @@ def main(kind="UADA"):
     train, val = batches(N_TRAIN, 100), batches(N_VAL, 200)
     with tempfile.TemporaryDirectory() as d:
         extra = dict(alpha=0.8, belta=0.2) if kind == "UPA" else {}
-        att = uada.OpenVLAAttacker(model, Proc(), save_dir=d, optimizer="adamW", resize_patch=False, **extra)
+        att = uada.OpenVLAAttacker(model, Proc(), save_dir=d, optimizer=optimizer, resize_patch=False, **extra)
         att.plot_loss = lambda: None          # matplotlib / seaborn are not installed
         random.seed(42)
         np.random.seed(42)
         torch.manual_seed(42)
+        rand = torch.rand
+
+        def capturing_rand(*a, **k):          # the loop creates its patch with torch.rand(patch_size): keep a handle on that tensor
+            t = rand(*a, **k)
+            FINAL.append(t)
+            return t
+        uada.torch.rand = capturing_rand
+
         class Loader:
             """Yields fresh copies: on the CPU ``labels.to(device)`` aliases the loader's tensor and the reference's in-place
             ``mask_labels`` would otherwise corrupt the batch for the next pass over the loader (on a GPU ``.to`` copies)."""
@@ -185,13 +193,15 @@ def main(kind="UADA"):
              "TMA": ["train_CE_loss", "train_inner_avg_loss", "val_CE_loss", "val_L1_loss", "val_ASR"]}[kind]
     for name in lists:
         out[name] = np.array([float(v) for v in getattr(att, name)])
-    out.update(grads=torch.stack(GRADS).numpy(), patches=torch.stack(PATCHES).numpy(), saved_last=saved_last.numpy(),
-               saved_best=saved_best.numpy())
-    suffix = "" if kind == "UADA" else "_" + kind.lower()
+    if optimizer == "adamW":
+        out.update(grads=torch.stack(GRADS).numpy(), patches=torch.stack(PATCHES).numpy())
+    out.update(saved_last=saved_last.numpy(), saved_best=saved_best.numpy(), final_patch=FINAL[-1].detach().numpy())
+    suffix = ("" if kind == "UADA" else "_" + kind.lower()) + ("" if optimizer == "adamW" else "_" + optimizer)
     np.savez_compressed(os.path.join(HERE, f"reference_golden_loop{suffix}.npz"), **out)
-    print(kind, "steps", len(GRADS), {n: out[n].tolist() for n in lists})
+    uada.torch.rand = rand
+    print(kind, optimizer, "steps", len(GRADS), {n: out[n].tolist() for n in lists})
 
 
 if __name__ == "__main__":
-    for k in (sys.argv[1:] or ["UADA", "UPA", "TMA"]):
-        main(k)
+    for k in (sys.argv[1:] or ["UADA", "UPA", "TMA", "TMA:pgd"]):
+        main(*k.split(":"))

@@ -292,8 +292,8 @@ def test_predict_action_postprocessing_matches_reference_method(monkeypatch):
         assert seen["n"] == 7
 
 
-@pytest.mark.parametrize("kind", ["UADA", "UPA", "TMA"])
-def test_attack_loops_track_the_reference_loops(tmp_path, kind):
+@pytest.mark.parametrize("kind,opt", [("UADA", "adamW"), ("UPA", "adamW"), ("TMA", "adamW"), ("TMA", "pgd")])
+def test_attack_loops_track_the_reference_loops(tmp_path, kind, opt):
     """The product's ``OpenVLAAttacker.patchattack_unconstrained`` (host loops of UADA / UPA / TMA: label preparation, host
     RNG protocol of the placements through training AND the validation pass (1000 / 100 / 100 batches), cosine schedule, the
     loss composition, AdamW step (+ UPA's L1 clip), clamp, validation metrics, best / last patch files) against the
@@ -310,7 +310,8 @@ def test_attack_loops_track_the_reference_loops(tmp_path, kind):
     from roboticattack_b200.config import LlamaConfig, OpenVLAConfig, ViTConfig
     gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     g = np.load(os.path.join(gdir, "reference_golden_loop.npz"))                       # weights + batches (+ the UADA trajectory)
-    gk = g if kind == "UADA" else np.load(os.path.join(gdir, f"reference_golden_loop_{kind.lower()}.npz"))
+    suffix = ("" if kind == "UADA" else "_" + kind.lower()) + ("" if opt == "adamW" else "_" + opt)
+    gk = g if suffix == "" else np.load(os.path.join(gdir, f"reference_golden_loop{suffix}.npz"))
 
     def big_matrix(rows, cols, a, b):       # embedding / lm_head by formula, as in the generator
         i, j = torch.arange(rows)[:, None], torch.arange(cols)[None, :]
@@ -331,7 +332,7 @@ def test_attack_loops_track_the_reference_loops(tmp_path, kind):
     lr = 2e-3
     mod = importlib.import_module(f"roboticattack_b200.white_patch.{kind}")
     kw = dict(alpha=0.8, belta=0.2) if kind == "UPA" else {}
-    att = mod.OpenVLAAttacker(sd, None, save_dir=str(tmp_path), optimizer="adamW", cfg=cfg, device="cpu",
+    att = mod.OpenVLAAttacker(sd, None, save_dir=str(tmp_path), optimizer=opt, cfg=cfg, device="cpu",
                               engine_factory=lambda c, B, T, device="cpu": OracleEngine(c, B, T, device, dtype=torch.bfloat16), **kw)
     random.seed(42), np.random.seed(42), torch.manual_seed(42)
     step_arg = dict(alpha=lr) if kind == "TMA" else dict(lr=lr)
@@ -343,15 +344,15 @@ def test_attack_loops_track_the_reference_loops(tmp_path, kind):
            "avg_angle_loss": dict(rtol=2e-3), "avg_distance_loss": dict(rtol=2e-3), "avg_reserve_loss": dict(rtol=2e-3)}
     checked = 0
     for name in gk.files:
-        if name.startswith("w:") or name in ("grads", "patches", "saved_last", "saved_best") or name[:3] in ("tra", "val") and name[-4:] in ("_obs", "_ids") \
-                or name.endswith("_mask") or name.endswith("_labels"):
+        if name.startswith("w:") or name in ("grads", "patches", "saved_last", "saved_best", "final_patch") \
+                or name[:3] in ("tra", "val") and name[-4:] in ("_obs", "_ids") or name.endswith("_mask") or name.endswith("_labels"):
             continue
         np.testing.assert_allclose([float(v) for v in getattr(att, name)], gk[name], err_msg=name, **tol.get(name, dict(rtol=1e-3)))
         checked += 1
     assert checked >= 4
-    ref_final = torch.from_numpy(gk["patches"][-1])
+    ref_final = torch.from_numpy(gk["final_patch"])
     assert (patch - ref_final).abs().max().item() < 2.5 * lr and (patch - ref_final).abs().mean().item() < lr / 10
     for sub, key in (("last", "saved_last"), ("0", "saved_best")):
         saved = torch.load(os.path.join(tmp_path, sub, "patch.pt"), weights_only=True)
         assert (saved - torch.from_numpy(gk[key])).abs().max().item() < 2.5 * lr
-    assert (ref_final - torch.from_numpy(gk["patches"][0])).abs().max().item() > lr / 2, "the golden trajectory moves"
+    assert (ref_final - torch.from_numpy(gk["saved_last"])).abs().max().item() > lr / 2, "the golden trajectory moves after iteration 0"
