@@ -14,7 +14,9 @@ from __future__ import annotations
 import math
 import os
 import pickle
+import queue
 import random
+import threading
 from typing import Iterable, Optional
 
 import numpy as np
@@ -48,6 +50,61 @@ def observations_to_uint8(pixel_values, img: int) -> torch.Tensor:
     if not t.is_cuda and torch.cuda.is_available() and not t.is_pinned():
         t = t.pin_memory()
     return t
+
+
+class BatchPrefetcher:
+    """Pulls batch k + 1 from the loader on a background thread while the device runs the ``innerLoop`` steps of batch k
+    (SURVEY.md 8f-2): ``next()`` of the TF / torch loader and the PIL -> pinned uint8 conversion leave the critical path
+    (the reference fetches and re-uploads synchronously, UADA.py:119-126 and appply_random_transform.py:108).  The worker
+    touches neither the Python / NumPy / torch RNG streams that drive placements nor the engine, so results are identical
+    with and without it; an exception raised by the loader surfaces at the ``next()`` that would have produced that batch.
+    Like ``_AttackerBase._next`` it restarts an exhausted loader (``restart=False``: ``next()`` raises StopIteration instead)."""
+
+    def __init__(self, loader, img: int, depth: int = 1, restart: bool = True):
+        self._loader, self._img, self._restart = loader, img, restart
+        self._q: "queue.Queue" = queue.Queue(maxsize=depth)
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, name="vla-batch-prefetch", daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        it = iter(self._loader)
+        while not self._stop.is_set():
+            try:
+                try:
+                    batch = next(it)
+                except StopIteration:
+                    if not self._restart:
+                        raise
+                    it = iter(self._loader)
+                    batch = next(it)
+                batch = dict(batch)
+                batch["pixel_values"] = observations_to_uint8(batch["pixel_values"], self._img)
+                item = (batch, None)
+            except BaseException as e:   # noqa: BLE001 -- handed to the consumer
+                item = (None, e)
+            while not self._stop.is_set():
+                try:
+                    self._q.put(item, timeout=0.1)
+                    break
+                except queue.Full:
+                    continue
+            if item[1] is not None:
+                return
+
+    def next(self):
+        batch, err = self._q.get()
+        if err is not None:
+            raise err
+        return batch
+
+    def close(self):
+        self._stop.set()
+        try:
+            while True:
+                self._q.get_nowait()
+        except queue.Empty:
+            pass
 
 
 class AttackEngineHost:
@@ -338,8 +395,24 @@ class _AttackerBase(object):
         out["pixel_values"] = [pv[i] for i in chosen] if isinstance(pv, (list, tuple)) else pv[chosen]
         return out
 
+    def _open(self, loader):
+        """Iterator over ``loader``: a background prefetcher (default) or the plain iterator (``VLA_PREFETCH=0``)."""
+        if loader is None:
+            return None
+        if os.environ.get("VLA_PREFETCH", "1") != "0":
+            return BatchPrefetcher(loader, self.host.cfg.img)
+        return iter(loader)
+
+    @staticmethod
+    def _close(*iterators):
+        for it in iterators:
+            if isinstance(it, BatchPrefetcher):
+                it.close()
+
     @staticmethod
     def _next(iterator, loader):
+        if isinstance(iterator, BatchPrefetcher):
+            return iterator.next(), iterator
         try:
             return next(iterator), iterator
         except StopIteration:
@@ -372,8 +445,8 @@ class UADAAttacker(_AttackerBase):
         total = int(num_iter / accumulate_steps)
         start_iter, sched_step = self._maybe_resume()
         self._sched_step = sched_step
-        train_it = iter(train_dataloader)
-        val_it = iter(val_dataloader) if val_dataloader is not None else None
+        train_it = self._open(train_dataloader)
+        val_it = self._open(val_dataloader)
         for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
             data = dict(data)
@@ -403,6 +476,7 @@ class UADAAttacker(_AttackerBase):
                 val_it = self._validate(i, val_it, val_dataloader, maskidx, fe_mode, loss, args)
             elif i % self.val_every == 0 and self.save_dir:
                 self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
+        self._close(train_it, val_it)
         return h.patch.detach().cpu()
 
     def _validate(self, i, val_it, val_dataloader, maskidx, fe_mode, loss, args):
@@ -471,7 +545,7 @@ class UPAAttacker(_AttackerBase):
         self.train_CE_loss, self.val_CE_loss = [], []
         self.avg_reserve_loss, self.avg_angle_loss, self.avg_distance_loss = [], [], []
         self.reverse_direction_loss = 1e8
-        val_it = iter(val_dataloader) if val_dataloader is not None else None
+        val_it = self._open(val_dataloader)
         h.init_patch(patch_size)
         if guide:
             loss = LossSpec(_lib.LOSS_CE, ce_scale=1.0)
@@ -484,7 +558,7 @@ class UPAAttacker(_AttackerBase):
         total = int(num_iter / accumulate_steps)
         start_iter, sched_step = self._maybe_resume()
         acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
-        train_it = iter(train_dataloader)
+        train_it = self._open(train_dataloader)
         for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
             data = dict(data)
@@ -514,6 +588,7 @@ class UPAAttacker(_AttackerBase):
                 else:
                     self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
                 self._dump(train_CE_loss=self.train_CE_loss)
+        self._close(train_it, val_it)
         return h.patch.detach().cpu()
 
     def _validate(self, i, val_it, val_dataloader, fe_mode, loss, sched_step, args):
@@ -576,7 +651,7 @@ class TMAAttacker(_AttackerBase):
         self.train_CE_loss, self.train_inner_avg_loss, self.train_inner_relatived_distance = [], [], []
         self.val_CE_loss, self.val_L1_loss, self.val_ASR, self.val_inner_relatived_distance = [], [], [], []
         self.min_val_avg_L1_loss = 1e8
-        val_it = iter(val_dataloader) if val_dataloader is not None else None
+        val_it = self._open(val_dataloader)
         h.init_patch(patch_size)
         target = lab.tma_target(target_action, maskidx)
         loss = LossSpec(_lib.LOSS_CE, ce_scale=1.0 / accumulate_steps)
@@ -585,7 +660,7 @@ class TMAAttacker(_AttackerBase):
         total = int(num_iter / accumulate_steps)
         start_iter, sched_step = self._maybe_resume()
         acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
-        train_it = iter(train_dataloader)
+        train_it = self._open(train_dataloader)
         for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
             data = dict(data)
@@ -616,6 +691,7 @@ class TMAAttacker(_AttackerBase):
                     self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
                 self._dump(train_CE_loss=self.train_CE_loss, train_inner_avg_loss=self.train_inner_avg_loss,
                            train_inner_relatived_distance=self.train_inner_relatived_distance)
+        self._close(train_it, val_it)
         return h.patch.detach().cpu()
 
     def _validate(self, i, val_it, val_dataloader, target, maskidx, fe_mode, sched_step, args):
@@ -770,8 +846,12 @@ class UADADDPAttacker(_AttackerBase):
         loss = LossSpec(_lib.LOSS_UADA_DDP, mse_weight=float(self.MSE_weights))
         fe_mode = _lib.FE_WARP if self.geometry else _lib.FE_PASTE20
         logs = []
-        for i, data in enumerate(train_dataloader, start=start_iter):
-            if i >= self.num_iter:
+        prefetch = os.environ.get("VLA_PREFETCH", "1") != "0"
+        train_it = BatchPrefetcher(train_dataloader, h.cfg.img, restart=False) if prefetch else iter(train_dataloader)
+        for i in range(start_iter, int(self.num_iter)):
+            try:                                   # ``for i, data in enumerate(loader)`` of UADA_ddp.py:176: ends with the loader
+                data = train_it.next() if prefetch else next(train_it)
+            except StopIteration:
                 break
             data = dict(data)
             data["labels"] = self.mask_labels(data["labels"].clone(), self.maskidx)
@@ -795,6 +875,7 @@ class UADADDPAttacker(_AttackerBase):
                 elif rank == 0 and self.save_dir:
                     self._save_patch(h.patch, "last", outer_iter=i, sched_step=i + 1)
         self.train_logs = logs
+        self._close(train_it)
         return h.patch.detach().cpu()
 
     def _validate(self, i, rank, world_size, val_dataloader, fe_mode, loss):

@@ -356,3 +356,45 @@ def test_attack_loops_track_the_reference_loops(tmp_path, kind, opt):
         saved = torch.load(os.path.join(tmp_path, sub, "patch.pt"), weights_only=True)
         assert (saved - torch.from_numpy(gk[key])).abs().max().item() < 2.5 * lr
     assert (ref_final - torch.from_numpy(gk["saved_last"])).abs().max().item() > lr / 2, "the golden trajectory moves after iteration 0"
+
+
+def test_batch_prefetcher_overlaps_and_preserves_order():
+    """the next batch is fetched (and its PIL images converted) on a background thread while the current one
+    is being worked on; order, restart-on-exhaustion and exception propagation are those of plain iteration."""
+    import time
+    from PIL import Image
+    from roboticattack_b200.attacker import BatchPrefetcher
+
+    class SlowLoader:
+        def __init__(self, n, fail_at=None):
+            self.n, self.fail_at, self.fetched = n, fail_at, []
+
+        def __iter__(self):
+            for k in range(self.n):
+                time.sleep(0.05)
+                if k == self.fail_at:
+                    raise RuntimeError("loader died")
+                self.fetched.append(k)
+                yield {"pixel_values": [Image.fromarray(np.full((28, 28, 3), k, dtype=np.uint8))], "k": k}
+
+    pf = BatchPrefetcher(SlowLoader(3), 28)
+    t0 = time.perf_counter()
+    ks = []
+    for _ in range(7):                       # more than one pass: the loader restarts like _AttackerBase._next
+        b = pf.next()
+        assert b["pixel_values"].dtype == torch.uint8 and tuple(b["pixel_values"].shape) == (1, 28, 28, 3)
+        assert int(b["pixel_values"][0, 0, 0, 0]) == b["k"]
+        ks.append(b["k"])
+        time.sleep(0.05)                     # "the inner loop"
+    dt = time.perf_counter() - t0
+    pf.close()
+    assert ks == [0, 1, 2, 0, 1, 2, 0]
+    assert dt < 0.60, f"fetch (7 x 50 ms) and work (7 x 50 ms) did not overlap: {dt:.2f}s"
+    pf = BatchPrefetcher(SlowLoader(3, fail_at=2), 28)
+    assert pf.next()["k"] == 0 and pf.next()["k"] == 1
+    with pytest.raises(RuntimeError, match="loader died"):
+        pf.next()
+    pf = BatchPrefetcher(SlowLoader(2), 28, restart=False)
+    assert [pf.next()["k"], pf.next()["k"]] == [0, 1]
+    with pytest.raises(StopIteration):
+        pf.next()
