@@ -182,6 +182,20 @@ def main(kind="UADA", optimizer="adamW"):
         saved_last = torch.load(os.path.join(d, "last", "patch.pt"))
         saved_best = torch.load(os.path.join(d, "0", "patch.pt"))
     out = dict(weights) if kind == "UADA" else {}      # the three fixtures share the weights and batches of the UADA one
+    if kind == "UADA":
+        # filter_train (UADA.py:309-340) on crafted gripper labels: 3 of 5 closed, none, exactly 8, 11 of 12 (random.sample of 8)
+        for c, grips in enumerate(([1, 0, 1, 1, 0], [0, 0, 0], [1] * 8, [1] * 11 + [0])):
+            n, T2 = len(grips), 12
+            lab_in = torch.full((n, T2), -100, dtype=torch.int64)
+            for r, gv in enumerate(grips):
+                lab_in[r, T2 - 8:T2 - 1] = torch.tensor([31800 + r] * 6 + [31744 if gv else 31872])
+                lab_in[r, T2 - 1] = 2
+            batch = {"labels": lab_in.clone(), "input_ids": torch.arange(n * T2).view(n, T2), "attention_mask": torch.ones(n, T2, dtype=torch.bool),
+                     "pixel_values": list(range(n))}
+            random.seed(5)
+            fl, fm, fi, fp = att.filter_train(batch)
+            out[f"ft{c}_grips"] = np.array(grips)
+            out[f"ft{c}_labels"], out[f"ft{c}_mask"], out[f"ft{c}_ids"], out[f"ft{c}_pixels"] = fl.numpy(), fm.numpy(), fi.numpy(), np.array(fp)
     for name, bs in ((("train", train), ("val", val)) if kind == "UADA" else ()):
         for k, b in enumerate(bs):
             out[f"{name}{k}_obs"] = b["obs"]

@@ -398,3 +398,25 @@ def test_batch_prefetcher_overlaps_and_preserves_order():
     assert [pf.next()["k"], pf.next()["k"]] == [0, 1]
     with pytest.raises(StopIteration):
         pf.next()
+
+
+def test_filter_train_matches_reference_method():
+    """``filter_train`` against the reference's own method (UADA.py:309-340, called from tests/golden/make_golden_loop.py):
+    2..7 closed-gripper samples are kept, more than 8 are sampled down to 8 with ``random.sample``, anything else passes."""
+    from roboticattack_b200.attacker import _AttackerBase
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_loop.npz"))
+    for c in range(4):
+        grips = g[f"ft{c}_grips"]
+        n, T2 = len(grips), 12
+        labels = torch.full((n, T2), -100, dtype=torch.int64)
+        for r, gv in enumerate(grips):
+            labels[r, T2 - 8:T2 - 1] = torch.tensor([31800 + r] * 6 + [31744 if gv else 31872])
+            labels[r, T2 - 1] = 2
+        batch = {"labels": labels, "input_ids": torch.arange(n * T2).view(n, T2), "attention_mask": torch.ones(n, T2, dtype=torch.bool),
+                 "pixel_values": list(range(n))}
+        random.seed(5)
+        out = _AttackerBase.filter_train(batch)
+        np.testing.assert_array_equal(out["labels"].numpy(), g[f"ft{c}_labels"])
+        np.testing.assert_array_equal(out["attention_mask"].numpy(), g[f"ft{c}_mask"])
+        np.testing.assert_array_equal(out["input_ids"].numpy(), g[f"ft{c}_ids"])
+        assert list(out["pixel_values"]) == g[f"ft{c}_pixels"].tolist()
