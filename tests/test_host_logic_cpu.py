@@ -371,25 +371,27 @@ def test_batch_prefetcher_overlaps_and_preserves_order():
 
         def __iter__(self):
             for k in range(self.n):
-                time.sleep(0.05)
+                time.sleep(0.04)
                 if k == self.fail_at:
                     raise RuntimeError("loader died")
                 self.fetched.append(k)
                 yield {"pixel_values": [Image.fromarray(np.full((28, 28, 3), k, dtype=np.uint8))], "k": k}
 
-    pf = BatchPrefetcher(SlowLoader(3), 28)
+    src = SlowLoader(3)
+    pf = BatchPrefetcher(src, 28)
     t0 = time.perf_counter()
     ks = []
-    for _ in range(7):                       # more than one pass: the loader restarts like _AttackerBase._next
+    for i in range(7):                       # more than one pass: the loader restarts like _AttackerBase._next
         b = pf.next()
         assert b["pixel_values"].dtype == torch.uint8 and tuple(b["pixel_values"].shape) == (1, 28, 28, 3)
         assert int(b["pixel_values"][0, 0, 0, 0]) == b["k"]
         ks.append(b["k"])
-        time.sleep(0.05)                     # "the inner loop"
+        time.sleep(0.08)                     # "the inner loop": twice the fetch time
+        assert len(src.fetched) >= i + 2, "the next batch was not fetched while this one was being worked on"
     dt = time.perf_counter() - t0
     pf.close()
     assert ks == [0, 1, 2, 0, 1, 2, 0]
-    assert dt < 0.60, f"fetch (7 x 50 ms) and work (7 x 50 ms) did not overlap: {dt:.2f}s"
+    assert dt < 0.78, f"fetch (7 x 40 ms) and work (7 x 80 ms) did not overlap: {dt:.2f}s (serial: 0.84 s)"
     pf = BatchPrefetcher(SlowLoader(3, fail_at=2), 28)
     assert pf.next()["k"] == 0 and pf.next()["k"] == 1
     with pytest.raises(RuntimeError, match="loader died"):
