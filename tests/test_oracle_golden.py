@@ -271,3 +271,23 @@ def test_multimodal_forward_matches_reference_model_class():
     mm_mask = torch.cat([mask[:, :1], torch.ones(mask.shape[0], P, dtype=torch.bool), mask[:, 1:]], dim=1)
     got, ref = out.logits.float(), torch.from_numpy(gold["logits"])
     torch.testing.assert_close(got[mm_mask], ref[mm_mask], rtol=1e-4, atol=1e-4)
+
+
+def test_checkpoint_names_match_the_reference_model_state_dict():
+    """The engine loads weights by HF checkpoint name (``vla_engine_load_weight``).  ``param_shapes`` against the state dict of
+    the reference's own ``OpenVLAForActionPrediction`` (fixture of make_golden_glue.py): every name and shape the engine asks
+    for exists there, and the only reference tensors it ignores are the last block of each tower, whose output the reference
+    computes and discards (``get_intermediate_layers(n={depth-2})``)."""
+    import os
+    from roboticattack_b200.config import LlamaConfig, OpenVLAConfig, ViTConfig
+    from roboticattack_b200.weights import param_shapes
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_glue.npz"))
+    ref = {k[2:]: tuple(gold[k].shape) for k in gold.files if k.startswith("w:")}
+    cfg = OpenVLAConfig(dino=ViTConfig(dim=32, depth=3, heads=2, mlp_hidden=128, num_prefix=5, layerscale=True, img=28),
+                        siglip=ViTConfig(dim=40, depth=4, heads=2, mlp_hidden=136, num_prefix=0, layerscale=False, img=28),
+                        llm=LlamaConfig(hidden=64, layers=2, heads=2, ffn=176, vocab=384), name="glue")
+    ours = {k: tuple(v) for k, v in dict(param_shapes(cfg)).items()}
+    assert set(ours) <= set(ref), sorted(set(ours) - set(ref))
+    assert all(ours[k] == ref[k] for k in ours), [(k, ours[k], ref[k]) for k in ours if ours[k] != ref[k]]
+    ignored = set(ref) - set(ours)
+    assert ignored and all(k.startswith(("vision_backbone.featurizer.blocks.2.", "vision_backbone.fused_featurizer.blocks.3.")) for k in ignored)
