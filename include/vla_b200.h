@@ -14,7 +14,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#define VLA_B200_ABI_VERSION 1
+#define VLA_B200_ABI_VERSION 2
 
 #ifdef __cplusplus
 extern "C" {
@@ -101,6 +101,28 @@ int vla_patch_update(float* patch, const float* grad, float* exp_avg, float* exp
 int vla_gemm_bf16_tn(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
                      const void* bias, const void* gamma, const void* resid, int64_t ldr, int act, void* preact_out,
                      int out_f32, void* stream);
+/* Every fused epilogue of the tcgen05 GEMM (csrc/gemm.h: GemmEpilogue), for the per-variant x per-epilogue parity tests.
+ * Zero-initialise and set what the mode needs; the kernel variant is pinned with vla_gemm_set_mode. */
+typedef struct vla_gemm_epilogue {
+  const void *bias, *gamma, *resid;   /* bf16 [N], [N], [M or resid_mod, ldr] */
+  int64_t ldr;
+  int act;                            /* 1 = erf GELU */
+  void* preact_out;                   /* bf16 [M, ldc]: Linear output before the activation */
+  int out_f32;
+  int out_group, out_stride, out_offset, resid_mod;
+  int aux_mode;                       /* 1 = GELU backward, 2 = SwiGLU backward (out = d(gate|up), ldc = 2N) */
+  const void* aux;                    /* bf16: saved pre-activation / gate|up / attention output O */
+  int64_t ldaux;
+  int pair_mode;                      /* 1 = RoPE on columns < rope_cols, 2 = SwiGLU forward (act_out [M, N/2]) */
+  const float *rope_cos, *rope_sin;   /* f32 [rope_L, 64] */
+  int rope_L, rope_cols;
+  void* act_out;
+  int64_t ld_act;
+  float* delta_out;                   /* f32 [M / delta_L, N / 128, delta_L]: rowsum(dO * O) per head; aux = O */
+  int delta_L;
+} vla_gemm_epilogue;
+int vla_gemm_bf16_tn_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
+                        const vla_gemm_epilogue* ep, void* stream);
 int vla_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t M, int d,
                       float eps, void* stream);
 int vla_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
@@ -175,6 +197,51 @@ enum { VLA_FLAG_FORWARD_ONLY = 1 };   /* validation pass: loss heads + metrics, 
 /* patch f32 [3,ph,pw] -> dpatch f32 [3,ph,pw], scalars f32 [VLA_NUM_SCALARS], pred_ids i32 [num_supervised] */
 int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, int step_idx, int fe_mode,
                 const vla_loss_params* lp, float* dpatch, float* scalars, int32_t* pred_ids, int flags, void* stream);
+/* ------------------------------------------------------------------------------------------------------------
+ * Patch-gradient exchange of the data-parallel attack (UADA_ddp.py:206: DDP's all-reduce of patch.grad on every backward).
+ * A vla_comm wraps an NCCL communicator (libnccl.so.2 is resolved at run time; one communicator per process / GPU).
+ * Rank 0 makes the 128-byte id, the host side distributes it (any channel), every rank calls vla_comm_create on its GPU. */
+typedef struct vla_comm vla_comm;
+#define VLA_COMM_ID_BYTES 128
+int vla_comm_unique_id(void* id_host);
+int vla_comm_create(const void* id_host, int rank, int world, vla_comm** out);
+void vla_comm_destroy(vla_comm* c);
+int vla_comm_world(const vla_comm* c);
+/* in-place sum over ranks of dpatch f32 [n] on `stream` (ncclAllReduce); the 1/world of DDP's mean is folded into
+ * vla_patch_update's grad_scale */
+int vla_allreduce_patch_grad(vla_comm* c, float* dpatch, int n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * One whole attack iteration = the body of the reference's inner loop (UADA.py:134-158, UADA_ddp.py:192-209,
+ * UPA.py:134-160, TMA.py:133-175) as ONE call: front end -> model forward -> loss head -> backward to the patch ->
+ * [accumulate] -> [all-reduce over ranks] -> [clip] -> AdamW / sign-PGD -> clamp.
+ * The placement index, the optimiser's step counter t and the learning rate live in device memory (so that the whole
+ * iteration is one replayable CUDA graph): step k of an outer iteration reads placement k of vla_engine_set_placements,
+ * writes its scalar record to scalars_hist[k] and advances the counters on the device.  vla_engine_set_step_state sets
+ * them (start of an outer iteration: place = 0; resume: adam_step = restored value).
+ * The first call with a new (plan, patch size, modes, buffers) runs eagerly (it also lets the GEMM autotuner see the
+ * shapes), the second one records the same launch sequence into a CUDA graph, later ones replay it: one graph launch per
+ * attack iteration.  VLA_STEP_NO_GRAPH keeps it eager (bit-identical results: same kernels, same order). */
+enum { VLA_STEP_NO_GRAPH = 1, VLA_STEP_NO_UPDATE = 2 /* accumulate-only iteration (accumulate_steps > 1) */ };
+typedef struct vla_step_params {
+  int ph, pw, fe_mode;
+  vla_loss_params loss;
+  int opt_kind;                    /* VLA_OPT_* */
+  float lr, beta1, beta2, eps;     /* transformers.AdamW defaults: 0.9, 0.999, 1e-6 */
+  float clip_l1;                   /* > 0: clip_grad_norm_(max_norm, norm_type=1) of UPA.py:157 */
+  int flags;                       /* VLA_STEP_* */
+} vla_step_params;
+int vla_engine_set_step_state(vla_engine* e, int placement_index, int adam_step, void* stream);
+/* host mirror of the device counters (no synchronisation) */
+int vla_engine_get_step_state(const vla_engine* e, int* placement_index, int* adam_step);
+/* patch / exp_avg / exp_avg_sq / dpatch f32 [3,ph,pw]; accumulate f32 [3,ph,pw] or NULL; comm NULL = single GPU;
+ * scalars_hist f32 [>= placements, VLA_NUM_SCALARS]; pred_ids i32 [num_supervised] */
+int vla_attack_step(vla_engine* e, float* patch, float* exp_avg, float* exp_avg_sq, float* dpatch, float* accumulate,
+                    const vla_step_params* sp, vla_comm* comm, float* scalars_hist, int32_t* pred_ids, void* stream);
+/* bookkeeping for bench.py: attack steps replayed from a graph so far / kernel nodes of the most recent graph */
+long long vla_graph_replays(void);
+int vla_graph_kernel_nodes(const vla_engine* e);
+
 /* test tap: copies a named internal activation ("px", "dino_out", "llm_out", "logits", ...) to dst (device) */
 int64_t vla_engine_debug_tap(vla_engine* e, const char* what, void* dst, int64_t max_bytes, void* stream);
 

@@ -17,6 +17,9 @@ LOSS_UADA, LOSS_UADA_DDP, LOSS_UPA, LOSS_CE, LOSS_NEG_CE = 0, 1, 2, 3, 4
 OPT_ADAMW, OPT_PGD = 0, 1
 S_LOSS, S_CE, S_AUX0, S_AUX1, S_UAD, S_NTOK, S_NACT, S_GRAD_MEAN, NUM_SCALARS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 FLAG_FORWARD_ONLY = 1
+STEP_NO_GRAPH, STEP_NO_UPDATE = 1, 2
+COMM_ID_BYTES = 128
+ABI_VERSION = 2
 
 
 class VLAError(RuntimeError):
@@ -25,6 +28,20 @@ class VLAError(RuntimeError):
 
 class LossParams(Structure):
     _fields_ = [("kind", c_int), ("mse_weight", c_float), ("alpha", c_float), ("belta", c_float), ("ce_scale", c_float)]
+
+
+class StepParams(Structure):
+    _fields_ = [("ph", c_int), ("pw", c_int), ("fe_mode", c_int), ("loss", LossParams), ("opt_kind", c_int),
+                ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("clip_l1", c_float), ("flags", c_int)]
+
+
+class GemmEpilogue(Structure):
+    """vla_gemm_epilogue (parity tests of the fused GEMM epilogues)."""
+    _fields_ = [("bias", c_void_p), ("gamma", c_void_p), ("resid", c_void_p), ("ldr", c_int64), ("act", c_int),
+                ("preact_out", c_void_p), ("out_f32", c_int), ("out_group", c_int), ("out_stride", c_int), ("out_offset", c_int),
+                ("resid_mod", c_int), ("aux_mode", c_int), ("aux", c_void_p), ("ldaux", c_int64), ("pair_mode", c_int),
+                ("rope_cos", c_void_p), ("rope_sin", c_void_p), ("rope_L", c_int), ("rope_cols", c_int), ("act_out", c_void_p),
+                ("ld_act", c_int64), ("delta_out", c_void_p), ("delta_L", c_int)]
 
 
 class Config(Structure):
@@ -60,6 +77,8 @@ SIGNATURES = {
                                  c_float, c_int, c_float, c_float, c_void_p, c_void_p]),
     "vla_gemm_bf16_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
+    "vla_gemm_bf16_tn_ex": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                                    POINTER(GemmEpilogue), c_void_p]),
     "vla_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float,
                                   c_void_p]),
     "vla_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
@@ -91,6 +110,17 @@ SIGNATURES = {
     "vla_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(LossParams), c_void_p, c_void_p,
                             c_void_p, c_int, c_void_p]),
     "vla_engine_debug_tap": (c_int64, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
+    "vla_comm_unique_id": (c_int, [c_void_p]),
+    "vla_comm_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "vla_comm_destroy": (None, [c_void_p]),
+    "vla_comm_world": (c_int, [c_void_p]),
+    "vla_allreduce_patch_grad": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "vla_engine_set_step_state": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "vla_engine_get_step_state": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "vla_attack_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(StepParams), c_void_p,
+                                c_void_p, c_void_p, c_void_p]),
+    "vla_graph_replays": (c_longlong, []),
+    "vla_graph_kernel_nodes": (c_int, [c_void_p]),
 }
 
 

@@ -52,59 +52,53 @@ def observations_to_uint8(pixel_values, img: int) -> torch.Tensor:
     return t
 
 
-class BatchPrefetcher:
-    """Pulls batch k + 1 from the loader on a background thread while the device runs the ``innerLoop`` steps of batch k
-    (SURVEY.md 8f-2): ``next()`` of the TF / torch loader and the PIL -> pinned uint8 conversion leave the critical path
-    (the reference fetches and re-uploads synchronously, UADA.py:119-126 and appply_random_transform.py:108).  The worker
-    touches neither the Python / NumPy / torch RNG streams that drive placements nor the engine, so results are identical
-    with and without it; an exception raised by the loader surfaces at the ``next()`` that would have produced that batch.
-    Like ``_AttackerBase._next`` it restarts an exhausted loader (``restart=False``: ``next()`` raises StopIteration instead)."""
+class LookaheadLoader:
+    """Batch k + 1 is pulled from the loader and converted (PIL -> pinned uint8) while the device runs the ``innerLoop``
+    steps of batch k -- on the CALLING thread, between the asynchronous launch of the inner steps and the
+    read-back of their scalars.  The reference fetches and re-uploads synchronously (UADA.py:119-126,
+    appply_random_transform.py:108).  Everything that consumes an RNG stream (the loader's ``iter`` / ``next``, label
+    helpers, placement draws) therefore runs on one thread in the reference's order: next(k), placements(k), next(k + 1),
+    placements(k + 1) ... so a seeded run is reproducible with and without the lookahead (``VLA_PREFETCH=0`` disables it).
+    ``next()`` restarts an exhausted loader like the reference's ``while``-loop (``restart=False``: StopIteration)."""
 
-    def __init__(self, loader, img: int, depth: int = 1, restart: bool = True):
-        self._loader, self._img, self._restart = loader, img, restart
-        self._q: "queue.Queue" = queue.Queue(maxsize=depth)
-        self._stop = threading.Event()
-        self._thread = threading.Thread(target=self._run, name="vla-batch-prefetch", daemon=True)
-        self._thread.start()
+    def __init__(self, loader, img: int, restart: bool = True, lookahead: bool = True):
+        self._loader, self._img, self._restart, self._lookahead = loader, img, restart, lookahead
+        self._it = None
+        self._slot = None          # (batch, exception) fetched ahead of time
 
-    def _run(self):
-        it = iter(self._loader)
-        while not self._stop.is_set():
-            try:
-                try:
-                    batch = next(it)
-                except StopIteration:
-                    if not self._restart:
-                        raise
-                    it = iter(self._loader)
-                    batch = next(it)
-                batch = dict(batch)
-                batch["pixel_values"] = observations_to_uint8(batch["pixel_values"], self._img)
-                item = (batch, None)
-            except BaseException as e:   # noqa: BLE001 -- handed to the consumer
-                item = (None, e)
-            while not self._stop.is_set():
-                try:
-                    self._q.put(item, timeout=0.1)
-                    break
-                except queue.Full:
-                    continue
-            if item[1] is not None:
-                return
-
-    def next(self):
-        batch, err = self._q.get()
-        if err is not None:
-            raise err
+    def _fetch(self):
+        if self._it is None:
+            self._it = iter(self._loader)
+        try:
+            batch = next(self._it)
+        except StopIteration:
+            if not self._restart:
+                raise
+            self._it = iter(self._loader)
+            batch = next(self._it)
+        batch = dict(batch)
+        batch["pixel_values"] = observations_to_uint8(batch["pixel_values"], self._img)
         return batch
 
-    def close(self):
-        self._stop.set()
+    def prefetch(self):
+        """Fetch the next batch now (called while the device is busy); an exception is kept for the ``next()`` that needs it."""
+        if not self._lookahead or self._slot is not None:
+            return
         try:
-            while True:
-                self._q.get_nowait()
-        except queue.Empty:
-            pass
+            self._slot = (self._fetch(), None)
+        except BaseException as e:   # noqa: BLE001 -- re-raised by next()
+            self._slot = (None, e)
+
+    def next(self):
+        if self._slot is not None:
+            (batch, err), self._slot = self._slot, None
+            if err is not None:
+                raise err
+            return batch
+        return self._fetch()
+
+    def close(self):
+        self._slot = None
 
 
 class AttackEngineHost:
@@ -122,6 +116,8 @@ class AttackEngineHost:
         self.patch = self.m = self.v = self.grad = None
         self.opt_step = 0
         self.world_size, self.rank = 1, 0
+        self.comm = None
+        self._scalars = self._pred = None
 
     # -- engine ---------------------------------------------------------------------------------------------
     def ensure_engine(self, B: int, T: int):
@@ -151,15 +147,29 @@ class AttackEngineHost:
         self.grad = torch.zeros_like(self.patch)
         self.opt_step = 0
 
-    def state_dict(self, outer_iter: int, sched_step: int) -> dict:
+    def state_dict(self, outer_iter: int, sched_step: int, accumulate: Optional[torch.Tensor] = None) -> dict:
         """Everything a restart needs beyond ``patch.pt`` (the reference cannot resume): the optimiser moments
-        and step counter, the outer / scheduler position and the three host RNG streams that drive placements and init."""
-        return {"patch": self.patch.detach().cpu(), "m": self.m.detach().cpu(), "v": self.v.detach().cpu(),
-                "opt_step": int(self.opt_step), "outer_iter": int(outer_iter), "sched_step": int(sched_step),
-                "py_random": random.getstate(), "np_random": np.random.get_state(), "torch_rng": torch.get_rng_state()}
+        and step counter, the gradient-accumulation buffer of TMA / UPA (``accumulate_steps`` > 1), the outer / scheduler
+        position and the three host RNG streams that drive placements and init.  Only tensors, numbers, strings and lists, so
+        that the file loads with ``torch.load(weights_only=True)`` (no pickle execution on a path taken from the environment).
+        In the data-parallel attack rank 0 writes the file and every rank restores from it: the reference seeds all ranks
+        identically (UADA_wrapper_ddp.py:53), i.e. the placement streams of the ranks are identical by design."""
+        ver, mt, gauss = random.getstate()
+        np_name, np_keys, np_pos, np_has_gauss, np_cached = np.random.get_state()
+        st = {"patch": self.patch.detach().cpu(), "m": self.m.detach().cpu(), "v": self.v.detach().cpu(),
+              "opt_step": int(self.opt_step), "outer_iter": int(outer_iter), "sched_step": int(sched_step),
+              "py_random": {"version": int(ver), "state": torch.tensor(list(mt), dtype=torch.int64),
+                            "gauss": None if gauss is None else float(gauss)},
+              "np_random": {"name": str(np_name), "keys": torch.from_numpy(np_keys.astype(np.int64)), "pos": int(np_pos),
+                            "has_gauss": int(np_has_gauss), "cached": float(np_cached)},
+              "torch_rng": torch.get_rng_state()}
+        if accumulate is not None:
+            st["accumulate"] = accumulate.detach().cpu()
+        return st
 
-    def load_state_dict(self, st: dict):
-        """Restores patch / moments / counters and the RNG streams; returns (next outer iteration, scheduler step)."""
+    def load_state_dict(self, st: dict, accumulate: Optional[torch.Tensor] = None):
+        """Restores patch / moments / counters / accumulation buffer and the RNG streams; returns (next outer iteration,
+        scheduler step)."""
         if self.patch is not None and tuple(st["patch"].shape) != tuple(self.patch.shape):
             raise ValueError(f"resume: patch shape {tuple(st['patch'].shape)} != configured {tuple(self.patch.shape)}")
         self.patch = st["patch"].to(self.device, torch.float32).contiguous()
@@ -167,38 +177,50 @@ class AttackEngineHost:
         self.v = st["v"].to(self.device, torch.float32).contiguous()
         self.grad = torch.zeros_like(self.patch)
         self.opt_step = int(st["opt_step"])
-        random.setstate(st["py_random"])
-        np.random.set_state(st["np_random"])
+        if accumulate is not None:
+            if "accumulate" not in st:
+                raise ValueError("resume: the run uses accumulate_steps > 1 but the state file has no accumulation buffer")
+            accumulate.copy_(st["accumulate"].to(accumulate.device))
+        pr, nr = st["py_random"], st["np_random"]
+        random.setstate((int(pr["version"]), tuple(int(x) for x in pr["state"].tolist()), pr["gauss"]))
+        np.random.set_state((nr["name"], nr["keys"].numpy().astype(np.uint32), int(nr["pos"]), int(nr["has_gauss"]), float(nr["cached"])))
         torch.set_rng_state(st["torch_rng"])
         return int(st["outer_iter"]) + 1, int(st["sched_step"])
 
+    def ensure_comm(self):
+        """Communicator of the patch-gradient all-reduce (created once, after ``world_size`` is known)."""
+        if self.world_size > 1 and self.comm is None:
+            self.comm = self.engine.make_comm(self.rank, self.world_size)
+        return self.comm
+
     def run_inner_loop(self, batch, n_inner, fe_mode, loss: LossSpec, lr, opt_kind, clip_l1=0.0, do_step=True,
-                       accumulate=None):
-        """One outer iteration. Returns (scalars [n_inner, 8] on the host, pred_ids [R] of the last inner step)."""
+                       accumulate=None, after_launch=None):
+        """One outer iteration: upload the batch and the placements of all inner steps, then ``n_inner`` calls of
+        ``vla_attack_step`` (one CUDA graph launch each), nothing read back in between.  ``after_launch`` runs on the host
+        while the device works (the loaders' lookahead).  Returns (scalars [n_inner, 8] on the host, pred_ids [R] of the last
+        inner step)."""
         obs = observations_to_uint8(batch["pixel_values"], self.cfg.img)
         B, T = batch["input_ids"].shape
         eng = self.ensure_engine(B, T)
+        comm = self.ensure_comm()
         R = eng.set_batch(obs, batch["input_ids"], batch["attention_mask"], batch["labels"])
         geometry = fe_mode == _lib.FE_WARP
         xy, theta = draw_placements(B, (self.cfg.img, self.cfg.img), tuple(self.patch.shape[1:]), geometry, steps=n_inner)
         eng.set_placements(xy, theta)
-        scalars = torch.zeros(n_inner, _lib.NUM_SCALARS, device=self.device)
-        pred = torch.full((R,), -1, dtype=torch.int32, device=self.device)
+        eng.set_step_state(0, self.opt_step)
+        if self._scalars is None or self._scalars.shape[0] < n_inner:
+            self._scalars = torch.zeros(n_inner, _lib.NUM_SCALARS, device=self.device)
+        if self._pred is None or self._pred.numel() < R:
+            self._pred = torch.full((max(R, B * 8),), -1, dtype=torch.int32, device=self.device)
+        scalars, pred = self._scalars, self._pred
         for s in range(n_inner):
-            eng.fwd_bwd(self.patch, s, fe_mode, loss, self.grad, scalars[s], pred)
-            g = self.grad
-            if accumulate is not None:        # TMA / UPA with accumulate_steps > 1: grads pile up until a stepping iteration
-                accumulate.add_(self.grad)
-                g = accumulate
-            if self.world_size > 1:           # DDP reducer: all-reduce of patch.grad on every backward (UADA_ddp.py:206)
-                torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM)
+            eng.attack_step(self.patch, self.m, self.v, self.grad, scalars, pred, fe_mode, loss, lr, opt_kind=opt_kind,
+                            clip_l1=clip_l1, accumulate=accumulate, comm=comm, do_update=do_step)
             if do_step:
                 self.opt_step += 1
-                eng.patch_update(self.patch, g, self.m, self.v, self.opt_step, lr, kind=opt_kind,
-                                 grad_scale=1.0 / self.world_size, clip_l1=clip_l1, scalars=scalars[s])
-                if accumulate is not None:
-                    accumulate.zero_()
-        return scalars.cpu(), self._full_vocab_pred(eng, R, pred).cpu()
+        if after_launch is not None:
+            after_launch()
+        return scalars[:n_inner].cpu(), self._full_vocab_pred(eng, R, pred[:R]).cpu()
 
     def _full_vocab_pred(self, eng, R, pred):
         """The reference's metrics take ``action_preds = logits.argmax(dim=2)`` over the FULL vocabulary (UADA.py:168,229;
@@ -220,8 +242,9 @@ class AttackEngineHost:
         B, T = batch["input_ids"].shape
         eng = self.ensure_engine(B, T)
         R = eng.set_batch(obs, batch["input_ids"], batch["attention_mask"], batch["labels"])
-        xy, theta = draw_placements(B, (self.cfg.img, self.cfg.img), tuple(self.patch.shape[1:]), fe_mode == _lib.FE_WARP, 1)
-        eng.set_placements(xy, theta)
+        if fe_mode != _lib.FE_NONE:   # im_process() pastes nothing and draws nothing (appply_random_transform.py:190-197)
+            xy, theta = draw_placements(B, (self.cfg.img, self.cfg.img), tuple(self.patch.shape[1:]), fe_mode == _lib.FE_WARP, 1)
+            eng.set_placements(xy, theta)
         scalars = torch.zeros(_lib.NUM_SCALARS, device=self.device)
         pred = torch.full((R,), -1, dtype=torch.int32, device=self.device)
         eng.fwd_bwd(self.patch, 0, fe_mode, loss, self.grad, scalars, pred, forward_only=True)
@@ -270,7 +293,7 @@ class _AttackerBase(object):
         os.makedirs(d, exist_ok=True)
         torch.save(patch.detach().cpu(), os.path.join(d, "patch.pt"))     # fp32 [3,h,w] CPU tensor, as the reference
         if outer_iter is not None:   # restart state next to it (not in the reference's run-dir format; ignored by its consumers)
-            torch.save(self.host.state_dict(outer_iter, sched_step), os.path.join(d, self.STATE_FILE))
+            torch.save(self.host.state_dict(outer_iter, sched_step, getattr(self, "_acc", None)), os.path.join(d, self.STATE_FILE))
         return d
 
     def _dump_val_images(self, d, extra=None):
@@ -299,8 +322,8 @@ class _AttackerBase(object):
         path = self.resume
         if os.path.isdir(path):
             path = os.path.join(path, self.STATE_FILE)
-        st = torch.load(path, map_location="cpu", weights_only=False)
-        return self.host.load_state_dict(st)
+        st = torch.load(path, map_location="cpu", weights_only=True)
+        return self.host.load_state_dict(st, getattr(self, "_acc", None))
 
     def _dump(self, **lists):
         os.makedirs(self.save_dir, exist_ok=True)
@@ -395,29 +418,28 @@ class _AttackerBase(object):
         out["pixel_values"] = [pv[i] for i in chosen] if isinstance(pv, (list, tuple)) else pv[chosen]
         return out
 
-    def _open(self, loader):
-        """Iterator over ``loader``: a background prefetcher (default) or the plain iterator (``VLA_PREFETCH=0``)."""
+    def _open(self, loader, restart=True):
+        """``LookaheadLoader`` over ``loader`` (``VLA_PREFETCH=0``: no lookahead, batches are fetched when needed)."""
         if loader is None:
             return None
-        if os.environ.get("VLA_PREFETCH", "1") != "0":
-            return BatchPrefetcher(loader, self.host.cfg.img)
-        return iter(loader)
+        return LookaheadLoader(loader, self.host.cfg.img, restart=restart, lookahead=os.environ.get("VLA_PREFETCH", "1") != "0")
 
     @staticmethod
     def _close(*iterators):
         for it in iterators:
-            if isinstance(it, BatchPrefetcher):
+            if isinstance(it, LookaheadLoader):
                 it.close()
 
     @staticmethod
     def _next(iterator, loader):
-        if isinstance(iterator, BatchPrefetcher):
-            return iterator.next(), iterator
-        try:
-            return next(iterator), iterator
-        except StopIteration:
-            iterator = iter(loader)
-            return next(iterator), iterator
+        return iterator.next(), iterator
+
+    def _lookahead(self, i, train_it, has_val=True):
+        """Host work to overlap with the device's inner loop: fetch the next training batch -- except on iterations that end
+        with a validation pass, whose ``next()`` calls on the validation loader come first in the reference's RNG order."""
+        if i % self.val_every == 0 and has_val:
+            return None
+        return train_it.prefetch
 
 
 class UADAAttacker(_AttackerBase):
@@ -454,7 +476,8 @@ class UADAAttacker(_AttackerBase):
                 data = self.filter_train(data)
             data["labels"] = self.mask_labels(data["labels"].clone(), maskidx)
             cur_lr = lr * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else lr
-            scalars, pred = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind)
+            scalars, pred = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind,
+                                             after_launch=self._lookahead(i, train_it, val_dataloader is not None))
             self.train_CE_loss += scalars[:, _lib.S_CE].tolist()
             self.train_MSE_distance_loss += scalars[:, _lib.S_LOSS].tolist()
             self.train_UAD += scalars[:, _lib.S_UAD].tolist()
@@ -556,8 +579,8 @@ class UPAAttacker(_AttackerBase):
         fe_mode = _lib.FE_WARP if geometry else _lib.FE_PASTE20
         opt_kind = _lib.OPT_ADAMW if self.optimizer == "adamW" else _lib.OPT_PGD
         total = int(num_iter / accumulate_steps)
+        acc = self._acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
         start_iter, sched_step = self._maybe_resume()
-        acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
         train_it = self._open(train_dataloader)
         for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
@@ -573,7 +596,8 @@ class UPAAttacker(_AttackerBase):
             stepping = (i + 1) % accumulate_steps == 0
             cur_lr = lr * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else lr
             scalars, _ = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind,
-                                          clip_l1=1e-3 if self.optimizer == "adamW" else 0.0, do_step=stepping, accumulate=acc)
+                                          clip_l1=1e-3 if self.optimizer == "adamW" else 0.0, do_step=stepping, accumulate=acc,
+                                          after_launch=self._lookahead(i, train_it, val_dataloader is not None and reverse_direction and not guide))
             if self.optimizer == "adamW" and stepping:
                 sched_step += 1
             log = {"TRAIN_attack_loss(CE)": scalars[-1, _lib.S_LOSS].item(),
@@ -658,8 +682,8 @@ class TMAAttacker(_AttackerBase):
         fe_mode = _lib.FE_WARP if geometry else _lib.FE_FIX          # paste_patch_fix when no geometry (TMA.py:133-135)
         opt_kind = _lib.OPT_ADAMW if self.optimizer == "adamW" else _lib.OPT_PGD
         total = int(num_iter / accumulate_steps)
+        acc = self._acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
         start_iter, sched_step = self._maybe_resume()
-        acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
         train_it = self._open(train_dataloader)
         for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
@@ -669,7 +693,8 @@ class TMAAttacker(_AttackerBase):
             data["labels"] = lab.tma_labels(data["labels"], target)
             stepping = (i + 1) % accumulate_steps == 0
             cur_lr = alpha * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else alpha
-            scalars, pred = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind, do_step=stepping, accumulate=acc)
+            scalars, pred = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind, do_step=stepping, accumulate=acc,
+                                             after_launch=self._lookahead(i, train_it, val_dataloader is not None))
             if self.optimizer == "adamW" and stepping:
                 sched_step += 1
             # logging only: the reference averages this metric over the inner steps (TMA.py:161,177); reading the predictions of
@@ -846,17 +871,18 @@ class UADADDPAttacker(_AttackerBase):
         loss = LossSpec(_lib.LOSS_UADA_DDP, mse_weight=float(self.MSE_weights))
         fe_mode = _lib.FE_WARP if self.geometry else _lib.FE_PASTE20
         logs = []
-        prefetch = os.environ.get("VLA_PREFETCH", "1") != "0"
-        train_it = BatchPrefetcher(train_dataloader, h.cfg.img, restart=False) if prefetch else iter(train_dataloader)
+        train_it = self._open(train_dataloader, restart=False)
+        val_dataloader = val_dataloader or (self.dataloaders[1] if self.dataloaders and len(self.dataloaders) > 1 else None)
         for i in range(start_iter, int(self.num_iter)):
             try:                                   # ``for i, data in enumerate(loader)`` of UADA_ddp.py:176: ends with the loader
-                data = train_it.next() if prefetch else next(train_it)
+                data = train_it.next()
             except StopIteration:
                 break
             data = dict(data)
             data["labels"] = self.mask_labels(data["labels"].clone(), self.maskidx)
             cur_lr = self.lr * cosine_with_warmup(i, self.warmup, int(self.num_iter))
-            scalars, _ = h.run_inner_loop(data, self.innerLoop, fe_mode, loss, cur_lr, _lib.OPT_ADAMW)
+            scalars, _ = h.run_inner_loop(data, self.innerLoop, fe_mode, loss, cur_lr, _lib.OPT_ADAMW,
+                                          after_launch=self._lookahead(i, train_it, val_dataloader is not None))
             # four scalar all-reduces of the reference (UADA_ddp.py:214-221) packed into one
             last = scalars[-1]
             pack = torch.tensor([last[_lib.S_CE], last[_lib.S_LOSS], last[_lib.S_UAD], last[_lib.S_GRAD_MEAN]], device=h.device)
@@ -869,7 +895,6 @@ class UADADDPAttacker(_AttackerBase):
                    "TRAIN_UAD": pack[2].item(), "TRAIN_patch_gradient": pack[3].item(), "TRAIN_LR": cur_lr}
             logs.append(log)
             if i % self.val_every == 0:
-                val_dataloader = val_dataloader or (self.dataloaders[1] if self.dataloaders and len(self.dataloaders) > 1 else None)
                 if val_dataloader is not None:
                     self._validate(i, rank, world_size, val_dataloader, fe_mode, loss)
                 elif rank == 0 and self.save_dir:

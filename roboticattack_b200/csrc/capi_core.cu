@@ -85,6 +85,35 @@ int vla_gemm_bf16_tn(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   e.out_f32 = out_f32;
   return gemm_bf16_tn(CBF(A), lda, CBF(W), ldw, out, ldc, M, N, K, e, S(stream));
 }
+int vla_gemm_bf16_tn_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
+                        const vla_gemm_epilogue* ep, void* stream) {
+  VLA_REQUIRE(ep != nullptr, "vla_gemm_bf16_tn_ex: null epilogue");
+  GemmEpilogue e;
+  e.bias = CBF(ep->bias);
+  e.gamma = CBF(ep->gamma);
+  e.resid = CBF(ep->resid);
+  e.ldr = ep->ldr;
+  e.act = ep->act;
+  e.preact_out = BF(ep->preact_out);
+  e.out_f32 = ep->out_f32;
+  e.out_group = ep->out_group;
+  e.out_stride = ep->out_stride;
+  e.out_offset = ep->out_offset;
+  e.resid_mod = ep->resid_mod;
+  e.aux_mode = ep->aux_mode;
+  e.aux = CBF(ep->aux);
+  e.ldaux = ep->ldaux;
+  e.pair_mode = ep->pair_mode;
+  e.rope_cos = ep->rope_cos;
+  e.rope_sin = ep->rope_sin;
+  e.rope_L = ep->rope_L;
+  e.rope_cols = ep->rope_cols;
+  e.act_out = BF(ep->act_out);
+  e.ld_act = ep->ld_act;
+  e.delta_out = ep->delta_out;
+  e.delta_L = ep->delta_L;
+  return gemm_bf16_tn(CBF(A), lda, CBF(W), ldw, out, ldc, M, N, K, e, S(stream));
+}
 int vla_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t M, int d,
                       float eps, void* stream) {
   return layernorm_fwd(CBF(x), CBF(w), CBF(b), BF(y), mean, rstd, M, d, eps, S(stream));

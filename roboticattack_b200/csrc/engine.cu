@@ -115,6 +115,23 @@ struct vla_engine {
        *ll_dgu = nullptr, *ll_dnorm = nullptr, *ll_dxm = nullptr, *ll_dattn = nullptr;
   float* ll_rstd2 = nullptr;
   FrontendNorm nrm;
+  // ---- vla_attack_step: device-resident step state + the CUDA graphs of whole attack iterations ----
+  StepState* dstate = nullptr;      // device
+  int* xy_cur = nullptr;            // placement of the running step (copied from xy / theta by step_begin)
+  float* theta_cur = nullptr;
+  float* scal_cur = nullptr;        // scalar record of the running step
+  int h_place = 0, h_adam = 0;      // host mirror of dstate (advanced with every vla_attack_step)
+  float h_lr = -1.f;                // learning rate currently in dstate->lr
+  float* lr_ring = nullptr;         // pinned staging for learning-rate uploads
+  int lr_ring_pos = 0;
+  cudaStream_t cap = nullptr;       // capture stream (the caller's stream may be the legacy default stream, which cannot capture)
+  struct StepGraph {
+    std::vector<uint8_t> key;
+    cudaGraphExec_t exec = nullptr;
+    int kernel_nodes = 0, calls = 0;
+  };
+  std::vector<StepGraph> graphs;
+  int last_kernel_nodes = 0;
 };
 
 namespace {
@@ -293,6 +310,10 @@ size_t plan(vla_engine* e, uint8_t* base, int B, int T) {
   e->theta = bp.take<float>(static_cast<size_t>(MAX_PLACEMENTS) * 6);
   e->rope_cos = bp.take<float>(static_cast<size_t>(L) * (h / c.llm_heads / 2));
   e->rope_sin = bp.take<float>(static_cast<size_t>(L) * (h / c.llm_heads / 2));
+  e->dstate = bp.take<StepState>(1);
+  e->xy_cur = bp.take<int>(static_cast<size_t>(B) * 2);
+  e->theta_cur = bp.take<float>(static_cast<size_t>(B) * 6);
+  e->scal_cur = bp.take<float>(LOSS_NUM_SCALARS);
   e->px = bp.take<bf16>(static_cast<size_t>(B) * 6 * H * H);
   e->dpx = bp.take<bf16>(static_cast<size_t>(B) * 6 * H * H);
   size_t max_md = 0, max_wide = 0, max_qkv = 0, max_lse = 0;
@@ -550,6 +571,10 @@ extern "C" void vla_engine_destroy(vla_engine* e) {
     cudaEventDestroy(e->ev_fork);
     cudaEventDestroy(e->ev_join);
   }
+  for (auto& g : e->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (e->cap) cudaStreamDestroy(e->cap);
+  if (e->lr_ring) cudaFreeHost(e->lr_ring);
   delete e;
 }
 
@@ -596,6 +621,13 @@ extern "C" int vla_engine_set_buffers(vla_engine* e, void* weight_arena, size_t 
   e->batch_set = false;
   e->rope_set = false;
   e->n_place = 0;
+  for (auto& g : e->graphs)   // the plan moved: recorded graphs hold stale pointers / shapes
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+  e->h_place = e->h_adam = 0;
+  e->h_lr = -1.f;
+  VLA_CHECK_CUDA(cudaMemset(e->dstate, 0, sizeof(StepState)));
+  VLA_CHECK_CUDA(cudaMemset(e->scal_cur, 0, sizeof(float) * LOSS_NUM_SCALARS));
   return resolve_weights(e);
 }
 
@@ -768,28 +800,43 @@ extern "C" int vla_engine_set_single_stream(vla_engine* e, int on) {
   return 0;
 }
 
+namespace {
+bool phase_timing_on() {
+  static const bool on = getenv("VLA_PHASE_TIMING") && atoi(getenv("VLA_PHASE_TIMING")) != 0;
+  return on;
+}
+int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* xy, const float* th, int fe_mode,
+                 const vla_loss_params* lp_c, float* dpatch, float* scalars, int* pred_ids, int flags, cudaStream_t s);
+}  // namespace
+
 extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, int step_idx, int fe_mode,
                            const vla_loss_params* lp_c, float* dpatch, float* scalars, int* pred_ids, int flags,
                            void* stream) {
   VLA_REQUIRE(e && e->weights_resolved, "vla_fwd_bwd: engine not initialised");
   VLA_REQUIRE(e->batch_set, "vla_fwd_bwd: call vla_engine_set_batch first");
   VLA_REQUIRE(e->rope_set, "vla_fwd_bwd: call vla_engine_set_rope first");
+  VLA_REQUIRE(patch && lp_c && dpatch && scalars && pred_ids, "vla_fwd_bwd: null argument");
   VLA_REQUIRE(fe_mode == FE_MODE_NONE || (step_idx >= 0 && step_idx < e->n_place),
               "vla_fwd_bwd: placement %d not uploaded (have %d)", step_idx, e->n_place);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int* xy = e->xy + static_cast<size_t>(step_idx < 0 ? 0 : step_idx) * e->B * 2;
+  const float* th = e->theta + static_cast<size_t>(step_idx < 0 ? 0 : step_idx) * e->B * 6;
+  return fwd_bwd_impl(e, patch, ph, pw, xy, th, fe_mode, lp_c, dpatch, scalars, pred_ids, flags, static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* xy, const float* th, int fe_mode,
+                 const vla_loss_params* lp_c, float* dpatch, float* scalars, int* pred_ids, int flags, cudaStream_t s) {
   const vla_config& c = e->cfg;
   const int B = e->B, T = e->T, L = e->L, P = e->np, H = c.img;
   const int h = c.llm_hidden, f = c.llm_ffn, V = c.vocab, NH = c.llm_heads, hd = h / NH;
   const int64_t ML = static_cast<int64_t>(B) * L;
   const int64_t MP = static_cast<int64_t>(B) * P;
   const int vd = c.dino_dim + c.sig_dim, phd = 4 * vd;
-  const int* xy = e->xy + static_cast<size_t>(step_idx < 0 ? 0 : step_idx) * B * 2;
-  const float* th = e->theta + static_cast<size_t>(step_idx < 0 ? 0 : step_idx) * B * 6;
   LossParams lp{lp_c->kind, lp_c->mse_weight, lp_c->alpha, lp_c->belta, lp_c->ce_scale};
   GemmEpilogue plain;
 
   // VLA_PHASE_TIMING=1 (diagnostics): events at the phase boundaries, printed after a synchronise
-  static const bool phase_timing = getenv("VLA_PHASE_TIMING") && atoi(getenv("VLA_PHASE_TIMING")) != 0;
+  const bool phase_timing = phase_timing_on();
   static cudaEvent_t pev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   auto mark = [&](int i) {
     if (!phase_timing) return;
@@ -1050,6 +1097,164 @@ extern "C" int vla_fwd_bwd(vla_engine* e, const float* patch, int ph, int pw, in
     fprintf(stderr, "[phase ms] front+vit_fwd %.3f | projector+llm_fwd+loss %.3f | llm_bwd %.3f | projector+vit_bwd %.3f | tail %.3f\n", t[0],
             t[1], t[2], t[3], t[4]);
   }
+  return 0;
+}
+}  // namespace
+
+// =================================================================================================================
+// vla_attack_step: the whole inner-loop body as one call / one CUDA graph (see include/vla_b200.h)
+// =================================================================================================================
+static long long g_graph_replays = 0;
+extern "C" long long vla_graph_replays(void) { return g_graph_replays; }
+extern "C" int vla_graph_kernel_nodes(const vla_engine* e) { return e ? e->last_kernel_nodes : 0; }
+
+extern "C" int vla_engine_set_step_state(vla_engine* e, int placement_index, int adam_step, void* stream) {
+  VLA_REQUIRE(e && e->ws, "vla_engine_set_step_state: call vla_engine_set_buffers first");
+  VLA_REQUIRE(placement_index >= 0 && adam_step >= 0, "vla_engine_set_step_state: negative counter");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int v[2] = {placement_index, adam_step};   // passed by value into the copy below (cudaMemcpyAsync from pageable memory stages it)
+  VLA_CHECK_CUDA(cudaMemcpyAsync(e->dstate, v, sizeof(v), cudaMemcpyHostToDevice, s));
+  e->h_place = placement_index;
+  e->h_adam = adam_step;
+  return 0;
+}
+
+extern "C" int vla_engine_get_step_state(const vla_engine* e, int* placement_index, int* adam_step) {
+  VLA_REQUIRE(e != nullptr, "vla_engine_get_step_state: null engine");
+  if (placement_index) *placement_index = e->h_place;
+  if (adam_step) *adam_step = e->h_adam;
+  return 0;
+}
+
+namespace {
+
+// The launch sequence of one attack iteration on stream s (eager or being captured).
+int attack_step_sequence(vla_engine* e, float* patch, float* m, float* v, float* dpatch, float* acc, const vla_step_params* sp,
+                         vla_comm* comm, float* scal_hist, int* pred_ids, cudaStream_t s) {
+  const int n = 3 * sp->ph * sp->pw;
+  const bool update = !(sp->flags & VLA_STEP_NO_UPDATE);
+  CK(step_begin(e->dstate, e->xy, e->theta, e->xy_cur, e->theta_cur, e->B, e->n_place > 0 ? e->n_place : 1, e->scal_cur, s));
+  CK(fwd_bwd_impl(e, patch, sp->ph, sp->pw, e->xy_cur, e->theta_cur, sp->fe_mode, &sp->loss, dpatch, e->scal_cur, pred_ids, 0, s));
+  float* g = dpatch;
+  if (acc) {   // TMA / UPA with accumulate_steps > 1: gradients pile up over outer iterations (TMA.py:162-170)
+    CK(accumulate_f32(acc, dpatch, n, s));
+    g = acc;
+  }
+  const int world = vla_comm_world(comm);
+  if (comm && world > 1) CK(vla_allreduce_patch_grad(comm, g, n, s));   // DDP reducer (UADA_ddp.py:206)
+  if (update)
+    CK(patch_update_dev(patch, g, m, v, n, e->dstate, sp->beta1, sp->beta2, sp->eps, sp->opt_kind, 1.f / static_cast<float>(world),
+                        sp->clip_l1, e->scal_cur, acc, s));
+  CK(step_end(e->dstate, e->scal_cur, scal_hist, update ? 1 : 0, s));
+  return 0;
+}
+
+struct StepKey {   // everything the recorded launch sequence depends on
+  int B, T, R, n_place;
+  vla_step_params sp;
+  const void *patch, *m, *v, *dpatch, *acc, *comm, *hist, *pred;
+  int single_stream, attn_impl, pad;
+};
+
+}  // namespace
+
+extern "C" int vla_attack_step(vla_engine* e, float* patch, float* exp_avg, float* exp_avg_sq, float* dpatch, float* accumulate,
+                               const vla_step_params* sp, vla_comm* comm, float* scalars_hist, int* pred_ids, void* stream) {
+  VLA_REQUIRE(e && e->weights_resolved, "vla_attack_step: engine not initialised");
+  VLA_REQUIRE(e->batch_set, "vla_attack_step: call vla_engine_set_batch first");
+  VLA_REQUIRE(e->rope_set, "vla_attack_step: call vla_engine_set_rope first");
+  VLA_REQUIRE(patch && dpatch && sp && pred_ids, "vla_attack_step: null argument");
+  VLA_REQUIRE(sp->opt_kind == OPT_ADAMW || sp->opt_kind == OPT_PGD, "vla_attack_step: bad optimiser kind %d", sp->opt_kind);
+  VLA_REQUIRE(sp->opt_kind != OPT_ADAMW || (exp_avg && exp_avg_sq) || (sp->flags & VLA_STEP_NO_UPDATE),
+              "vla_attack_step: AdamW needs the moment buffers");
+  VLA_REQUIRE(sp->fe_mode == FE_MODE_NONE || e->h_place < e->n_place,
+              "vla_attack_step: placement %d not uploaded (have %d): call vla_engine_set_placements / vla_engine_set_step_state",
+              e->h_place, e->n_place);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // learning rate -> device state (changes once per outer iteration: LambdaLR is stepped outside the inner loop, UADA.py:162-164)
+  if (sp->lr != e->h_lr) {
+    if (!e->lr_ring) VLA_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->lr_ring), 64 * sizeof(float), cudaHostAllocDefault));
+    float* slot = e->lr_ring + (e->lr_ring_pos++ & 63);
+    *slot = sp->lr;
+    VLA_CHECK_CUDA(cudaMemcpyAsync(&e->dstate->lr, slot, sizeof(float), cudaMemcpyHostToDevice, s));
+    e->h_lr = sp->lr;
+  }
+  const bool update = !(sp->flags & VLA_STEP_NO_UPDATE);
+  static const bool graphs_off = getenv("VLA_STEP_GRAPH") && atoi(getenv("VLA_STEP_GRAPH")) == 0;
+  const bool eager = (sp->flags & VLA_STEP_NO_GRAPH) || graphs_off || phase_timing_on() || vla_gemm_profiling();
+  int rc = 0;
+  if (eager) {
+    rc = attack_step_sequence(e, patch, exp_avg, exp_avg_sq, dpatch, accumulate, sp, comm, scalars_hist, pred_ids, s);
+  } else {
+    StepKey k;
+    memset(&k, 0, sizeof(k));
+    k.B = e->B; k.T = e->T; k.R = e->R; k.n_place = e->n_place;
+    k.sp = *sp;
+    k.sp.lr = 0.f;   // read from device memory
+    k.patch = patch; k.m = exp_avg; k.v = exp_avg_sq; k.dpatch = dpatch; k.acc = accumulate; k.comm = comm; k.hist = scalars_hist;
+    k.pred = pred_ids;
+    k.single_stream = e->single_stream ? 1 : 0;
+    k.attn_impl = g_attn_impl;
+    vla_engine::StepGraph* g = nullptr;
+    for (auto& cand : e->graphs)
+      if (cand.key.size() == sizeof(k) && memcmp(cand.key.data(), &k, sizeof(k)) == 0) g = &cand;
+    if (!g) {
+      if (e->graphs.size() >= 16) {   // bounded cache: drop the oldest recording
+        if (e->graphs.front().exec) cudaGraphExecDestroy(e->graphs.front().exec);
+        e->graphs.erase(e->graphs.begin());
+      }
+      e->graphs.emplace_back();
+      g = &e->graphs.back();
+      g->key.assign(reinterpret_cast<uint8_t*>(&k), reinterpret_cast<uint8_t*>(&k) + sizeof(k));
+    }
+    g->calls++;
+    if (g->calls == 1) {
+      // first sight: eager (the GEMM autotuner times its variants on first use of a shape, which cannot happen inside a capture)
+      rc = attack_step_sequence(e, patch, exp_avg, exp_avg_sq, dpatch, accumulate, sp, comm, scalars_hist, pred_ids, s);
+    } else {
+      if (!g->exec) {
+        if (!e->cap) VLA_CHECK_CUDA(cudaStreamCreateWithFlags(&e->cap, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        VLA_CHECK_CUDA(cudaStreamBeginCapture(e->cap, cudaStreamCaptureModeThreadLocal));
+        const long long launches0 = g_vla_launch_count;
+        rc = attack_step_sequence(e, patch, exp_avg, exp_avg_sq, dpatch, accumulate, sp, comm, scalars_hist, pred_ids, e->cap);
+        const cudaError_t ce = cudaStreamEndCapture(e->cap, &graph);
+        g_vla_launch_count = launches0;   // nothing ran: the replays are counted below
+        if (rc != 0 || ce != cudaSuccess || !graph) {
+          if (graph) cudaGraphDestroy(graph);
+          if (rc == 0) vla_set_error("vla_attack_step: stream capture failed: %s", cudaGetErrorString(ce));
+          cudaGetLastError();
+          g->calls = 0;
+          return rc ? rc : 1;
+        }
+        size_t nn = 0;
+        VLA_CHECK_CUDA(cudaGraphGetNodes(graph, nullptr, &nn));
+        std::vector<cudaGraphNode_t> nodes(nn);
+        VLA_CHECK_CUDA(cudaGraphGetNodes(graph, nodes.data(), &nn));
+        int kn = 0;
+        for (size_t i = 0; i < nn; ++i) {
+          cudaGraphNodeType ty;
+          if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) ++kn;
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+          vla_set_error("vla_attack_step: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+          g->exec = nullptr;
+          g->calls = 0;
+          return 1;
+        }
+        g->kernel_nodes = kn;
+      }
+      VLA_CHECK_CUDA(cudaGraphLaunch(g->exec, s));
+      e->last_kernel_nodes = g->kernel_nodes;
+      g_vla_launch_count += g->kernel_nodes;   // the recorded kernels run on every replay
+      ++g_graph_replays;
+    }
+  }
+  if (rc) return rc;
+  e->h_place++;
+  if (update) e->h_adam++;
   return 0;
 }
 

@@ -64,3 +64,6 @@ extern int g_vla_sm_limit;
 
 // number of GEMM kernel launches since process start (for bench.py's gpu_launches accounting)
 extern long long g_vla_launch_count;
+
+// true while vla_profile_gemm_begin/_end bracket per-launch event timing (such steps must not be graph-captured)
+bool vla_gemm_profiling();

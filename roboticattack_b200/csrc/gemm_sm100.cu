@@ -36,6 +36,8 @@ struct GemmProf {
 } g_prof;
 }  // namespace
 
+bool vla_gemm_profiling() { return g_prof.on; }
+
 extern "C" int vla_profile_gemm_begin(void) {
   g_prof.on = true;
   g_prof.used = 0;

@@ -114,3 +114,19 @@ enum { OPT_ADAMW = 0, OPT_PGD = 1 };
 // clip_grad_norm_(max_norm=clip_l1, norm_type=1) (UPA.py:157); then the update and clamp(0,1).
 int patch_update(float* patch, const float* grad, float* m, float* v, int n, int step, float lr, float beta1,
                  float beta2, float eps, int kind, float grad_scale, float clip_l1, float* scalars, cudaStream_t s);
+
+// ---- device-resident step state of vla_attack_step (patch_update.cu) --------------------------------------
+struct StepState {
+  int place;     // index of the placement (and scalar-history row) the next attack step uses
+  int adam_t;    // optimiser steps taken so far (transformers.AdamW state["step"])
+  float lr;      // learning rate of the current outer iteration (LambdaLR value)
+  int pad;
+};
+int patch_update_dev(float* patch, const float* grad, float* m, float* v, int n, const StepState* st, float beta1, float beta2,
+                     float eps, int kind, float grad_scale, float clip_l1, float* scalars, float* zero_after, cudaStream_t s);
+// copies placement st->place of the uploaded set into the "current placement" buffers the front-end kernels read
+int step_begin(const StepState* st, const int* xy_all, const float* th_all, int* xy_cur, float* th_cur, int B, int n_place,
+               float* scal_cur, cudaStream_t s);
+// scal_hist[st->place] = scal_cur; st->place += 1; st->adam_t += adam_inc
+int step_end(StepState* st, const float* scal_cur, float* scal_hist, int adam_inc, cudaStream_t s);
+int accumulate_f32(float* acc, const float* g, int n, cudaStream_t s);

@@ -54,6 +54,26 @@ def _c_config(cfg: OpenVLAConfig) -> _lib.Config:
     return c
 
 
+class NcclComm:
+    """Owner of a ``vla_comm`` handle."""
+
+    def __init__(self, lib, handle, world):
+        self._lib, self.handle, self.world = lib, handle, world
+
+    def all_reduce_(self, t):
+        """In-place sum over ranks of a float32 device tensor on the current stream (``vla_allreduce_patch_grad``)."""
+        assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
+        _lib.check(self._lib.vla_allreduce_patch_grad(self.handle, _lib.ptr(t), t.numel(), _lib.cur_stream()), "vla_allreduce_patch_grad")
+
+    def close(self):
+        if self.handle:
+            self._lib.vla_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        self.close()
+
+
 class VLAEngine:
     """One engine per process / GPU.  ``batch`` is the per-GPU batch, ``text_len`` the padded text length T."""
 
@@ -174,11 +194,58 @@ class VLAEngine:
                                               step, lr, betas[0], betas[1], eps, kind, grad_scale, clip_l1,
                                               _lib.ptr(scalars), _lib.cur_stream()), "vla_patch_update")
 
+    # ---- whole attack iteration (one C-ABI call, one CUDA graph launch after the first two calls) ----------
+    def set_step_state(self, placement_index: int, adam_step: int):
+        """Device-side counters of ``attack_step``: which uploaded placement the next step uses, and optimiser steps so far."""
+        _lib.check(self._lib.vla_engine_set_step_state(self._h, int(placement_index), int(adam_step), _lib.cur_stream()),
+                   "vla_engine_set_step_state")
+
+    def get_step_state(self):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        _lib.check(self._lib.vla_engine_get_step_state(self._h, byref(a), byref(b)), "vla_engine_get_step_state")
+        return a.value, b.value
+
+    def make_comm(self, rank: int, world: int):
+        """NCCL communicator for the patch-gradient all-reduce (``vla_comm``); the 128-byte id travels over the already
+        initialised ``torch.distributed`` group (host-side plumbing only).  ``None`` for a single process."""
+        if world <= 1:
+            return None
+        import torch.distributed as dist
+        idbuf = (ctypes.c_uint8 * _lib.COMM_ID_BYTES)()
+        if rank == 0:
+            _lib.check(self._lib.vla_comm_unique_id(idbuf), "vla_comm_unique_id")
+        box = [bytes(idbuf)]
+        dist.broadcast_object_list(box, src=0)
+        idbuf = (ctypes.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(box[0])
+        h = c_void_p()
+        torch.cuda.set_device(self.device)
+        _lib.check(self._lib.vla_comm_create(idbuf, rank, world, byref(h)), "vla_comm_create")
+        return NcclComm(self._lib, h, world)
+
+    def attack_step(self, patch, m, v, dpatch, scalars_hist, pred_ids, fe_mode, loss: LossSpec, lr, opt_kind=_lib.OPT_ADAMW,
+                    clip_l1=0.0, accumulate=None, comm=None, do_update=True, graph=True, betas=(0.9, 0.999), eps=1e-6):
+        """front end -> model -> loss -> backward -> [accumulate] -> [all-reduce] -> update -> clamp, for the placement the
+        device-side counter points at; the step's scalar record lands in ``scalars_hist[counter]``."""
+        assert self._weights_ok, "weights not loaded"
+        sp = _lib.StepParams(patch.shape[1], patch.shape[2], fe_mode, loss.to_c(), opt_kind, float(lr), betas[0], betas[1], eps,
+                             float(clip_l1), (0 if graph else _lib.STEP_NO_GRAPH) | (0 if do_update else _lib.STEP_NO_UPDATE))
+        _lib.check(self._lib.vla_attack_step(self._h, _lib.ptr(patch), _lib.ptr(m), _lib.ptr(v), _lib.ptr(dpatch),
+                                             _lib.ptr(accumulate), byref(sp), comm.handle if comm is not None else None,
+                                             _lib.ptr(scalars_hist), _lib.ptr(pred_ids), _lib.cur_stream()), "vla_attack_step")
+
+    @property
+    def graph_kernel_nodes(self) -> int:
+        return self._lib.vla_graph_kernel_nodes(self._h)
+
     def set_single_stream(self, on: bool):
         """True: both vision towers on the caller's stream (clean per-kernel timing); False (default): two streams."""
         _lib.check(self._lib.vla_engine_set_single_stream(self._h, int(on)), "vla_engine_set_single_stream")
 
-    def tap(self, what: str, dtype=torch.bfloat16, max_elems=1 << 28):
+    def tap(self, what: str, dtype=torch.bfloat16, max_elems=None):
+        if max_elems is None:   # largest tappable activation: the residual stream / the 6-channel image / the supervised logits
+            max_elems = max(self.B * self.L * self.cfg.llm.hidden, self.B * 6 * self.cfg.img ** 2,
+                            max(self.num_supervised, 1) * self.cfg.llm.vocab,
+                            self.B * max(self.cfg.dino.tokens * self.cfg.dino.dim, self.cfg.siglip.tokens * self.cfg.siglip.dim))
         buf = torch.empty(max_elems, dtype=dtype, device=self.device)
         n = self._lib.vla_engine_debug_tap(self._h, what.encode(), _lib.ptr(buf), buf.numel() * buf.element_size(),
                                            _lib.cur_stream())

@@ -10,11 +10,22 @@ from roboticattack_b200 import _lib
 from roboticattack_b200.config import NORM_MEAN, NORM_STD
 
 
+class GlooComm:
+    """Stand-in for the NCCL communicator on CPU: sum over the ranks of the default (gloo) process group."""
+
+    def __init__(self, world):
+        self.world = world
+
+    def all_reduce_(self, t):
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+
+
 class OracleEngine:
     def __init__(self, cfg, batch, text_len, device="cpu", dtype=torch.float32):
         self.cfg, self.B, self.T, self.dtype = cfg, batch, text_len, dtype
         self.sd = None
         self.num_supervised = 0
+        self._place, self._adam = 0, 0
 
     def load_state_dict(self, sd, strict=True):
         self.sd = {k: v.to(self.dtype) for k, v in sd.items()}
@@ -65,7 +76,38 @@ class OracleEngine:
             scalars[_lib.S_AUX1] = aux1
             scalars[_lib.S_UAD] = uad
 
-    def tap(self, what, dtype=torch.float32, max_elems=1 << 28):
+    # ---- the whole attack iteration, same contract as VLAEngine.attack_step (vla_attack_step) ----
+    def set_step_state(self, placement_index, adam_step):
+        self._place, self._adam = int(placement_index), int(adam_step)
+
+    def get_step_state(self):
+        return self._place, self._adam
+
+    def make_comm(self, rank, world):
+        return GlooComm(world) if world > 1 else None
+
+    def attack_step(self, patch, m, v, dpatch, scalars_hist, pred_ids, fe_mode, loss, lr, opt_kind=_lib.OPT_ADAMW, clip_l1=0.0,
+                    accumulate=None, comm=None, do_update=True, graph=True, betas=(0.9, 0.999), eps=1e-6):
+        sc = scalars_hist[self._place]
+        sc.zero_()
+        self.fwd_bwd(patch, self._place, fe_mode, loss, dpatch, sc, pred_ids[:self.num_supervised])
+        g = dpatch
+        if accumulate is not None:
+            accumulate.add_(dpatch)
+            g = accumulate
+        world = 1
+        if comm is not None:
+            comm.all_reduce_(g)
+            world = comm.world
+        if do_update:
+            self.patch_update(patch, g, m, v, self._adam + 1, lr, kind=opt_kind, grad_scale=1.0 / world, clip_l1=clip_l1, scalars=sc,
+                              betas=betas, eps=eps)
+            self._adam += 1
+            if accumulate is not None:
+                accumulate.zero_()
+        self._place += 1
+
+    def tap(self, what, dtype=torch.float32, max_elems=None):
         if what == "px":                                           # normalised 6-channel front-end output of the last pass
             return self._px.reshape(-1).to(dtype)
         assert what == "logits", what

@@ -359,48 +359,100 @@ def test_attack_loops_track_the_reference_loops(tmp_path, kind, opt):
     assert (ref_final - torch.from_numpy(gk["saved_last"])).abs().max().item() > lr / 2, "the golden trajectory moves after iteration 0"
 
 
-def test_batch_prefetcher_overlaps_and_preserves_order():
-    """the next batch is fetched (and its PIL images converted) on a background thread while the current one
-    is being worked on; order, restart-on-exhaustion and exception propagation are those of plain iteration."""
-    import time
+def test_lookahead_loader_order_restart_and_errors():
+    """the next batch is fetched (and its PIL images converted) by ``prefetch()`` -- which the attack loops
+    call between launching the inner steps and reading their scalars -- on the calling thread; order,
+    restart-on-exhaustion and exception propagation are those of plain iteration."""
     from PIL import Image
-    from roboticattack_b200.attacker import BatchPrefetcher
+    from roboticattack_b200.attacker import LookaheadLoader
 
-    class SlowLoader:
+    class Loader:
         def __init__(self, n, fail_at=None):
             self.n, self.fail_at, self.fetched = n, fail_at, []
 
         def __iter__(self):
             for k in range(self.n):
-                time.sleep(0.04)
                 if k == self.fail_at:
                     raise RuntimeError("loader died")
                 self.fetched.append(k)
                 yield {"pixel_values": [Image.fromarray(np.full((28, 28, 3), k, dtype=np.uint8))], "k": k}
 
-    src = SlowLoader(3)
-    pf = BatchPrefetcher(src, 28)
-    t0 = time.perf_counter()
+    src = Loader(3)
+    pf = LookaheadLoader(src, 28)
+    assert src.fetched == [], "nothing is drawn from the loader (or its RNG) before the first next()"
     ks = []
-    for i in range(7):                       # more than one pass: the loader restarts like _AttackerBase._next
+    for i in range(7):                       # more than one pass: the loader restarts like the reference's while-loop
         b = pf.next()
         assert b["pixel_values"].dtype == torch.uint8 and tuple(b["pixel_values"].shape) == (1, 28, 28, 3)
         assert int(b["pixel_values"][0, 0, 0, 0]) == b["k"]
         ks.append(b["k"])
-        time.sleep(0.08)                     # "the inner loop": twice the fetch time
-        assert len(src.fetched) >= i + 2, "the next batch was not fetched while this one was being worked on"
-    dt = time.perf_counter() - t0
+        n_before = len(src.fetched)
+        pf.prefetch()                        # "while the device runs the inner loop"
+        pf.prefetch()                        # idempotent until consumed
+        assert len(src.fetched) == n_before + 1
     pf.close()
     assert ks == [0, 1, 2, 0, 1, 2, 0]
-    assert dt < 0.78, f"fetch (7 x 40 ms) and work (7 x 80 ms) did not overlap: {dt:.2f}s (serial: 0.84 s)"
-    pf = BatchPrefetcher(SlowLoader(3, fail_at=2), 28)
-    assert pf.next()["k"] == 0 and pf.next()["k"] == 1
+    pf = LookaheadLoader(Loader(3, fail_at=2), 28)
+    assert pf.next()["k"] == 0
+    pf.prefetch()
+    assert pf.next()["k"] == 1
+    pf.prefetch()                            # the failure is kept for the next() that would have produced the batch
     with pytest.raises(RuntimeError, match="loader died"):
         pf.next()
-    pf = BatchPrefetcher(SlowLoader(2), 28, restart=False)
+    pf = LookaheadLoader(Loader(2), 28, restart=False)
     assert [pf.next()["k"], pf.next()["k"]] == [0, 1]
     with pytest.raises(StopIteration):
         pf.next()
+    off = Loader(3)
+    pf = LookaheadLoader(off, 28, lookahead=False)
+    pf.next()
+    pf.prefetch()
+    assert off.fetched == [0], "VLA_PREFETCH=0: batches are fetched only when asked for"
+
+
+def test_seeded_run_is_reproducible_with_a_shuffled_torch_dataloader(tmp_path, monkeypatch):
+    """A torch DataLoader draws its base seed and its RandomSampler seed from the GLOBAL torch RNG inside iter() / next().
+    With the lookahead on the calling thread a seeded run (initial patch, batches, placements, final patch) is a pure
+    function of the seeds -- with and without the lookahead."""
+    import argparse
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from roboticattack_b200.attacker import UPAAttacker
+    from roboticattack_b200.config import tiny
+    from roboticattack_b200.synthetic import synthetic_batch
+    from roboticattack_b200.weights import random_state_dict
+    cfg = tiny(img=28, llm_layers=1, vit_depth=2)
+    sd = random_state_dict(cfg, seed=0, dtype=torch.float32, init="test")
+    big = synthetic_batch(cfg, 6, 14, seed=3)
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 6
+
+        def __getitem__(self, i):
+            return {"pixel_values": big["obs"][i], "input_ids": big["input_ids"][i], "attention_mask": big["attention_mask"][i],
+                    "labels": big["labels"][i]}
+
+    def run(prefetch):
+        monkeypatch.setenv("VLA_PREFETCH", prefetch)
+        random.seed(7)
+        np.random.seed(7)
+        torch.manual_seed(7)
+        loader = torch.utils.data.DataLoader(DS(), batch_size=2, shuffle=True)
+        vloader = torch.utils.data.DataLoader(DS(), batch_size=2, shuffle=True)
+        a = UPAAttacker(sd, None, save_dir=str(tmp_path / prefetch), optimizer="adamW", alpha=0.8, belta=0.2, cfg=cfg, device="cpu",
+                        engine_factory=OracleEngine)
+        a.val_batches, a.val_every = 1, 2
+        p = a.patchattack_unconstrained(loader, vloader, num_iter=4, patch_size=[3, 6, 6], lr=2e-3, maskidx=[0, 1, 2], warmup=0,
+                                        geometry=True, innerLoop=2, args=argparse.Namespace(wandb_project="false"))
+        return p, list(a.train_CE_loss)
+
+    p1, l1 = run("1")
+    p1b, l1b = run("1")
+    p0, l0 = run("0")
+    assert torch.equal(p1, p1b) and l1 == l1b, "seeded run is not reproducible"
+    assert torch.equal(p1, p0) and l1 == l0, "the lookahead changed the RNG order"
 
 
 def test_filter_train_matches_reference_method():
