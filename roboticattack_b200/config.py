@@ -139,3 +139,38 @@ def flops_per_sample(cfg: OpenVLAConfig, text_len: int, supervised_rows: int = 8
     saved = 2 * (L - supervised_rows) * (hd * hd + 3 * hd * cfg.llm.ffn)
     return {"f_lin": f_lin, "f_att": f_att, "fwd": f_lin + f_att, "iter": 2 * f_lin + 3 * f_att,
             "iter_executed": 2 * (f_lin - saved) + 3 * f_att}
+
+
+def gemm_shape_table(cfg: OpenVLAConfig, batch: int, text_len: int, supervised_rows: int):
+    """The tcgen05 GEMM launches of one attack iteration as the engine issues them (csrc/engine.cu), as tuples
+    (count, M, N, K, extra bf16 elements read by the fused epilogue, extra bf16 elements written, bytes per output element).
+    Used for the roofline's algorithmic bytes (every operand and every result once) and FLOPs."""
+    rows = []
+    B, P = batch, cfg.num_patches
+    kpad = -(-3 * cfg.dino.patch ** 2 // 64) * 64
+    for v in (cfg.dino, cfg.siglip):
+        Mv, d, m, n = B * v.tokens, v.dim, v.mlp_hidden, v.blocks_used
+        rows += [(1, B * P, d, kpad, P * d, 0, 2), (1, B * P, kpad, d, 0, 0, 2)]                     # patch embed fwd (+pos_embed) / bwd
+        rows += [(n, Mv, 3 * d, d, 0, 0, 2), (n, Mv, d, d, Mv * d, 0, 2), (n, Mv, m, d, 0, Mv * m, 2), (n, Mv, d, m, Mv * d, 0, 2)]
+        rows += [(n, Mv, m, d, Mv * m, 0, 2), (n, Mv, d, m, 0, 0, 2), (n, Mv, d, d, 0, 0, 2), (n, Mv, d, 3 * d, 0, 0, 2)]
+    vd, ph, h, f, V = cfg.vision_dim, cfg.proj_hidden, cfg.llm.hidden, cfg.llm.ffn, cfg.llm.vocab
+    MP = B * P
+    rows += [(1, MP, ph, vd, 0, MP * ph, 2), (1, MP, h, ph, 0, MP * h, 2), (1, MP, h, h, 0, 0, 2)]
+    rows += [(1, MP, h, h, MP * h, 0, 2), (1, MP, ph, h, MP * ph, 0, 2), (1, MP, vd, ph, 0, 0, 2)]
+    L = text_len + P - 1
+    ML, R, nl = B * L, B * supervised_rows, cfg.llm.layers
+    rows += [(nl, ML, 3 * h, h, 0, 0, 2), (nl, ML, h, 3 * h, 0, 0, 2)]                               # q|k|v fwd (+RoPE), d(q|k|v) . W
+    for cnt, M in ((nl - 1, ML), (1, R)):                                                           # last layer on the supervised rows
+        rows += [(cnt, M, h, h, M * h, 0, 2), (cnt, M, 2 * f, h, 0, M * f, 2), (cnt, M, h, f, M * h, 0, 2)]
+        # backward: d(act) = dX . W_down with the SwiGLU backward fused (reads gate|up, writes d(gate|up) = 2 x N columns)
+        rows += [(cnt, M, f, h, 2 * M * f, M * f, 2), (cnt, M, h, 2 * f, 0, 0, 2), (cnt, M, h, h, M * h, 0, 2)]
+    rows += [(1, R, V, h, 0, 0, 4), (1, R, h, V, 0, 0, 2)]
+    return rows
+
+
+def gemm_algorithmic_bytes(cfg: OpenVLAConfig, batch: int, text_len: int, supervised_rows: int) -> int:
+    """Bytes the GEMMs of one attack iteration must move if every operand and result crosses HBM exactly once."""
+    total = 0
+    for cnt, M, N, K, rd, wr, ob in gemm_shape_table(cfg, batch, text_len, supervised_rows):
+        total += cnt * (2 * (M * K + N * K + rd + wr) + ob * M * N)
+    return int(total)

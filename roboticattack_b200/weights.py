@@ -16,9 +16,10 @@ SIGLIP = "vision_backbone.fused_featurizer."
 PROJ = "projector."
 LM = "language_model."
 
-def param_shapes(cfg: OpenVLAConfig) -> dict:
+def param_shapes(cfg: OpenVLAConfig, all_blocks: bool = False) -> dict:
     """name -> shape for every parameter the hot path touches (unused checkpoint entries such as the towers'
-    final ``norm``, SigLIP ``attn_pool`` and the last block of each tower are omitted)."""
+    final ``norm``, SigLIP ``attn_pool`` and the last block of each tower are omitted; ``all_blocks`` adds the last
+    block of each tower, which timm executes although its output is discarded)."""
     shapes = {}
     for prefix, v in ((DINO, cfg.dino), (SIGLIP, cfg.siglip)):
         shapes[prefix + "patch_embed.proj.weight"] = (v.dim, 3, v.patch, v.patch)
@@ -27,7 +28,7 @@ def param_shapes(cfg: OpenVLAConfig) -> dict:
         if v.num_prefix:
             shapes[prefix + "cls_token"] = (1, 1, v.dim)
             shapes[prefix + "reg_token"] = (1, v.num_prefix - 1, v.dim)
-        for i in range(v.blocks_used):
+        for i in range(v.depth if all_blocks else v.blocks_used):
             p = f"{prefix}blocks.{i}."
             shapes[p + "norm1.weight"] = (v.dim,)
             shapes[p + "norm1.bias"] = (v.dim,)

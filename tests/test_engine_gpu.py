@@ -173,8 +173,11 @@ def test_engine_attack_trajectory(tiny_setup):
     print("oracle losses", [f"{x:.4f}" for x in o_losses])
     print("engine losses", [f"{x:.4f}" for x in e_losses])
     print(f"patch Linf {dev_.max().item():.4g} mean {dev_.mean().item():.4g} frac within lr/2: {(dev_ < lr / 2).float().mean().item():.3f}")
-    assert abs(e_losses[0] - o_losses[0]) <= 2e-2 * abs(o_losses[0]) + 1e-3
-    assert dev_.mean().item() < 2 * lr
+    for s_, (a, b) in enumerate(zip(e_losses, o_losses)):          # every step, not only the first
+        assert abs(a - b) <= 2e-2 * abs(b) + 1e-3, f"step {s_}: engine {a} oracle {b}"
+    # stated tolerance of the short-horizon trajectory: >= 95 % of the pixels within lr/2, mean <= lr/4
+    assert (dev_ < lr / 2).float().mean().item() >= 0.95 and dev_.mean().item() <= lr / 4
+    assert dev_.max().item() <= 2 * steps * lr
     assert ((pe.cpu() - patch0).abs().max().item()) > 0
 
 

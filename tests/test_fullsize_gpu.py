@@ -36,7 +36,11 @@ def full():
     xy, theta = draw_placements(8, (224, 224), (50, 50), True, steps=1)
     torch.manual_seed(42)
     patch = torch.rand(3, 50, 50).cuda()
-    return cfg, eng, batch, xy, theta, patch
+    yield cfg, eng, batch, xy, theta, patch
+    del eng
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
 
 
 def run(eng, batch, xy, theta, patch, idx, loss, forward_only=False):
