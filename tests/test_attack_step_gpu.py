@@ -78,8 +78,8 @@ def test_graph_replay_equals_eager_equals_composed(setup):
     assert L.vla_graph_replays() - r0 == STEPS - 1
     assert eng.graph_kernel_nodes > 50, "the recorded graph must hold the step's kernels"
     r1 = L.vla_graph_replays()
-    gra2 = run_steps(eng, patch0, "graph", loss)         # same buffers? no: new clones -> new recording; still identical results
-    assert L.vla_graph_replays() - r1 == STEPS - 1
+    gra2 = run_steps(eng, patch0, "graph", loss)         # fresh buffers: a new recording, or -- when the allocator hands back the
+    assert L.vla_graph_replays() - r1 >= STEPS - 1       # same addresses -- the recorded graph replayed from the first step on
     assert eng.get_step_state() == (STEPS, STEPS)
     for name, out in (("eager", eag), ("graph", gra), ("graph again", gra2)):
         assert torch.equal(out[1][0, :_lib.S_GRAD_MEAN], ref[1][0, :_lib.S_GRAD_MEAN]), f"{name}: first-step scalars must be bit-identical"

@@ -196,7 +196,13 @@ def test_forward_taps_vs_oracle(results, name):
     L = e["x0"].shape[1]
     r_x = rel(e["x0"], t["x0"][:, :L])
     print(f"[{name}] px differing fraction {frac:.5f}; rel-err vs fp32 truth: dino_out {r_d:.4f} siglip_out {r_s:.4f} llm_x0 {r_x:.4f}")
-    assert frac < 2e-3          # bf16 rounding-boundary flips + patch-border pixels (see test_kernels_gpu.py)
+    # bf16 rounding-boundary flips + patch-border pixels (see test_kernels_gpu.py::test_frontend_vs_oracle, which compares with
+    # ATen's CPU grid_sample; here the oracle's front end runs ATen's CUDA path, whose coordinate maths differ from the CPU
+    # one by an fp32 ulp as well): few pixels differ, by one bf16 ulp, never by more than two (0.02 at the -100 border)
+    diff = (e["px"] - t["px"]).abs()
+    assert frac < 4e-3
+    assert (diff > 2.0 ** -8 * t["px"].abs().clamp_min(1.0) * 1.01).float().mean().item() < 2e-4
+    assert (diff <= torch.maximum(torch.full_like(diff, 0.02), 2.02 * 2.0 ** -8 * t["px"].abs())).all()
     assert r_d < 0.03 and r_s < 0.03 and r_x < 0.03
 
 
