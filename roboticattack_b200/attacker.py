@@ -107,6 +107,9 @@ class AttackEngineHost:
 
     def __init__(self, vla, cfg: Optional[OpenVLAConfig] = None, device="cuda:0", max_text_len: int = 64,
                  engine_factory=None):
+        if cfg is None and getattr(vla, "cfg", None) is None and hasattr(getattr(vla, "config", None), "text_config"):
+            from .config import config_from_hf
+            cfg = config_from_hf(vla.config)          # the HF OpenVLAForActionPrediction module the wrappers pass in
         self.cfg = cfg or getattr(vla, "cfg", None) or openvla_7b()
         self.engine_factory = engine_factory or VLAEngine
         self.device = torch.device(device)
@@ -126,8 +129,9 @@ class AttackEngineHost:
             src = self._vla
             if src is None:
                 raise _lib.VLAError("no weights: pass an HF model, a state dict or a loaded VLAEngine")
-            if isinstance(src, (str, os.PathLike)):   # the reference's `vla_path` (UADA_ddp.py:46): a torch.save'd state dict
-                sd = torch.load(src, map_location="cpu", weights_only=True, mmap=True)
+            if isinstance(src, (str, os.PathLike)):   # the reference's `vla_path` (UADA_ddp.py:37-50)
+                from .weights import resolve_vla
+                sd, _ = resolve_vla(src)
             else:
                 sd = src if isinstance(src, dict) else src.state_dict()
             self.engine.load_state_dict(sd, strict=False)
@@ -265,8 +269,10 @@ class _AttackerBase(object):
 
     STATE_FILE = "attack_state.pt"
 
-    def __init__(self, vla, processor=None, save_dir="", optimizer="pgd", resize_patch=False, cfg=None, device="cuda:0",
+    def __init__(self, vla, processor=None, save_dir="", optimizer="pgd", resize_patch=False, cfg=None, device=None,
                  engine_factory=None, resume=None):
+        if device is None:   # the reference works on the device the caller moved the model to (``self.vla.device``, UADA.py:55)
+            device = getattr(vla, "device", None) or "cuda:0"
         self.vla = vla
         self.processor = processor
         self.save_dir = save_dir
@@ -798,19 +804,54 @@ class UADADDPAttacker(_AttackerBase):
     Constructor mirrors UADA_ddp.py:37 except that the model / dataset are passed in instead of loaded by path."""
     KIND = "UADA_DDP"
 
-    def __init__(self, vla, dataloaders=None, save_dir="", resize_patch=False, patch_size=[3, 50, 50], lr=0.01, bs=1,
-                 warmup=20, num_iter=10000, maskidx=[], innerLoop=1, geometry=True, use_wandb=False, MSE_weights=1,
-                 cfg=None, device=None, engine_factory=None, backend="nccl", resume=None):
+    def __init__(self, vla_path, dataset_name=None, save_dir="", resize_patch=False, patch_size=[3, 50, 50], lr=0.01, bs=1,
+                 warmup=20, num_iter=10000, maskidx=[], innerLoop=1, geometry=True, use_wandb=True, MSE_weights=1,
+                 cfg=None, device=None, engine_factory=None, backend="nccl", resume=None, dataloaders=None):
+        """Positional / keyword compatible with UADA_ddp.py:37.  ``vla_path``: what the reference passes (a hub id or checkpoint
+        directory, loaded like the reference does) or a ``torch.save``d state dict file, a state dict, an HF module or a loaded
+        ``VLAEngine``.  ``dataset_name``: the RLDS dataset name (resolved through the caller's ``white_patch.openvla_dataloader
+        .get_dataset`` and sharded over ranks as UADA_ddp.py:157-160 does), or ``(train_loader, val_loader)``, or a callable
+        ``(rank, world_size) -> (train_loader, val_loader)``."""
         rank = int(os.environ.get("LOCAL_RANK", 0))
         device = device or f"cuda:{rank}"
-        super().__init__(vla, None, save_dir, "adamW", resize_patch, cfg=cfg, device=device, engine_factory=engine_factory, resume=resume)
+        if cfg is None and isinstance(vla_path, (str, os.PathLike)) and not os.path.isfile(vla_path):
+            from .config import config_from_hf
+            from .weights import resolve_vla
+            vla_path, hf_cfg = resolve_vla(vla_path)     # -> state dict (+ HF config): loaded once, here, like the reference
+            cfg = config_from_hf(hf_cfg) if hf_cfg is not None else None
+        super().__init__(vla_path, None, save_dir, "adamW", resize_patch, cfg=cfg, device=device, engine_factory=engine_factory, resume=resume)
         self.backend = backend
-        self.dataloaders = dataloaders
+        self.dataloaders = dataloaders if dataloaders is not None else dataset_name
         self.patch_size, self.lr, self.bs, self.warmup, self.num_iter = patch_size, lr, bs, warmup, num_iter
         self.maskidx, self.innerLoop, self.geometry, self.use_wandb, self.MSE_weights = maskidx, innerLoop, geometry, use_wandb, MSE_weights
         self.val_every, self.val_batches = 200, 100
         self.val_CE_loss, self.val_MSE_Distance, self.val_UAD = [], [], []
         self.MSE_Distance_best = 10000
+
+    def _resolve_dataloaders(self, rank, world_size):
+        """-> (train_loader, val_loader | None) for this rank."""
+        d = self.dataloaders
+        if d is None:
+            raise ValueError("no data: pass dataset_name (an RLDS name, a (train, val) pair or a callable (rank, world) -> pair)")
+        if callable(d):
+            d = d(rank, world_size)
+        if isinstance(d, str):
+            # the reference's own data path (UADA_ddp.py:52,157-160): get_dataset(name) -> RLDS datasets, sharded by rank, batched
+            # by a torch DataLoader with the padded collator; all of it is the caller's code (out of this repo's scope)
+            from white_patch.openvla_dataloader import get_dataset
+            train_ds, val_ds = get_dataset(dataset=d)
+            try:
+                from prismatic.util.data_utils import PaddedCollatorForActionPrediction
+                from transformers import AutoProcessor
+                tok = AutoProcessor.from_pretrained(self.vla if isinstance(self.vla, str) else "openvla/openvla-7b", trust_remote_code=True).tokenizer
+                collator = PaddedCollatorForActionPrediction(tok.model_max_length, tok.pad_token_id, padding_side="right")
+            except ImportError:
+                collator = None
+            mk = lambda ds: torch.utils.data.DataLoader(ds.shard(num_shards=world_size, index=rank) if hasattr(ds, "shard") else ds,  # noqa: E731
+                                                        batch_size=self.bs, collate_fn=collator)
+            d = (mk(train_ds), mk(val_ds) if val_ds is not None else None)
+        d = tuple(d)
+        return d[0], (d[1] if len(d) > 1 else None)
 
     def setup(self, rank, world_size):
         import torch.distributed as dist
@@ -840,7 +881,7 @@ class UADADDPAttacker(_AttackerBase):
         ``extra`` (cfg, backend, device, engine_factory, resume) goes to the constructor."""
         import torch.multiprocessing as mp
         world_size = world_size or torch.cuda.device_count()
-        instance_params = dict(vla=vla_path, dataloaders=dataset_name, save_dir=save_dir, resize_patch=resize_patch, patch_size=patch_size,
+        instance_params = dict(vla_path=vla_path, dataset_name=dataset_name, save_dir=save_dir, resize_patch=resize_patch, patch_size=patch_size,
                                lr=lr, bs=bs, warmup=warmup, num_iter=num_iter, maskidx=maskidx, innerLoop=innerLoop, geometry=geometry,
                                use_wandb=use_wandb, MSE_weights=MSE_weights, **extra)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -855,8 +896,6 @@ class UADADDPAttacker(_AttackerBase):
         params = dict(instance_params)
         if not dist.is_initialized():
             dist.init_process_group(params.get("backend", "nccl"), rank=rank, world_size=world_size)
-        if callable(params["dataloaders"]):
-            params["dataloaders"] = params["dataloaders"](rank, world_size)
         instance = UADADDPAttacker(**params)
         instance.attack(rank, world_size)
         instance.cleanup()
@@ -865,14 +904,15 @@ class UADADDPAttacker(_AttackerBase):
         import torch.distributed as dist
         self.setup(rank, world_size)
         h = self.host
-        train_dataloader = train_dataloader or self.dataloaders[0]
+        if train_dataloader is None:
+            train_dataloader, val_from_name = self._resolve_dataloaders(rank, world_size)
+            val_dataloader = val_dataloader or val_from_name
         h.init_patch(self.patch_size)
         start_iter, _ = self._maybe_resume()   # every rank restores the same replicated state (scheduler step = outer index)
         loss = LossSpec(_lib.LOSS_UADA_DDP, mse_weight=float(self.MSE_weights))
         fe_mode = _lib.FE_WARP if self.geometry else _lib.FE_PASTE20
         logs = []
         train_it = self._open(train_dataloader, restart=False)
-        val_dataloader = val_dataloader or (self.dataloaders[1] if self.dataloaders and len(self.dataloaders) > 1 else None)
         for i in range(start_iter, int(self.num_iter)):
             try:                                   # ``for i, data in enumerate(loader)`` of UADA_ddp.py:176: ends with the loader
                 data = train_it.next()

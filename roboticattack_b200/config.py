@@ -174,3 +174,26 @@ def gemm_algorithmic_bytes(cfg: OpenVLAConfig, batch: int, text_len: int, superv
     for cnt, M, N, K, rd, wr, ob in gemm_shape_table(cfg, batch, text_len, supervised_rows):
         total += cnt * (2 * (M * K + N * K + rd + wr) + ob * M * N)
     return int(total)
+
+
+def config_from_hf(hf_config) -> OpenVLAConfig:
+    """Engine configuration for an HF ``OpenVLAConfig`` (prismatic/extern/hf/configuration_prismatic.py:72-140): the LLM fields
+    come from ``text_config`` (LlamaConfig), the vocabulary is padded to ``pad_to_multiple_of`` as the HF port does, the vision
+    towers are the fused DINOv2-L/14-reg4 + SigLIP-so400m/14 pair (``timm_model_ids`` is checked when present)."""
+    import dataclasses
+    base = openvla_7b()
+    ids = getattr(hf_config, "timm_model_ids", None)
+    if ids is not None and list(ids) != ["vit_large_patch14_reg4_dinov2.lvd142m", "vit_so400m_patch14_siglip_224"]:
+        raise ValueError(f"unsupported vision backbone {ids}: the engine implements the fused DINOv2 + SigLIP towers of OpenVLA")
+    tc = getattr(hf_config, "text_config", None)
+    if tc is None:
+        return base
+    get = (lambda k, d: tc.get(k, d)) if isinstance(tc, dict) else (lambda k, d: getattr(tc, k, d))
+    vocab = int(get("vocab_size", base.llm.vocab))
+    mult = int(getattr(hf_config, "pad_to_multiple_of", 64) or 1)
+    vocab = -(-vocab // mult) * mult
+    llm = dataclasses.replace(base.llm, hidden=int(get("hidden_size", base.llm.hidden)), layers=int(get("num_hidden_layers", base.llm.layers)),
+                              heads=int(get("num_attention_heads", base.llm.heads)), ffn=int(get("intermediate_size", base.llm.ffn)),
+                              vocab=vocab, rms_eps=float(get("rms_norm_eps", base.llm.rms_eps)),
+                              rope_theta=float(get("rope_theta", base.llm.rope_theta)))
+    return dataclasses.replace(base, llm=llm)

@@ -105,3 +105,30 @@ def random_state_dict(cfg: OpenVLAConfig, seed: int = 0, device="cpu", dtype=tor
     """
     g = torch.Generator(device=device).manual_seed(seed)
     return {name: random_tensor(name, shape, g, device, init).to(dtype) for name, shape in param_shapes(cfg).items()}
+
+
+def resolve_vla(src):
+    """The reference's ``vla_path`` (UADA_ddp.py:37-50, *_wrapper.py) -> (state dict, HF config or None).  A file is a
+    ``torch.save``d state dict; anything else (a hub id such as ``openvla/openvla-7b`` or a checkpoint directory) goes through
+    ``AutoModelForVision2Seq.from_pretrained`` exactly as the reference loads it (bf16, low_cpu_mem_usage, trust_remote_code),
+    which needs the reference's own environment (transformers 4.40 + the prismatic HF classes)."""
+    import os
+    if isinstance(src, (str, os.PathLike)) and os.path.isfile(src):
+        return torch.load(src, map_location="cpu", weights_only=True, mmap=True), None
+    try:
+        from transformers import AutoModelForVision2Seq
+    except ImportError as e:
+        raise RuntimeError(f"cannot load '{src}': this transformers has no AutoModelForVision2Seq (the reference pins 4.40.1); "
+                           "pass a torch.save'd state dict, a state dict or a loaded model instead") from e
+    try:   # the registrations the reference performs before from_pretrained (UADA_ddp.py:38-40)
+        from transformers import AutoConfig, AutoProcessor
+        from prismatic.extern.hf.configuration_prismatic import OpenVLAConfig as HFOpenVLAConfig
+        from prismatic.extern.hf.modeling_prismatic import OpenVLAForActionPrediction
+        from prismatic.extern.hf.processing_prismatic import PrismaticProcessor
+        AutoConfig.register("openvla", HFOpenVLAConfig)
+        AutoProcessor.register(HFOpenVLAConfig, PrismaticProcessor)
+        AutoModelForVision2Seq.register(HFOpenVLAConfig, OpenVLAForActionPrediction)
+    except Exception:   # noqa: BLE001 -- already registered, or remote code is used
+        pass
+    vla = AutoModelForVision2Seq.from_pretrained(src, torch_dtype=torch.bfloat16, low_cpu_mem_usage=True, trust_remote_code=True)
+    return vla.state_dict(), getattr(vla, "config", None)
