@@ -815,10 +815,8 @@ class UADADDPAttacker(_AttackerBase):
         rank = int(os.environ.get("LOCAL_RANK", 0))
         device = device or f"cuda:{rank}"
         if cfg is None and isinstance(vla_path, (str, os.PathLike)) and not os.path.isfile(vla_path):
-            from .config import config_from_hf
             from .weights import resolve_vla
-            vla_path, hf_cfg = resolve_vla(vla_path)     # -> state dict (+ HF config): loaded once, here, like the reference
-            cfg = config_from_hf(hf_cfg) if hf_cfg is not None else None
+            vla_path, cfg = resolve_vla(vla_path)        # -> state dict + engine configuration: loaded once, here, like the reference
         super().__init__(vla_path, None, save_dir, "adamW", resize_patch, cfg=cfg, device=device, engine_factory=engine_factory, resume=resume)
         self.backend = backend
         self.dataloaders = dataloaders if dataloaders is not None else dataset_name

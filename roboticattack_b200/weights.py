@@ -108,7 +108,7 @@ def random_state_dict(cfg: OpenVLAConfig, seed: int = 0, device="cpu", dtype=tor
 
 
 def resolve_vla(src):
-    """The reference's ``vla_path`` (UADA_ddp.py:37-50, *_wrapper.py) -> (state dict, HF config or None).  A file is a
+    """The reference's ``vla_path`` (UADA_ddp.py:37-50, *_wrapper.py) -> (state dict, engine configuration or None).  A file is a
     ``torch.save``d state dict; anything else (a hub id such as ``openvla/openvla-7b`` or a checkpoint directory) goes through
     ``AutoModelForVision2Seq.from_pretrained`` exactly as the reference loads it (bf16, low_cpu_mem_usage, trust_remote_code),
     which needs the reference's own environment (transformers 4.40 + the prismatic HF classes)."""
@@ -131,4 +131,8 @@ def resolve_vla(src):
     except Exception:   # noqa: BLE001 -- already registered, or remote code is used
         pass
     vla = AutoModelForVision2Seq.from_pretrained(src, torch_dtype=torch.bfloat16, low_cpu_mem_usage=True, trust_remote_code=True)
-    return vla.state_dict(), getattr(vla, "config", None)
+    cfg = getattr(vla, "cfg", None)
+    if cfg is None and hasattr(getattr(vla, "config", None), "text_config"):
+        from .config import config_from_hf
+        cfg = config_from_hf(vla.config)
+    return vla.state_dict(), cfg
