@@ -232,6 +232,9 @@ typedef struct vla_step_params {
   int flags;                       /* VLA_STEP_* */
 } vla_step_params;
 int vla_engine_set_step_state(vla_engine* e, int placement_index, int adam_step, void* stream);
+/* drops the recorded graphs (re-recorded on demand); call before vla_comm_destroy of a communicator they used: NCCL blocks the
+ * destruction of a communicator while a graph still holds its collectives */
+int vla_engine_drop_graphs(vla_engine* e);
 /* host mirror of the device counters (no synchronisation) */
 int vla_engine_get_step_state(const vla_engine* e, int* placement_index, int* adam_step);
 /* patch / exp_avg / exp_avg_sq / dpatch f32 [3,ph,pw]; accumulate f32 [3,ph,pw] or NULL; comm NULL = single GPU;
@@ -241,6 +244,18 @@ int vla_attack_step(vla_engine* e, float* patch, float* exp_avg, float* exp_avg_
 /* bookkeeping for bench.py: attack steps replayed from a graph so far / kernel nodes of the most recent graph */
 long long vla_graph_replays(void);
 int vla_graph_kernel_nodes(const vla_engine* e);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Greedy action decode with a KV cache.  Replaces `self.generate(input_ids, max_new_tokens=action_dim)` inside
+ * OpenVLAForActionPrediction.predict_action (prismatic/extern/hf/modeling_prismatic.py:506-536; consumer:
+ * experiments/robot/libero/run_libero_eval_args_geo_batch.py:105-228).
+ * Prefill = one vla_fwd_bwd(VLA_FLAG_FORWARD_ONLY) over prompts of equal length `prompt_len` (BOS included) whose only
+ * supervised row per sample is the last prompt position (set_batch: labels[b, prompt_len] != -100 on a plan with
+ * T >= prompt_len + n_tokens); its post-RoPE k / v rows stay in the activation arena and are the cache.  Then n_tokens - 1
+ * single-position steps: embed the previous argmax, project q|k|v into the cache row, attend to the cached rows, MLP, final norm,
+ * lm_head, argmax over the full vocabulary -- all on the device, nothing read back in between.
+ * tokens i32 [B, n_tokens] (device). */
+int vla_engine_decode_greedy(vla_engine* e, int prompt_len, int n_tokens, int32_t* tokens, void* stream);
 
 /* test tap: copies a named internal activation ("px", "dino_out", "llm_out", "logits", ...) to dst (device) */
 int64_t vla_engine_debug_tap(vla_engine* e, const char* what, void* dst, int64_t max_bytes, void* stream);

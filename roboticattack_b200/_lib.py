@@ -110,12 +110,14 @@ SIGNATURES = {
     "vla_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(LossParams), c_void_p, c_void_p,
                             c_void_p, c_int, c_void_p]),
     "vla_engine_debug_tap": (c_int64, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
+    "vla_engine_decode_greedy": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "vla_comm_unique_id": (c_int, [c_void_p]),
     "vla_comm_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
     "vla_comm_destroy": (None, [c_void_p]),
     "vla_comm_world": (c_int, [c_void_p]),
     "vla_allreduce_patch_grad": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "vla_engine_set_step_state": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "vla_engine_drop_graphs": (c_int, [c_void_p]),
     "vla_engine_get_step_state": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
     "vla_attack_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(StepParams), c_void_p,
                                 c_void_p, c_void_p, c_void_p]),

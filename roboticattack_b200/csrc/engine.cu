@@ -132,6 +132,10 @@ struct vla_engine {
   };
   std::vector<StepGraph> graphs;
   int last_kernel_nodes = 0;
+  // greedy decode (vla_engine_decode_greedy)
+  int* dec_ids = nullptr;           // device: the B token ids fed to the next decode step
+  std::vector<int> h_sup_rows;      // host copy of the supervised-row table of the current batch
+  bool last_pass_forward_only = false;
 };
 
 namespace {
@@ -310,6 +314,7 @@ size_t plan(vla_engine* e, uint8_t* base, int B, int T) {
   e->theta = bp.take<float>(static_cast<size_t>(MAX_PLACEMENTS) * 6);
   e->rope_cos = bp.take<float>(static_cast<size_t>(L) * (h / c.llm_heads / 2));
   e->rope_sin = bp.take<float>(static_cast<size_t>(L) * (h / c.llm_heads / 2));
+  e->dec_ids = bp.take<int>(B);
   e->dstate = bp.take<StepState>(1);
   e->xy_cur = bp.take<int>(static_cast<size_t>(B) * 2);
   e->theta_cur = bp.take<float>(static_cast<size_t>(B) * 6);
@@ -528,6 +533,182 @@ int vit_backward(vla_engine* e, int t, Transients& tr, cudaStream_t s) {
   // patch-token rows of d x[0] -> d conv output [B*np, d] -> d im2col rows [B*np, kpad]
   CK(copy_rows(dx, d, v.ntok, v.npre, tr.c, d, e->np, 0, B, e->np, d, s));
   CK(G(tr.c, d, w.pe_t, d, a.a_col, e->kpad, static_cast<int64_t>(B) * e->np, e->kpad, d, plain, s));
+  return 0;
+}
+
+// ---- both vision towers in lock step: the same-depth kernels of DINOv2 and SigLIP share one launch --------------------
+// The towers are independent until the feature concat, but every one of their kernels is a short (10-30 us), latency-bound
+// launch that fills at most 1-3 waves of the machine; two streams do not help because the persistent GEMM / attention kernels
+// occupy every SM (one CTA of ~200 KB shared memory each) and therefore serialise anyway.  Issuing the DINOv2 and the SigLIP
+// GEMM (and LayerNorm) of the same depth as ONE launch pays the prologue / pipeline fill / drain once and lets a tile's
+// epilogue overlap the next tile's main loop.  SigLIP's three extra blocks run as single-problem launches.
+struct TowerCtx {
+  const VitDims* v;
+  const VitW* w;
+  VitActs* a;
+  Transients* tr;
+  int64_t Mv;
+};
+
+GemmProblem GP(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int64_t M, int N, int K, const GemmEpilogue& ep) {
+  return GemmProblem{A, lda, W, ldw, out, ldc, static_cast<int>(M), N, K, ep};
+}
+// runs problem builder f(tower) for the towers that still have block i: one dual launch, or one single launch
+template <typename F>
+int gemm_towers(const TowerCtx (&tc)[2], int i, F f, cudaStream_t s) {
+  const bool h0 = i < tc[0].v->used, h1 = i < tc[1].v->used;
+  if (h0 && h1) return gemm_bf16_tn_dual(f(tc[0]), f(tc[1]), s);
+  const GemmProblem p = f(tc[h0 ? 0 : 1]);
+  return gemm_bf16_tn(p.A, p.lda, p.W, p.ldw, p.out, p.ldc, p.M, p.N, p.K, p.epi, s);
+}
+
+int vit_forward_both(vla_engine* e, cudaStream_t s) {
+  const int B = e->B;
+  TowerCtx tc[2];
+  for (int t = 0; t < 2; ++t) tc[t] = TowerCtx{&e->vit[t], &e->vw[t], &e->va[t], &e->tr[t], static_cast<int64_t>(B) * e->vit[t].ntok};
+  const float eps = e->cfg.vit_ln_eps;
+  for (int t = 0; t < 2; ++t)
+    CK(write_prefix_tokens(tc[t].w->cls, tc[t].w->reg, tc[t].a->x[0], B, tc[t].v->ntok, tc[t].v->npre, tc[t].v->dim, s));
+  CK(gemm_towers(tc, 0, [&](const TowerCtx& c) {
+    GemmEpilogue ep;   // conv-as-GEMM + bias, + pos_embed (broadcast over batch), rows remapped past the prefix tokens
+    ep.bias = c.w->pe_b;
+    ep.resid = c.w->pos;
+    ep.ldr = c.v->dim;
+    ep.resid_mod = e->np;
+    ep.out_group = e->np;
+    ep.out_stride = c.v->ntok;
+    ep.out_offset = c.v->npre;
+    return GP(c.a->a_col, e->kpad, c.w->pe_w, e->kpad, c.a->x[0], c.v->dim, static_cast<int64_t>(B) * e->np, c.v->dim, e->kpad, ep);
+  }, s));
+  const int nb = std::max(tc[0].v->used, tc[1].v->used);
+  auto ln_fwd = [&](int i, bool second) -> int {
+    LnFwdProblem p[2];
+    int n = 0;
+    for (int t = 0; t < 2; ++t) {
+      const TowerCtx& c = tc[t];
+      if (i >= c.v->used) continue;
+      const VitBlockW& k = c.w->blk[i];
+      p[n++] = second ? LnFwdProblem{c.a->x_mid[i], k.n2w, k.n2b, c.tr->norm, c.a->mean2[i], c.a->rstd2[i], c.Mv, c.v->dim}
+                      : LnFwdProblem{c.a->x[i], k.n1w, k.n1b, c.tr->norm, c.a->mean1[i], c.a->rstd1[i], c.Mv, c.v->dim};
+    }
+    if (n == 2) return layernorm_fwd2(p[0], p[1], eps, s);
+    return layernorm_fwd(p[0].x, p[0].w, p[0].b, p[0].y, p[0].mean, p[0].rstd, p[0].M, p[0].d, eps, s);
+  };
+  for (int i = 0; i < nb; ++i) {
+    CK(ln_fwd(i, false));
+    CK(gemm_towers(tc, i, [&](const TowerCtx& c) {
+      const int d = c.v->dim;
+      GemmEpilogue ep;
+      ep.bias = c.w->blk[i].qkv_b;
+      return GP(c.tr->norm, d, c.w->blk[i].qkv_w, d, c.a->qkv[i], 3 * d, c.Mv, 3 * d, d, ep);
+    }, s));
+    for (int t = 0; t < 2; ++t)
+      if (i < tc[t].v->used)
+        CK(attention_fwd(tc[t].a->qkv[i], tc[t].a->attn_o[i], tc[t].a->lse[i], nullptr, B, tc[t].v->ntok, tc[t].v->heads, tc[t].v->hd, 0, s));
+    CK(gemm_towers(tc, i, [&](const TowerCtx& c) {
+      const int d = c.v->dim;
+      GemmEpilogue ep;
+      ep.bias = c.w->blk[i].proj_b;
+      ep.gamma = c.v->layerscale ? c.w->blk[i].ls1 : nullptr;
+      ep.resid = c.a->x[i];
+      ep.ldr = d;
+      return GP(c.a->attn_o[i], d, c.w->blk[i].proj_w, d, c.a->x_mid[i], d, c.Mv, d, d, ep);
+    }, s));
+    CK(ln_fwd(i, true));
+    CK(gemm_towers(tc, i, [&](const TowerCtx& c) {
+      const int d = c.v->dim;
+      GemmEpilogue ep;
+      ep.bias = c.w->blk[i].fc1_b;
+      ep.act = 1;
+      ep.preact_out = c.a->fc1_pre[i];
+      return GP(c.tr->norm, d, c.w->blk[i].fc1_w, d, c.tr->wide, c.v->mlp, c.Mv, c.v->mlp, d, ep);
+    }, s));
+    CK(gemm_towers(tc, i, [&](const TowerCtx& c) {
+      const int d = c.v->dim;
+      GemmEpilogue ep;
+      ep.bias = c.w->blk[i].fc2_b;
+      ep.gamma = c.v->layerscale ? c.w->blk[i].ls2 : nullptr;
+      ep.resid = c.a->x_mid[i];
+      ep.ldr = d;
+      return GP(c.tr->wide, c.v->mlp, c.w->blk[i].fc2_w, c.v->mlp, c.a->x[i + 1], d, c.Mv, d, c.v->mlp, ep);
+    }, s));
+  }
+  return 0;
+}
+
+// Gradients wrt the tower outputs in tr[t].a ([Mv, d], prefix rows zero).  Leaves d(im2col rows) in va[t].a_col.
+int vit_backward_both(vla_engine* e, cudaStream_t s) {
+  const int B = e->B;
+  TowerCtx tc[2];
+  for (int t = 0; t < 2; ++t) tc[t] = TowerCtx{&e->vit[t], &e->vw[t], &e->va[t], &e->tr[t], static_cast<int64_t>(B) * e->vit[t].ntok};
+  GemmEpilogue plain;
+  // per tower: dx = tr.a (gradient wrt x[i+1]), dxm = tr.b (wrt x_mid[i]); LayerScale towers keep dx o gamma in tr.c
+  for (int t = 0; t < 2; ++t)
+    if (tc[t].v->layerscale)
+      CK(scale_cols(tc[t].tr->a, tc[t].w->blk[tc[t].v->used - 1].ls2, tc[t].tr->c, tc[t].Mv, tc[t].v->dim, s));
+  // all towers' MLP widths must allow the fused GELU backward for the dual launch to share one epilogue kind
+  const bool fuse_gelu = tc[0].v->mlp % 8 == 0 && tc[1].v->mlp % 8 == 0;
+  const int nb = std::max(tc[0].v->used, tc[1].v->used);
+  auto ln_bwd = [&](int i, bool first) -> int {   // first: norm1 (end of the block's backward), else norm2
+    LnBwdProblem p[2];
+    int n = 0;
+    for (int t = 0; t < 2; ++t) {
+      const TowerCtx& c = tc[t];
+      if (i >= c.v->used) continue;
+      const VitBlockW& k = c.w->blk[i];
+      bf16 *dx = c.tr->a, *dxm = c.tr->b;
+      if (!first) {
+        p[n++] = LnBwdProblem{c.tr->norm, c.a->x_mid[i], k.n2w, c.a->mean2[i], c.a->rstd2[i], dx, dxm, c.Mv, c.v->dim,
+                              c.v->layerscale ? k.ls1 : nullptr, c.v->layerscale ? c.tr->c : nullptr};
+      } else {
+        const bool more = c.v->layerscale && i > 0;
+        p[n++] = LnBwdProblem{c.tr->norm, c.a->x[i], k.n1w, c.a->mean1[i], c.a->rstd1[i], dxm, dx, c.Mv, c.v->dim,
+                              more ? c.w->blk[i - 1].ls2 : nullptr, more ? c.tr->c : nullptr};
+      }
+    }
+    if (n == 2) return layernorm_bwd2(p[0], p[1], s);
+    return layernorm_bwd(p[0].dy, p[0].x, p[0].w, p[0].mean, p[0].rstd, p[0].dres, p[0].dx, p[0].M, p[0].d, s, p[0].gamma2, p[0].scaled);
+  };
+  for (int i = nb - 1; i >= 0; --i) {
+    CK(gemm_towers(tc, i, [&](const TowerCtx& c) {   // d(fc2 input) = g . W_fc2, GELU backward fused
+      const int d = c.v->dim;
+      const bf16* g = c.v->layerscale ? c.tr->c : c.tr->a;
+      GemmEpilogue ep;
+      if (fuse_gelu) {
+        ep.aux_mode = 1;
+        ep.aux = c.a->fc1_pre[i];
+        ep.ldaux = c.v->mlp;
+      }
+      return GP(g, d, c.w->blk[i].fc2_t, d, c.tr->wide, c.v->mlp, c.Mv, c.v->mlp, d, ep);
+    }, s));
+    if (!fuse_gelu)
+      for (int t = 0; t < 2; ++t)
+        if (i < tc[t].v->used) CK(gelu_bwd(tc[t].tr->wide, tc[t].a->fc1_pre[i], tc[t].tr->wide, tc[t].Mv * tc[t].v->mlp, s));
+    CK(gemm_towers(tc, i, [&](const TowerCtx& c) {
+      return GP(c.tr->wide, c.v->mlp, c.w->blk[i].fc1_t, c.v->mlp, c.tr->norm, c.v->dim, c.Mv, c.v->dim, c.v->mlp, plain);
+    }, s));
+    CK(ln_bwd(i, false));
+    CK(gemm_towers(tc, i, [&](const TowerCtx& c) {
+      const int d = c.v->dim;
+      const bf16* g = c.v->layerscale ? c.tr->c : c.tr->b;
+      return GP(g, d, c.w->blk[i].proj_t, d, c.tr->d, d, c.Mv, d, d, plain);
+    }, s));
+    for (int t = 0; t < 2; ++t)
+      if (i < tc[t].v->used)
+        CK(attention_bwd(tc[t].a->qkv[i], tc[t].a->attn_o[i], tc[t].tr->d, tc[t].a->lse[i], tc[t].tr->delta, tc[t].tr->qkv, nullptr, B,
+                         tc[t].v->ntok, tc[t].v->heads, tc[t].v->hd, 0, nullptr, nullptr, 0, s));
+    CK(gemm_towers(tc, i, [&](const TowerCtx& c) {
+      const int d = c.v->dim;
+      return GP(c.tr->qkv, 3 * d, c.w->blk[i].qkv_t, 3 * d, c.tr->norm, d, c.Mv, d, 3 * d, plain);
+    }, s));
+    CK(ln_bwd(i, true));
+  }
+  // patch-token rows of d x[0] -> d conv output [B*np, d] -> d im2col rows [B*np, kpad]
+  for (int t = 0; t < 2; ++t)
+    CK(copy_rows(tc[t].tr->a, tc[t].v->dim, tc[t].v->ntok, tc[t].v->npre, tc[t].tr->c, tc[t].v->dim, e->np, 0, B, e->np, tc[t].v->dim, s));
+  CK(gemm_towers(tc, 0, [&](const TowerCtx& c) {
+    return GP(c.tr->c, c.v->dim, c.w->pe_t, c.v->dim, c.a->a_col, e->kpad, static_cast<int64_t>(B) * e->np, e->kpad, c.v->dim, plain);
+  }, s));
   return 0;
 }
 
@@ -772,6 +953,8 @@ extern "C" int vla_engine_set_batch(vla_engine* e, const uint8_t* obs, int obs_o
   VLA_CHECK_CUDA(cudaMemcpyAsync(e->meta, meta.data(), sizeof(int) * meta.size(), cudaMemcpyHostToDevice, s));
   VLA_CHECK_CUDA(cudaMemcpyAsync(e->sup_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice, s));
   VLA_CHECK_CUDA(cudaStreamSynchronize(s));   // the std::vectors above are pageable staging
+  e->h_sup_rows = rows;
+  e->last_pass_forward_only = false;
   e->batch_set = true;
   return 0;
 }
@@ -851,7 +1034,9 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
   // The two towers are independent until the feature concat: DINOv2 stays on the caller's stream, SigLIP runs on the
   // engine's side stream (fork / join with events), so the many small kernels of one tower fill the launch gaps, ramps
   // and tails of the other.  VLA_SINGLE_STREAM=1 keeps everything on one stream.
-  const bool two_streams = e->side != nullptr && !e->single_stream;
+  const char* towers_env = getenv("VLA_TOWERS");   // read per call (A/B switch, tests): "streams" = the round-1 two-stream path
+  const bool towers_dual = !(towers_env && strcmp(towers_env, "streams") == 0);
+  const bool two_streams = !towers_dual && e->side != nullptr && !e->single_stream;
   cudaStream_t s1 = two_streams ? e->side : s;
   if (two_streams) {
     VLA_CHECK_CUDA(cudaEventRecord(e->ev_fork, s));
@@ -862,18 +1047,27 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, cur_dev);
   const int tower_sms = (two_streams && e->split_sms && num_sms >= 8) ? (num_sms / 2) & ~1 : 0;
   int col_off = 0;
-  g_vla_sm_limit = tower_sms;
-  for (int t = 0; t < 2; ++t) {
-    cudaStream_t st = t == 0 ? s : s1;
-    if (int rc = vit_forward(e, t, e->tr[two_streams ? t : 0], st)) {
-      g_vla_sm_limit = 0;
-      return rc;
+  if (towers_dual) {
+    CK(vit_forward_both(e, s));
+    for (int t = 0; t < 2; ++t) {
+      const VitDims& v = e->vit[t];
+      CK(copy_rows(e->va[t].x[v.used], v.dim, v.ntok, v.npre, e->feats + col_off, vd, P, 0, B, P, v.dim, s));
+      col_off += v.dim;
     }
-    const VitDims& v = e->vit[t];
-    CK(copy_rows(e->va[t].x[v.used], v.dim, v.ntok, v.npre, e->feats + col_off, vd, P, 0, B, P, v.dim, st));
-    col_off += v.dim;
+  } else {
+    g_vla_sm_limit = tower_sms;
+    for (int t = 0; t < 2; ++t) {
+      cudaStream_t st = t == 0 ? s : s1;
+      if (int rc = vit_forward(e, t, e->tr[two_streams ? t : 0], st)) {
+        g_vla_sm_limit = 0;
+        return rc;
+      }
+      const VitDims& v = e->vit[t];
+      CK(copy_rows(e->va[t].x[v.used], v.dim, v.ntok, v.npre, e->feats + col_off, vd, P, 0, B, P, v.dim, st));
+      col_off += v.dim;
+    }
+    g_vla_sm_limit = 0;
   }
-  g_vla_sm_limit = 0;
   if (two_streams) {
     VLA_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
     VLA_CHECK_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
@@ -968,6 +1162,7 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
     CK(G(e->hn, h, e->lm_head, h, e->logits, V, R, V, h, ep, s));
   }
   CK(loss_head_fwd_bwd(e->logits, e->meta, R, V, B, lp, e->row_stats, e->dlogits, scalars, pred_ids, s));
+  e->last_pass_forward_only = (flags & VLA_FLAG_FORWARD_ONLY) != 0;
   if (flags & VLA_FLAG_FORWARD_ONLY) return 0;
 
   mark(2);
@@ -1073,15 +1268,18 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
     const VitDims& v = e->vit[t];
     const int64_t Mv = static_cast<int64_t>(B) * v.ntok;
     cudaStream_t st = t == 0 ? s : s1;
-    Transients& tr = e->tr[two_streams ? t : 0];
+    Transients& tr = e->tr[(two_streams || towers_dual) ? t : 0];
     VLA_CHECK_CUDA(cudaMemsetAsync(tr.a, 0, static_cast<size_t>(Mv) * v.dim * sizeof(bf16), st));
     CK(copy_rows(e->feats + col_off, vd, P, 0, tr.a, v.dim, v.ntok, v.npre, B, P, v.dim, st));
-    g_vla_sm_limit = tower_sms;
-    const int rc_b = vit_backward(e, t, tr, st);
-    g_vla_sm_limit = 0;
-    if (rc_b) return rc_b;
+    if (!towers_dual) {
+      g_vla_sm_limit = tower_sms;
+      const int rc_b = vit_backward(e, t, tr, st);
+      g_vla_sm_limit = 0;
+      if (rc_b) return rc_b;
+    }
     col_off += v.dim;
   }
+  if (towers_dual) CK(vit_backward_both(e, s));
   if (two_streams) {
     VLA_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
     VLA_CHECK_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
@@ -1107,6 +1305,17 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
 static long long g_graph_replays = 0;
 extern "C" long long vla_graph_replays(void) { return g_graph_replays; }
 extern "C" int vla_graph_kernel_nodes(const vla_engine* e) { return e ? e->last_kernel_nodes : 0; }
+
+// Destroys the recorded attack-step graphs (they are re-recorded on demand).  Must precede vla_comm_destroy of a communicator
+// whose all-reduce was recorded: NCCL keeps a communicator alive -- and blocks its destruction -- while graphs hold its work.
+extern "C" int vla_engine_drop_graphs(vla_engine* e) {
+  VLA_REQUIRE(e != nullptr, "vla_engine_drop_graphs: null engine");
+  VLA_CHECK_CUDA(cudaDeviceSynchronize());
+  for (auto& g : e->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+  return 0;
+}
 
 extern "C" int vla_engine_set_step_state(vla_engine* e, int placement_index, int adam_step, void* stream) {
   VLA_REQUIRE(e && e->ws, "vla_engine_set_step_state: call vla_engine_set_buffers first");
@@ -1255,6 +1464,73 @@ extern "C" int vla_attack_step(vla_engine* e, float* patch, float* exp_avg, floa
   if (rc) return rc;
   e->h_place++;
   if (update) e->h_adam++;
+  return 0;
+}
+
+// =================================================================================================================
+// Greedy action decode with the KV cache of the last forward-only pass (predict_action, modeling_prismatic.py:506-536 ->
+// HF generate(do_sample=False, max_new_tokens=action_dim)).  See decode.cu.
+// =================================================================================================================
+extern "C" int vla_engine_decode_greedy(vla_engine* e, int prompt_len, int n_tokens, int* tokens, void* stream) {
+  VLA_REQUIRE(e && e->weights_resolved && e->batch_set, "vla_engine_decode_greedy: engine / batch not set");
+  VLA_REQUIRE(tokens && n_tokens >= 1, "vla_engine_decode_greedy: null / empty output");
+  VLA_REQUIRE(e->last_pass_forward_only, "vla_engine_decode_greedy: run the prefill first (vla_fwd_bwd with VLA_FLAG_FORWARD_ONLY)");
+  const vla_config& c = e->cfg;
+  const int B = e->B, L = e->L, P = e->np, h = c.llm_hidden, f = c.llm_ffn, V = c.vocab, NH = c.llm_heads, hd = h / NH;
+  VLA_REQUIRE(e->R == B, "vla_engine_decode_greedy: the prefill must have exactly one supervised row per sample (got %d rows for %d samples)", e->R, B);
+  for (int b = 0; b < B; ++b)
+    VLA_REQUIRE(e->h_sup_rows[b] == b * L + P + prompt_len - 1,
+                "vla_engine_decode_greedy: sample %d: the supervised row must be the last prompt position (prompts of equal length %d)", b, prompt_len);
+  VLA_REQUIRE(P + prompt_len + n_tokens - 2 <= L - 1, "vla_engine_decode_greedy: plan too short: T must be >= prompt_len + n_tokens (= %d)",
+              prompt_len + n_tokens);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // token 0: the argmax of the prefill's logits row (full vocabulary, as generate() does)
+  CK(argmax_rows(e->logits, B, V, e->dec_ids, tokens, n_tokens, 0, s));
+  for (int k = 1; k < n_tokens; ++k) {
+    const int pos = P + prompt_len + k - 1;   // cache row (within a sample) of the token generated in the previous step
+    bf16* x = e->ll_xs;
+    CK(embed_rows(e->dec_ids, e->embed, x, B, h, s));
+    for (int l = 0; l < c.llm_layers; ++l) {
+      const LlamaLayerW& w = e->lw[l];
+      CK(rmsnorm_fwd(x, w.n1, e->ll_norm, e->ll_rstd2, B, h, c.rms_eps, s));
+      {   // q|k|v of the new position, written straight into the layer's cache row b * L + pos
+        GemmEpilogue ep;
+        ep.out_group = 1;
+        ep.out_stride = L;
+        ep.out_offset = pos;
+        CK(G(e->ll_norm, h, w.qkv, h, e->la.qkv[l], 3 * h, B, 3 * h, h, ep, s));
+      }
+      CK(rope_cache_rows(e->la.qkv[l], e->rope_cos, e->rope_sin, B, L, pos, NH, hd, s));
+      CK(attention_decode(e->la.qkv[l], e->ll_as, B, L, pos, NH, hd, s));
+      {
+        GemmEpilogue ep;
+        ep.resid = x;
+        ep.ldr = h;
+        CK(G(e->ll_as, h, w.o, h, e->ll_xm, h, B, h, h, ep, s));
+      }
+      CK(rmsnorm_fwd(e->ll_xm, w.n2, e->ll_norm, e->ll_rstd2, B, h, c.rms_eps, s));
+      {
+        GemmEpilogue ep;
+        ep.pair_mode = 2;
+        ep.act_out = e->ll_act;
+        ep.ld_act = f;
+        CK(G(e->ll_norm, h, w.gu, h, e->ll_gu, 2 * f, B, 2 * f, h, ep, s));
+      }
+      {
+        GemmEpilogue ep;
+        ep.resid = e->ll_xm;
+        ep.ldr = h;
+        CK(G(e->ll_act, f, w.down, f, x, h, B, h, f, ep, s));
+      }
+    }
+    CK(rmsnorm_fwd(x, e->final_norm, e->hn, e->rstd_f, B, h, c.rms_eps, s));
+    {
+      GemmEpilogue ep;
+      ep.out_f32 = 1;
+      CK(G(e->hn, h, e->lm_head, h, e->logits, V, B, V, h, ep, s));
+    }
+    CK(argmax_rows(e->logits, B, V, e->dec_ids, tokens, n_tokens, k, s));
+  }
   return 0;
 }
 

@@ -52,6 +52,22 @@ struct GemmEpilogue {
   int delta_L = 0;
 };
 
+// One problem of a launch.
+struct GemmProblem {
+  const bf16* A;
+  int64_t lda;
+  const bf16* W;
+  int64_t ldw;
+  void* out;
+  int64_t ldc;
+  int M, N, K;
+  GemmEpilogue epi;
+};
+// Two independent problems of the same epilogue kind in ONE persistent launch (the DINOv2 and the SigLIP GEMM of the same
+// depth): one prologue / pipeline fill / drain for both.  Results are bit-identical to two separate launches (same tiles,
+// same accumulation order).
+int gemm_bf16_tn_dual(const GemmProblem& p0, const GemmProblem& p1, cudaStream_t stream);
+
 // Returns 0 on success. No allocation, no synchronisation; launches on `stream`.
 int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
                  const GemmEpilogue& epi, cudaStream_t stream);

@@ -103,6 +103,15 @@ struct GemmArgs {
   int wide;           // every epilogue tensor is 32-byte aligned with a 32-byte multiple row pitch: 256-bit global accesses
 };
 
+// A launch works on up to two independent problems of the same kernel variant and epilogue mode (the DINOv2 and the SigLIP
+// GEMM of the same depth): the tiles of problem 1 follow those of problem 0 in the persistent tile loop, so that one launch's
+// prologue / pipeline fill / drain is paid once for both and the epilogue of a tile overlaps the main loop of the next one
+// even when a single problem has only one tile per CTA.  tiles1 == 0: plain single-problem launch.
+struct GemmArgs2 {
+  GemmArgs p[2];
+  int tiles0, tiles1;
+};
+
 // The epilogue mode is a template parameter of the kernel: one kernel that branches over every mode at run time is ~9400
 // instructions (150 KB) of which a launch executes ~1600 scattered ones, and the epilogue warps then lose ~18 % of their
 // samples to instruction-fetch stalls (ncu stall_no_inst on the fc1+GELU shape).
@@ -522,8 +531,9 @@ __device__ __forceinline__ void epilogue_store_pair(const GemmArgs& g, const uin
 
 template <int BLOCK_N, int CTAS, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const GemmArgs g) {
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_b0,
+                    const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
+                    const __grid_constant__ GemmArgs2 gg) {
   using Cfg = GemmCfg<BLOCK_N, CTAS>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TILE_M = BLOCK_M * CTAS;
@@ -545,13 +555,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
-  const int num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
-  const int num_tiles = g.num_m_blocks * g.num_n_blocks;
+  const int num_tiles = gg.tiles0 + gg.tiles1;
   const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_b0);
+    if (gg.tiles1 > 0) {
+      tma_prefetch_desc(&map_a1);
+      tma_prefetch_desc(&map_b1);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -580,7 +593,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = tile % g.num_m_blocks, n_blk = tile / g.num_m_blocks;
+        const int pi = tile >= gg.tiles0 ? 1 : 0;
+        const GemmArgs& g = gg.p[pi];
+        const CUtensorMap* map_a = pi ? &map_a1 : &map_a0;
+        const CUtensorMap* map_b = pi ? &map_b1 : &map_b0;
+        const int t = tile - (pi ? gg.tiles0 : 0);
+        const int m_blk = t % g.num_m_blocks, n_blk = t / g.num_m_blocks;
+        const int num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
         const int row_a = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
         const int row_b = n_blk * BLOCK_N + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
@@ -589,14 +608,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           if (CTAS == 1) {
             mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-            tma_load_2d(sa, &map_a, full_bar(stage), kb * BLOCK_K, row_a);
-            tma_load_2d(sa + A_TILE_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, row_b);
+            tma_load_2d(sa, map_a, full_bar(stage), kb * BLOCK_K, row_a);
+            tma_load_2d(sa + A_TILE_BYTES, map_b, full_bar(stage), kb * BLOCK_K, row_b);
           } else {
             // both CTAs' bytes are accounted on the LEADER's full barrier (peer bit of the address cleared)
             if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
             else mbar_arrive_remote(full_bar(stage), 0);
-            tma_load_2d_pair(sa, &map_a, full_bar(stage), kb * BLOCK_K, row_a);
-            tma_load_2d_pair(sa + A_TILE_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, row_b);
+            tma_load_2d_pair(sa, map_a, full_bar(stage), kb * BLOCK_K, row_a);
+            tma_load_2d_pair(sa + A_TILE_BYTES, map_b, full_bar(stage), kb * BLOCK_K, row_b);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -618,6 +637,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int num_k_blocks = (gg.p[tile >= gg.tiles0 ? 1 : 0].K + BLOCK_K - 1) / BLOCK_K;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -654,7 +674,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_blk = tile % g.num_m_blocks, n_blk = tile / g.num_m_blocks;
+      const int pi = tile >= gg.tiles0 ? 1 : 0;
+      const GemmArgs& g = gg.p[pi];
+      const int t = tile - (pi ? gg.tiles0 : 0);
+      const int m_blk = t % g.num_m_blocks, n_blk = t / g.num_m_blocks;
       const int row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
       constexpr bool waited = EPI == EPI_PAIR;
@@ -752,7 +775,7 @@ int get_tmap(const bf16* ptr, int64_t ld, int rows, int cols, int box_rows, CUte
 int g_num_sms = 0;
 
 template <int BLOCK_N, int CTAS, int EPI>
-int launch_gemm_epi(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t stream) {
+int launch_gemm_epi(const CUtensorMap (&maps)[4], const GemmArgs2& gg, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CTAS>;
   static bool configured = false;
   if (!configured) {
@@ -760,7 +783,7 @@ int launch_gemm_epi(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs
                                         Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int tiles = g.num_m_blocks * g.num_n_blocks;
+  const int tiles = gg.tiles0 + gg.tiles1;
   const int sms = (g_vla_sm_limit > 0 && g_vla_sm_limit < g_num_sms) ? g_vla_sm_limit : g_num_sms;
   const int units = sms / CTAS;   // persistent: one CTA (or CTA pair) per SM (pair)
   const int grid = (tiles < units ? tiles : units) * CTAS;
@@ -790,11 +813,16 @@ int launch_gemm_epi(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs
   attr[1].val.programmaticStreamSerializationAllowed = g_vla_pdl;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  VLA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BLOCK_N, CTAS, EPI>, ma, mb, g));
+  VLA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BLOCK_N, CTAS, EPI>, maps[0], maps[1], maps[2], maps[3], gg));
   if (e1) {
     VLA_CHECK_CUDA(cudaEventRecord(e1, stream));
-    g_prof.flops.push_back(2.0 * g.M * g.N * g.K);
-    g_prof.shape.push_back((static_cast<uint64_t>(g.M) << 42) | (static_cast<uint64_t>(g.N) << 21) | static_cast<uint64_t>(g.K));
+    const GemmArgs& g = gg.p[0];
+    double fl = 2.0 * g.M * g.N * g.K;
+    if (gg.tiles1 > 0) fl += 2.0 * gg.p[1].M * gg.p[1].N * gg.p[1].K;
+    g_prof.flops.push_back(fl);
+    // a two-problem launch is listed under its first problem's shape with the top bit of M set
+    g_prof.shape.push_back((static_cast<uint64_t>(g.M + (gg.tiles1 > 0 ? (1 << 20) : 0)) << 42) | (static_cast<uint64_t>(g.N) << 21) |
+                           static_cast<uint64_t>(g.K));
     g_prof.variant.push_back(CTAS * 1000 + BLOCK_N);
   }
   ++g_vla_launch_count;
@@ -822,54 +850,89 @@ int epilogue_kind(const GemmEpilogue& e, int N) {
   return EPI_GENERAL;
 }
 template <int BLOCK_N, int CTAS>
-int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t stream) {
-  switch (epilogue_kind(g.epi, g.N)) {
-    case EPI_PLAIN: return launch_gemm_epi<BLOCK_N, CTAS, EPI_PLAIN>(ma, mb, g, stream);
-    case EPI_GELU: return launch_gemm_epi<BLOCK_N, CTAS, EPI_GELU>(ma, mb, g, stream);
-    case EPI_GELU_BWD: return launch_gemm_epi<BLOCK_N, CTAS, EPI_GELU_BWD>(ma, mb, g, stream);
-    case EPI_SWIGLU_BWD: return launch_gemm_epi<BLOCK_N, CTAS, EPI_SWIGLU_BWD>(ma, mb, g, stream);
-    case EPI_PAIR: return launch_gemm_epi<BLOCK_N, CTAS, EPI_PAIR>(ma, mb, g, stream);
+int launch_gemm(int kind, const CUtensorMap (&maps)[4], const GemmArgs2& gg, cudaStream_t stream) {
+  switch (kind) {
+    case EPI_PLAIN: return launch_gemm_epi<BLOCK_N, CTAS, EPI_PLAIN>(maps, gg, stream);
+    case EPI_GELU: return launch_gemm_epi<BLOCK_N, CTAS, EPI_GELU>(maps, gg, stream);
+    case EPI_GELU_BWD: return launch_gemm_epi<BLOCK_N, CTAS, EPI_GELU_BWD>(maps, gg, stream);
+    case EPI_SWIGLU_BWD: return launch_gemm_epi<BLOCK_N, CTAS, EPI_SWIGLU_BWD>(maps, gg, stream);
+    case EPI_PAIR: return launch_gemm_epi<BLOCK_N, CTAS, EPI_PAIR>(maps, gg, stream);
     case EPI_DELTA:
-      if constexpr (BLOCK_N == 256) return launch_gemm_epi<BLOCK_N, CTAS, EPI_DELTA>(ma, mb, g, stream);
+      if constexpr (BLOCK_N == 256) return launch_gemm_epi<BLOCK_N, CTAS, EPI_DELTA>(maps, gg, stream);
       else VLA_REQUIRE(false, "gemm: the delta epilogue needs a 256-wide tile");
-    default: return launch_gemm_epi<BLOCK_N, CTAS, EPI_GENERAL>(ma, mb, g, stream);
+    default: return launch_gemm_epi<BLOCK_N, CTAS, EPI_GENERAL>(maps, gg, stream);
   }
 }
-int launch_variant(int ctas, int block_n, const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc,
-                   int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
-  GemmArgs g;
-  g.M = M;
-  g.N = N;
-  g.K = K;
-  g.num_m_blocks = ceil_div(M, BLOCK_M * ctas);
-  g.num_n_blocks = ceil_div(N, block_n);
-  g.ldc = ldc;
-  g.out = out;
-  g.epi = epi;
+
+int fill_args(const GemmProblem& p, int ctas, int block_n, GemmArgs* g, CUtensorMap* ma, CUtensorMap* mb) {
+  g->M = p.M;
+  g->N = p.N;
+  g->K = p.K;
+  g->num_m_blocks = ceil_div(p.M, BLOCK_M * ctas);
+  g->num_n_blocks = ceil_div(p.N, block_n);
+  g->ldc = p.ldc;
+  g->out = p.out;
+  g->epi = p.epi;
   static int sleep_ns = -1;
   if (sleep_ns < 0) {
     const char* e = getenv("VLA_EPI_SLEEP_NS");
     sleep_ns = e ? atoi(e) : 0;
   }
-  g.epi_sleep_ns = sleep_ns;
-  {
-    auto ok = [](const void* p, int64_t ld_elems, int elem) {
-      return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 31) == 0 && (ld_elems * elem) % 32 == 0);
-    };
-    static int no_wide = -1;
-    if (no_wide < 0) no_wide = getenv("VLA_GEMM_NO_WIDE") ? 1 : 0;   // A/B switch
-    g.wide = !no_wide && ok(out, ldc, epi.out_f32 ? 4 : 2) && ok(epi.resid, epi.ldr, 2) && ok(epi.aux, epi.ldaux, 2) &&
-             ok(epi.preact_out, ldc, 2) && ok(epi.act_out, epi.ld_act, 2) && ok(epi.bias, 16, 2) &&
-             ok(epi.rope_cos, 8, 4) && ok(epi.rope_sin, 8, 4);
-  }
-  CUtensorMap ma, mbm;
-  if (int rc = get_tmap(A, lda, M, K, BLOCK_M, &ma)) return rc;
-  if (int rc = get_tmap(W, ldw, N, K, block_n / ctas, &mbm)) return rc;
-  if (ctas == 2) return block_n == 256 ? launch_gemm<256, 2>(ma, mbm, g, stream) : launch_gemm<128, 2>(ma, mbm, g, stream);
-  return block_n == 256 ? launch_gemm<256, 1>(ma, mbm, g, stream) : launch_gemm<128, 1>(ma, mbm, g, stream);
+  g->epi_sleep_ns = sleep_ns;
+  auto ok = [](const void* q, int64_t ld_elems, int elem) {
+    return q == nullptr || ((reinterpret_cast<uintptr_t>(q) & 31) == 0 && (ld_elems * elem) % 32 == 0);
+  };
+  static int no_wide = -1;
+  if (no_wide < 0) no_wide = getenv("VLA_GEMM_NO_WIDE") ? 1 : 0;   // A/B switch
+  const GemmEpilogue& epi = p.epi;
+  g->wide = !no_wide && ok(p.out, p.ldc, epi.out_f32 ? 4 : 2) && ok(epi.resid, epi.ldr, 2) && ok(epi.aux, epi.ldaux, 2) &&
+            ok(epi.preact_out, p.ldc, 2) && ok(epi.act_out, epi.ld_act, 2) && ok(epi.bias, 16, 2) && ok(epi.rope_cos, 8, 4) &&
+            ok(epi.rope_sin, 8, 4);
+  if (int rc = get_tmap(p.A, p.lda, p.M, p.K, BLOCK_M, ma)) return rc;
+  if (int rc = get_tmap(p.W, p.ldw, p.N, p.K, block_n / ctas, mb)) return rc;
+  return 0;
 }
-std::unordered_map<uint64_t, Variant> g_tuned;   // (M, N, K) -> fastest variant measured on this device
+
+// p1 == nullptr: single problem
+int launch_variant(int ctas, int block_n, const GemmProblem& p0, const GemmProblem* p1, int kind, cudaStream_t stream) {
+  GemmArgs2 gg;
+  CUtensorMap maps[4];
+  if (int rc = fill_args(p0, ctas, block_n, &gg.p[0], &maps[0], &maps[1])) return rc;
+  gg.tiles0 = gg.p[0].num_m_blocks * gg.p[0].num_n_blocks;
+  if (p1) {
+    if (int rc = fill_args(*p1, ctas, block_n, &gg.p[1], &maps[2], &maps[3])) return rc;
+    gg.tiles1 = gg.p[1].num_m_blocks * gg.p[1].num_n_blocks;
+  } else {
+    gg.p[1] = gg.p[0];
+    maps[2] = maps[0];
+    maps[3] = maps[1];
+    gg.tiles1 = 0;
+  }
+  if (ctas == 2) return block_n == 256 ? launch_gemm<256, 2>(kind, maps, gg, stream) : launch_gemm<128, 2>(kind, maps, gg, stream);
+  return block_n == 256 ? launch_gemm<256, 1>(kind, maps, gg, stream) : launch_gemm<128, 1>(kind, maps, gg, stream);
+}
+std::unordered_map<uint64_t, Variant> g_tuned;   // shape(s) -> fastest variant measured on this device
 int g_autotune = 1;
+
+int validate(const GemmProblem& p) {
+  const GemmEpilogue& epi = p.epi;
+  const int M = p.M, N = p.N, K = p.K;
+  VLA_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  VLA_REQUIRE(p.lda % 8 == 0 && p.ldw % 8 == 0 && p.ldc % 8 == 0, "gemm: leading dims must be multiples of 8 elements");
+  VLA_REQUIRE((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(p.out) & 15) == 0,
+              "gemm: operands must be 16-byte aligned");
+  VLA_REQUIRE(!epi.resid || epi.ldr % 8 == 0, "gemm: residual ld must be a multiple of 8");
+  VLA_REQUIRE(!epi.pair_mode || N % 128 == 0, "gemm: pair-mode epilogues need N %% 128 == 0 (got %d)", N);
+  VLA_REQUIRE(!epi.aux_mode || (N % (epi.aux_mode == 1 ? 8 : 32) == 0 && epi.aux && epi.ldaux % 8 == 0),
+              "gemm: aux-mode epilogues need N %% 32 == 0 (GELU backward: N %% 8 == 0) and an aux tensor");
+  VLA_REQUIRE(epi.pair_mode != 1 || (epi.rope_cos && epi.rope_sin && epi.rope_L > 0 && epi.rope_cols % 128 == 0), "gemm: bad RoPE epilogue");
+  VLA_REQUIRE(epi.pair_mode != 2 || (epi.act_out && epi.ld_act % 8 == 0), "gemm: bad SwiGLU epilogue");
+  VLA_REQUIRE(!epi.delta_out || (N % 128 == 0 && epi.aux && epi.ldaux % 8 == 0 && epi.delta_L > 0 && M % epi.delta_L == 0 && !epi.aux_mode &&
+                                 !epi.pair_mode && !epi.bias && !epi.gamma && !epi.resid && !epi.act && !epi.out_f32 && !epi.out_group),
+              "gemm: bad delta epilogue (needs N %% 128 == 0, O in aux, M %% delta_L == 0 and no other epilogue option)");
+  return 0;
+}
 }  // namespace
 
 // autotune on: the first call with a new (M,N,K) times all kernel variants (synchronises the stream; warm-up only).
@@ -889,22 +952,20 @@ extern "C" int vla_gemm_set_mode(int ctas, int block_n) {
   return 0;
 }
 
-int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
-                 const GemmEpilogue& epi, cudaStream_t stream) {
-  VLA_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  VLA_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "gemm: leading dims must be multiples of 8 elements");
-  VLA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-              "gemm: operands must be 16-byte aligned");
-  VLA_REQUIRE(!epi.resid || epi.ldr % 8 == 0, "gemm: residual ld must be a multiple of 8");
-  VLA_REQUIRE(!epi.pair_mode || N % 128 == 0, "gemm: pair-mode epilogues need N %% 128 == 0 (got %d)", N);
-  VLA_REQUIRE(!epi.aux_mode || (N % (epi.aux_mode == 1 ? 8 : 32) == 0 && epi.aux && epi.ldaux % 8 == 0),
-              "gemm: aux-mode epilogues need N %% 32 == 0 (GELU backward: N %% 8 == 0) and an aux tensor");
-  VLA_REQUIRE(epi.pair_mode != 1 || (epi.rope_cos && epi.rope_sin && epi.rope_L > 0 && epi.rope_cols % 128 == 0), "gemm: bad RoPE epilogue");
-  VLA_REQUIRE(epi.pair_mode != 2 || (epi.act_out && epi.ld_act % 8 == 0), "gemm: bad SwiGLU epilogue");
-  VLA_REQUIRE(!epi.delta_out || (N % 128 == 0 && epi.aux && epi.ldaux % 8 == 0 && epi.delta_L > 0 && M % epi.delta_L == 0 && !epi.aux_mode &&
-                                 !epi.pair_mode && !epi.bias && !epi.gamma && !epi.resid && !epi.act && !epi.out_f32 && !epi.out_group),
-              "gemm: bad delta epilogue (needs N %% 128 == 0, O in aux, M %% delta_L == 0 and no other epilogue option)");
+// One launch for one problem (p1 == nullptr) or two problems of the same epilogue kind.
+static int gemm_launch(const GemmProblem& p0, const GemmProblem* p1, cudaStream_t stream) {
+  if (int rc = validate(p0)) return rc;
+  int kind = epilogue_kind(p0.epi, p0.N);
+  if (p1) {
+    if (int rc = validate(*p1)) return rc;
+    const int kind1 = epilogue_kind(p1->epi, p1->N);
+    if (kind1 != kind) {   // plain + general (e.g. one N is not a multiple of 32): the general epilogue serves both
+      VLA_REQUIRE((kind == EPI_PLAIN || kind == EPI_GENERAL) && (kind1 == EPI_PLAIN || kind1 == EPI_GENERAL),
+                  "gemm: the two problems of a launch need the same epilogue kind (%d vs %d)", kind, kind1);
+      kind = EPI_GENERAL;
+    }
+    VLA_REQUIRE(!p0.epi.delta_out, "gemm: the delta epilogue is single-problem only");
+  }
   if (g_num_sms == 0) {
     int dev = 0;
     VLA_CHECK_CUDA(cudaGetDevice(&dev));
@@ -914,14 +975,18 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
     g_forced_ctas = 0;
     if (const char* s = getenv("VLA_GEMM_MODE")) sscanf(s, "%d,%d", &g_forced_ctas, &g_forced_n);
   }
+  const bool delta = p0.epi.delta_out != nullptr;
   int ctas = 1, block_n = 256;
   if (g_forced_ctas) {
     ctas = g_forced_ctas;
-    block_n = epi.delta_out ? 256 : g_forced_n;
+    block_n = delta ? 256 : g_forced_n;
   } else {
-    const uint64_t key = (static_cast<uint64_t>(M) << 42) ^ (static_cast<uint64_t>(N) << 21) ^ static_cast<uint64_t>(K) ^
-                         (g_vla_sm_limit > 0 ? (1ull << 62) : 0ull) ^   // the best variant depends on the SM budget
-                         (epi.delta_out ? (1ull << 61) : 0ull);         // and the delta epilogue only has the 256-wide variants
+    auto shape_key = [](const GemmProblem& p) {
+      return (static_cast<uint64_t>(p.M) << 42) ^ (static_cast<uint64_t>(p.N) << 21) ^ static_cast<uint64_t>(p.K);
+    };
+    uint64_t key = shape_key(p0) ^ (g_vla_sm_limit > 0 ? (1ull << 62) : 0ull) ^   // the best variant depends on the SM budget
+                   (delta ? (1ull << 61) : 0ull);                                 // and the delta epilogue only has the 256-wide variants
+    if (p1) key = key * 0x9E3779B97F4A7C15ull + shape_key(*p1) + 1;
     auto it = g_tuned.find(key);
     if (it != g_tuned.end()) {
       ctas = it->second.ctas;
@@ -931,18 +996,18 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
       cudaStreamIsCapturing(stream, &cap);
       Variant best_v = kVariants[0];
       if (g_autotune && cap == cudaStreamCaptureStatusNone) {
-        // First sight of this shape (warm-up): time every variant on the real operands with a plain epilogue into a
-        // scratch-free dry run (output is rewritten by the real launch below), keep the fastest.
+        // First sight of this shape (warm-up): time every variant on the real operands (the outputs are rewritten by the real
+        // launch below), keep the fastest.
         double best_ms = 1e300;
         cudaEvent_t e0, e1;
         VLA_CHECK_CUDA(cudaEventCreate(&e0));
         VLA_CHECK_CUDA(cudaEventCreate(&e1));
         for (const Variant& v : kVariants) {
-          if (epi.delta_out && v.block_n != 256) continue;
+          if (delta && v.block_n != 256) continue;
           float ms_min = 1e30f;
           for (int rep = 0; rep < 4; ++rep) {
             VLA_CHECK_CUDA(cudaEventRecord(e0, stream));
-            if (int rc = launch_variant(v.ctas, v.block_n, A, lda, W, ldw, out, ldc, M, N, K, epi, stream)) return rc;
+            if (int rc = launch_variant(v.ctas, v.block_n, p0, p1, kind, stream)) return rc;
             VLA_CHECK_CUDA(cudaEventRecord(e1, stream));
             VLA_CHECK_CUDA(cudaEventSynchronize(e1));
             float ms = 0.f;
@@ -964,8 +1029,9 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
       } else {
         double best = 1e300;
         for (const Variant& v : kVariants) {
-          if (epi.delta_out && v.block_n != 256) continue;
-          const long tiles = static_cast<long>(ceil_div(M, BLOCK_M * v.ctas)) * ceil_div(N, v.block_n);
+          if (delta && v.block_n != 256) continue;
+          long tiles = static_cast<long>(ceil_div(p0.M, BLOCK_M * v.ctas)) * ceil_div(p0.N, v.block_n);
+          if (p1) tiles += static_cast<long>(ceil_div(p1->M, BLOCK_M * v.ctas)) * ceil_div(p1->N, v.block_n);
           const int sms = (g_vla_sm_limit > 0 && g_vla_sm_limit < g_num_sms) ? g_vla_sm_limit : g_num_sms;
           const long waves = (tiles + sms / v.ctas - 1) / (sms / v.ctas);
           const double t = static_cast<double>(waves) * v.block_n / v.eff;
@@ -979,5 +1045,20 @@ int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* o
       block_n = best_v.block_n;
     }
   }
-  return launch_variant(ctas, block_n, A, lda, W, ldw, out, ldc, M, N, K, epi, stream);
+  return launch_variant(ctas, block_n, p0, p1, kind, stream);
+}
+
+int gemm_bf16_tn(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
+                 const GemmEpilogue& epi, cudaStream_t stream) {
+  GemmProblem p{A, lda, W, ldw, out, ldc, M, N, K, epi};
+  return gemm_launch(p, nullptr, stream);
+}
+
+int gemm_bf16_tn_dual(const GemmProblem& p0, const GemmProblem& p1, cudaStream_t stream) {
+  static const bool off = getenv("VLA_GEMM_DUAL") && atoi(getenv("VLA_GEMM_DUAL")) == 0;   // A/B switch: two launches
+  if (off) {
+    if (int rc = gemm_launch(p0, nullptr, stream)) return rc;
+    return gemm_launch(p1, nullptr, stream);
+  }
+  return gemm_launch(p0, &p1, stream);
 }

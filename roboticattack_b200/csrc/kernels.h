@@ -56,6 +56,26 @@ int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* m
 // optional second output: scaled = bf16(dx * gamma2[col]) (timm LayerScale backward of the branch dx enters next)
 int layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* mean, const float* rstd, const bf16* dres,
                   bf16* dx, int64_t M, int d, cudaStream_t s, const bf16* gamma2 = nullptr, bf16* scaled = nullptr);
+// two independent LayerNorm problems in one launch (the two vision towers at the same depth)
+struct LnFwdProblem {
+  const bf16 *x, *w, *b;
+  bf16* y;
+  float *mean, *rstd;
+  int64_t M;
+  int d;
+};
+struct LnBwdProblem {
+  const bf16 *dy, *x, *w;
+  const float *mean, *rstd;
+  const bf16* dres;
+  bf16* dx;
+  int64_t M;
+  int d;
+  const bf16* gamma2;
+  bf16* scaled;
+};
+int layernorm_fwd2(const LnFwdProblem& p0, const LnFwdProblem& p1, float eps, cudaStream_t s);
+int layernorm_bwd2(const LnBwdProblem& p0, const LnBwdProblem& p1, cudaStream_t s);
 int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int64_t M, int d, float eps, cudaStream_t s);
 int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx, int64_t M,
                 int d, cudaStream_t s);
@@ -130,3 +150,10 @@ int step_begin(const StepState* st, const int* xy_all, const float* th_all, int*
 // scal_hist[st->place] = scal_cur; st->place += 1; st->adam_t += adam_inc
 int step_end(StepState* st, const float* scal_cur, float* scal_hist, int adam_inc, cudaStream_t s);
 int accumulate_f32(float* acc, const float* g, int n, cudaStream_t s);
+
+// ---- greedy decode with the KV cache (decode.cu, elementwise.cu) -------------------------------------------
+int embed_rows(const int* ids, const bf16* table, bf16* x, int B, int d, cudaStream_t s);
+int rope_cache_rows(bf16* qkv, const float* cos_tab, const float* sin_tab, int B, int L, int pos, int H, int hd, cudaStream_t s);
+// qkv = a layer's cache [B*L, 3*H*hd]; query = row b*L + pos; o [B, H*hd]
+int attention_decode(const bf16* qkv, bf16* o, int B, int L, int pos, int H, int hd, cudaStream_t s);
+int argmax_rows(const float* logits, int R, int V, int* ids, int* out, int out_ld, int out_col, cudaStream_t s);

@@ -33,14 +33,10 @@ __device__ __forceinline__ void store8(bf16* p, const float (&x)[8]) {
                                             pack_bf16x2(x[6], x[7]));
 }
 
-__global__ void __launch_bounds__(NORM_THREADS) layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
-                                                                      const bf16* __restrict__ b, bf16* __restrict__ y,
-                                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                                      int d, float eps) {
-  __shared__ float red[32];
-  pdl_trigger();
-  pdl_wait();
-  const int64_t row = blockIdx.x;
+__device__ __forceinline__ void layernorm_fwd_row(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                  const bf16* __restrict__ b, bf16* __restrict__ y,
+                                                  float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                  int d, float eps, const int64_t row, float* red) {
   const int d8 = d / 8;
   float xv[MAX_VEC][8];
   float s = 0.f;
@@ -74,15 +70,47 @@ __global__ void __launch_bounds__(NORM_THREADS) layernorm_fwd_kernel(const bf16*
   });
 }
 
-__global__ void __launch_bounds__(NORM_THREADS) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                                      const bf16* __restrict__ w, const float* __restrict__ mean_in,
-                                                                      const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
-                                                                      bf16* __restrict__ dx, int d, const bf16* __restrict__ gamma2,
-                                                                      bf16* __restrict__ scaled) {
+__global__ void __launch_bounds__(NORM_THREADS) layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                      const bf16* __restrict__ b, bf16* __restrict__ y,
+                                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                      int d, float eps) {
   __shared__ float red[32];
   pdl_trigger();
   pdl_wait();
-  const int64_t row = blockIdx.x;
+  layernorm_fwd_row(x, w, b, y, mean_out, rstd_out, d, eps, blockIdx.x, red);
+}
+
+// Two independent LayerNorm problems in one launch (the DINOv2 and the SigLIP norm of the same depth): rows [0, M0) belong to
+// problem 0, the rest to problem 1.
+struct LnFwdArgs {
+  const bf16 *x, *w, *b;
+  bf16* y;
+  float *mean, *rstd;
+  int d;
+};
+struct LnBwdArgs {
+  const bf16 *dy, *x, *w;
+  const float *mean, *rstd;
+  const bf16* dres;
+  bf16* dx;
+  int d;
+  const bf16* gamma2;
+  bf16* scaled;
+};
+__global__ void __launch_bounds__(NORM_THREADS) layernorm_fwd2_kernel(const LnFwdArgs a0, const LnFwdArgs a1, int M0, float eps) {
+  __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
+  const bool second = static_cast<int>(blockIdx.x) >= M0;
+  const LnFwdArgs& a = second ? a1 : a0;
+  layernorm_fwd_row(a.x, a.w, a.b, a.y, a.mean, a.rstd, a.d, eps, second ? blockIdx.x - M0 : blockIdx.x, red);
+}
+
+__device__ __forceinline__ void layernorm_bwd_row(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                  const bf16* __restrict__ w, const float* __restrict__ mean_in,
+                                                  const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
+                                                  bf16* __restrict__ dx, int d, const bf16* __restrict__ gamma2,
+                                                  bf16* __restrict__ scaled, const int64_t row, float* red) {
   const int d8 = d / 8;
   const float mean = mean_in[row], rstd = rstd_in[row];
   float g[MAX_VEC][8], xh[MAX_VEC][8];
@@ -127,6 +155,25 @@ __global__ void __launch_bounds__(NORM_THREADS) layernorm_bwd_kernel(const bf16*
       store8(scaled + row * d + v * 8, sc);
     }
   });
+}
+
+__global__ void __launch_bounds__(NORM_THREADS) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                      const bf16* __restrict__ w, const float* __restrict__ mean_in,
+                                                                      const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
+                                                                      bf16* __restrict__ dx, int d, const bf16* __restrict__ gamma2,
+                                                                      bf16* __restrict__ scaled) {
+  __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
+  layernorm_bwd_row(dy, x, w, mean_in, rstd_in, dres, dx, d, gamma2, scaled, blockIdx.x, red);
+}
+__global__ void __launch_bounds__(NORM_THREADS) layernorm_bwd2_kernel(const LnBwdArgs a0, const LnBwdArgs a1, int M0) {
+  __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
+  const bool second = static_cast<int>(blockIdx.x) >= M0;
+  const LnBwdArgs& a = second ? a1 : a0;
+  layernorm_bwd_row(a.dy, a.x, a.w, a.mean, a.rstd, a.dres, a.dx, a.d, a.gamma2, a.scaled, second ? blockIdx.x - M0 : blockIdx.x, red);
 }
 
 __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
@@ -219,6 +266,29 @@ int layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* mea
   VLA_REQUIRE((gamma2 == nullptr) == (scaled == nullptr), "layernorm_bwd: gamma2 and scaled go together");
   VLA_CHECK_CUDA(vla_launch(layernorm_bwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, dy, x, w, mean, rstd, dres, dx, d,
                             gamma2, scaled));
+  VLA_LAUNCH_CHECK();
+  ++g_vla_launch_count;
+  return 0;
+}
+int layernorm_fwd2(const LnFwdProblem& p0, const LnFwdProblem& p1, float eps, cudaStream_t s) {
+  if (int rc = check_dims(p0.M, p0.d, "layernorm_fwd2")) return rc;
+  if (int rc = check_dims(p1.M, p1.d, "layernorm_fwd2")) return rc;
+  const LnFwdArgs a0{p0.x, p0.w, p0.b, p0.y, p0.mean, p0.rstd, p0.d}, a1{p1.x, p1.w, p1.b, p1.y, p1.mean, p1.rstd, p1.d};
+  VLA_CHECK_CUDA(vla_launch(layernorm_fwd2_kernel, dim3(static_cast<unsigned>(p0.M + p1.M)), dim3(NORM_THREADS), 0, s, a0, a1,
+                            static_cast<int>(p0.M), eps));
+  VLA_LAUNCH_CHECK();
+  ++g_vla_launch_count;
+  return 0;
+}
+int layernorm_bwd2(const LnBwdProblem& p0, const LnBwdProblem& p1, cudaStream_t s) {
+  if (int rc = check_dims(p0.M, p0.d, "layernorm_bwd2")) return rc;
+  if (int rc = check_dims(p1.M, p1.d, "layernorm_bwd2")) return rc;
+  VLA_REQUIRE((p0.gamma2 == nullptr) == (p0.scaled == nullptr) && (p1.gamma2 == nullptr) == (p1.scaled == nullptr),
+              "layernorm_bwd2: gamma2 and scaled go together");
+  const LnBwdArgs a0{p0.dy, p0.x, p0.w, p0.mean, p0.rstd, p0.dres, p0.dx, p0.d, p0.gamma2, p0.scaled},
+      a1{p1.dy, p1.x, p1.w, p1.mean, p1.rstd, p1.dres, p1.dx, p1.d, p1.gamma2, p1.scaled};
+  VLA_CHECK_CUDA(vla_launch(layernorm_bwd2_kernel, dim3(static_cast<unsigned>(p0.M + p1.M)), dim3(NORM_THREADS), 0, s, a0, a1,
+                            static_cast<int>(p0.M)));
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;

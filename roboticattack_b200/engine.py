@@ -55,10 +55,11 @@ def _c_config(cfg: OpenVLAConfig) -> _lib.Config:
 
 
 class NcclComm:
-    """Owner of a ``vla_comm`` handle."""
+    """A ``vla_comm`` handle.  It belongs to the engine that made it (``VLAEngine.make_comm`` hands out ONE communicator per
+    engine and destroys it with the engine, after the CUDA graphs that recorded its all-reduce)."""
 
-    def __init__(self, lib, handle, world):
-        self._lib, self.handle, self.world = lib, handle, world
+    def __init__(self, lib, handle, world, engine=None):
+        self._lib, self.handle, self.world, self._engine = lib, handle, world, engine
 
     def all_reduce_(self, t):
         """In-place sum over ranks of a float32 device tensor on the current stream (``vla_allreduce_patch_grad``)."""
@@ -66,12 +67,15 @@ class NcclComm:
         _lib.check(self._lib.vla_allreduce_patch_grad(self.handle, _lib.ptr(t), t.numel(), _lib.cur_stream()), "vla_allreduce_patch_grad")
 
     def close(self):
+        """Destroy the communicator (all ranks must call it).  The engine's recorded graphs go first: NCCL blocks the destruction
+        of a communicator while a graph still holds its collectives."""
         if self.handle:
+            eng = self._engine() if self._engine is not None else None
+            if eng is not None and getattr(eng, "_h", None):
+                eng.drop_graphs()
+                eng._comm = None
             self._lib.vla_comm_destroy(self.handle)
             self.handle = None
-
-    def __del__(self):
-        self.close()
 
 
 class VLAEngine:
@@ -121,6 +125,8 @@ class VLAEngine:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
+            # the communicator is NOT destroyed here: ncclCommDestroy is a collective, and garbage collection is not a point all
+            # ranks reach together; call comm.close() explicitly (or leave it to process exit)
             self._lib.vla_engine_destroy(h)
             self._h = None
 
@@ -210,6 +216,9 @@ class VLAEngine:
         initialised ``torch.distributed`` group (host-side plumbing only).  ``None`` for a single process."""
         if world <= 1:
             return None
+        if getattr(self, "_comm", None) is not None and self._comm.handle and self._comm.world == world:
+            return self._comm
+        import weakref
         import torch.distributed as dist
         idbuf = (ctypes.c_uint8 * _lib.COMM_ID_BYTES)()
         if rank == 0:
@@ -220,7 +229,11 @@ class VLAEngine:
         h = c_void_p()
         torch.cuda.set_device(self.device)
         _lib.check(self._lib.vla_comm_create(idbuf, rank, world, byref(h)), "vla_comm_create")
-        return NcclComm(self._lib, h, world)
+        self._comm = NcclComm(self._lib, h, world, weakref.ref(self))
+        return self._comm
+
+    def drop_graphs(self):
+        _lib.check(self._lib.vla_engine_drop_graphs(self._h), "vla_engine_drop_graphs")
 
     def attack_step(self, patch, m, v, dpatch, scalars_hist, pred_ids, fe_mode, loss: LossSpec, lr, opt_kind=_lib.OPT_ADAMW,
                     clip_l1=0.0, accumulate=None, comm=None, do_update=True, graph=True, betas=(0.9, 0.999), eps=1e-6):
@@ -232,6 +245,12 @@ class VLAEngine:
         _lib.check(self._lib.vla_attack_step(self._h, _lib.ptr(patch), _lib.ptr(m), _lib.ptr(v), _lib.ptr(dpatch),
                                              _lib.ptr(accumulate), byref(sp), comm.handle if comm is not None else None,
                                              _lib.ptr(scalars_hist), _lib.ptr(pred_ids), _lib.cur_stream()), "vla_attack_step")
+
+    def decode_greedy(self, prompt_len: int, n_tokens: int, tokens):
+        """KV-cache greedy decode after a forward-only prefill (``vla_engine_decode_greedy``); tokens int32 [B, n_tokens] (device)."""
+        assert tokens.dtype == torch.int32 and tokens.is_cuda and tuple(tokens.shape) == (self.B, n_tokens) and tokens.is_contiguous()
+        _lib.check(self._lib.vla_engine_decode_greedy(self._h, int(prompt_len), int(n_tokens), _lib.ptr(tokens), _lib.cur_stream()),
+                   "vla_engine_decode_greedy")
 
     @property
     def graph_kernel_nodes(self) -> int:

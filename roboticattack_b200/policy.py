@@ -2,9 +2,9 @@
 
 Mirrors ``OpenVLAForActionPrediction.predict_action`` (prismatic/extern/hf/modeling_prismatic.py:506-536): append the
 empty token 29871 when missing, generate ``action_dim`` tokens greedily, map token ids to bin centres
-(``vocab_size - id``, clip, centres) and un-normalise with the dataset statistics.  HF ``generate`` re-uses a KV cache;
-here every token is one forward-only pass of the engine over the (short, <= 300 position) sequence -- at batch 1 both are
-bound by one sweep over the 15 GB of weights per token.  The image is expected to carry the patch already
+(``vocab_size - id``, clip, centres) and un-normalise with the dataset statistics.  Like HF ``generate`` the decode
+re-uses a KV cache: one prefill pass of the engine over image + prompt, then one single-position step per further token
+(``vla_engine_decode_greedy``: M = batch GEMMs against the cached k / v rows).  The image is expected to carry the patch already
 (``RandomPatchTransform.simulation_random_patch``), so the front end runs in its no-patch mode (``im_process``).
 """
 from __future__ import annotations
@@ -29,9 +29,12 @@ class ActionPolicy:
 
     # -- token level ---------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def generate_action_tokens(self, images_u8: torch.Tensor, input_ids: torch.Tensor, n_tokens: int = 7) -> np.ndarray:
+    def generate_action_tokens(self, images_u8: torch.Tensor, input_ids: torch.Tensor, n_tokens: int = 7, kv_cache: bool = True) -> np.ndarray:
         """images_u8 uint8 [B,H,W,3], input_ids int64 [B,T0] (un-padded prompts of equal length) -> int64 [B, n_tokens]:
-        argmax over the full vocabulary at every step, as ``generate(do_sample=False)`` does."""
+        argmax over the full vocabulary at every step, as ``generate(do_sample=False)`` does.  One prefill pass over the prompt
+        and the image, then ``n_tokens - 1`` single-position steps on the KV cache the prefill left in the engine's arena
+        (``vla_engine_decode_greedy``); ``kv_cache=False`` re-runs the full forward for every token (round-1 path, kept as
+        the cross-check of the cache)."""
         eng = self.engine
         ids0 = input_ids.to(torch.int64).cpu()
         B, T0 = ids0.shape
@@ -46,10 +49,13 @@ class ActionPolicy:
         theta = np.zeros((1, B, 2, 3), dtype=np.float32)
         gen = torch.zeros(B, 0, dtype=torch.int64)
         obs = images_u8.contiguous()
-        for k in range(n_tokens):
-            cur = T0 + k                             # tokens known so far; the row of position cur - 1 predicts the next one
+        ce = LossSpec(_lib.LOSS_CE, ce_scale=1.0)
+
+        def forward(known):
+            """Full forward over the ``known`` tokens; the logits row of the last known position is the supervised row."""
+            cur = known.shape[1]
             ids = torch.full((B, T), PAD_TOKEN_ID, dtype=torch.int64)
-            ids[:, :cur] = torch.cat([ids0, gen], dim=1)
+            ids[:, :cur] = known
             ids[:, cur] = DUMMY_LABEL
             mask = torch.zeros(B, T, dtype=torch.bool)
             mask[:, :cur + 1] = True
@@ -58,7 +64,15 @@ class ActionPolicy:
             R = eng.set_batch(obs, ids, mask, labels)
             assert R == B, (R, B)
             eng.set_placements(xy, theta)
-            eng.fwd_bwd(zeros_patch, 0, _lib.FE_NONE, LossSpec(_lib.LOSS_CE, ce_scale=1.0), dpatch, scal, pred, forward_only=True)
+            eng.fwd_bwd(zeros_patch, 0, _lib.FE_NONE, ce, dpatch, scal, pred, forward_only=True)
+
+        if kv_cache:
+            forward(ids0)                            # prefill: image + prompt, KV cache left in the arena
+            toks = torch.zeros(B, n_tokens, dtype=torch.int32, device=dev)
+            eng.decode_greedy(T0, n_tokens, toks)
+            return toks.cpu().to(torch.int64).numpy()
+        for k in range(n_tokens):
+            forward(torch.cat([ids0, gen], dim=1))
             logits = eng.tap("logits", dtype=torch.float32, max_elems=B * self.engine.cfg.llm.vocab).view(B, -1)
             nxt = logits.argmax(dim=1).cpu().to(torch.int64)
             gen = torch.cat([gen, nxt[:, None]], dim=1)
