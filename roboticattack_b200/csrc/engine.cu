@@ -436,6 +436,26 @@ int G(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t
   return gemm_bf16_tn(A, lda, W, ldw, out, ldc, static_cast<int>(M), N, K, ep, s);
 }
 
+// Wave quantisation of the two widest Llama GEMMs: with 256 x 256 CTA-pair tiles on 74 SM pairs, gate|up (9 x 86 = 774 tiles =
+// 10.46 waves) and the SwiGLU-backward GEMM (9 x 43 = 387 tiles = 5.23 waves) leave 40 / 57 pairs idle for a whole tile time in
+// their last wave.  The leftover column blocks are issued as a second launch with 128-wide tiles (twice as many, half as long:
+// all pairs busy for half a tile time).  Returns the number of output columns of the main launch (a multiple of 256; N when
+// splitting does not pay).  Same tiles' arithmetic either way: results are bit-identical.
+int split_tail_n(int64_t M, int N) {
+  static const bool off = getenv("VLA_TAIL_SPLIT") && atoi(getenv("VLA_TAIL_SPLIT")) == 0;
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int units = sms / 2;
+  if (off || units <= 0 || N % 256 != 0 || M <= 256) return N;
+  const int mb = static_cast<int>((M + 255) / 256), nb = N / 256;
+  const int tiles = mb * nb, rem = tiles % units;
+  if (tiles < 3 * units || rem == 0 || 2 * rem > units) return N;   // only long GEMMs whose last wave is less than half full
+  const int tail_nb = (rem + mb - 1) / mb;                          // column blocks that make up the partial wave
+  if (2 * tail_nb * mb > units + mb) return N;                      // the 128-wide tail must fit one wave (about)
+  return (nb - tail_nb) * 256;
+}
+
 // ---- vision tower -----------------------------------------------------------------------------------------
 int vit_forward(vla_engine* e, int t, Transients& tr, cudaStream_t s) {
   const VitDims& v = e->vit[t];
@@ -1144,7 +1164,14 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
       ep.pair_mode = 2;
       ep.act_out = e->tr[0].wide;
       ep.ld_act = f;
-      CK(G(e->tr[0].norm, h, w.gu, h, la.gu[l], 2 * f, ML, 2 * f, h, ep, s));
+      const int n1 = split_tail_n(ML, 2 * f);
+      CK(G(e->tr[0].norm, h, w.gu, h, la.gu[l], 2 * f, ML, n1, h, ep, s));
+      if (n1 < 2 * f) {   // leftover column blocks: 128-wide tiles (see split_tail_n); packed column c <-> activation column c / 2
+        ep.act_out = e->tr[0].wide + n1 / 2;
+        ep.force_ctas = 2;
+        ep.force_block_n = 128;
+        CK(G(e->tr[0].norm, h, w.gu + static_cast<size_t>(n1) * h, h, la.gu[l] + n1, 2 * f, ML, 2 * f - n1, h, ep, s));
+      }
     }
     {
       GemmEpilogue ep;
@@ -1213,7 +1240,14 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
       ep.aux_mode = 2;
       ep.aux = la.gu[l];
       ep.ldaux = 2 * f;
-      CK(G(dx, h, w.down_t, h, e->tr[0].wide2, 2 * f, ML, f, h, ep, s));
+      const int n1 = split_tail_n(ML, f);
+      CK(G(dx, h, w.down_t, h, e->tr[0].wide2, 2 * f, ML, n1, h, ep, s));
+      if (n1 < f) {   // leftover column blocks with 128-wide tiles; d(act) column c <-> packed gate|up column 2 c
+        ep.aux = la.gu[l] + 2 * n1;
+        ep.force_ctas = 2;
+        ep.force_block_n = 128;
+        CK(G(dx, h, w.down_t + static_cast<size_t>(n1) * h, h, e->tr[0].wide2 + 2 * n1, 2 * f, ML, f - n1, h, ep, s));
+      }
     } else {
       CK(G(dx, h, w.down_t, h, e->tr[0].wide, f, ML, f, h, plain, s));
       CK(swiglu_bwd(e->tr[0].wide, la.gu[l], e->tr[0].wide2, ML, f, s));

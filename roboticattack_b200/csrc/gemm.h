@@ -50,6 +50,9 @@ struct GemmEpilogue {
   //   a plain serial reduction: no atomics, no extra pass over dO and O.  Plain epilogue otherwise; 256-wide tiles only.
   float* delta_out = nullptr;
   int delta_L = 0;
+  // pin the kernel variant of THIS launch (0 = automatic): used by the engine for the 128-wide tail launch of a GEMM whose
+  // tile count leaves most of the last wave idle (see split_tail_n in engine.cu)
+  int force_ctas = 0, force_block_n = 0;
 };
 
 // One problem of a launch.

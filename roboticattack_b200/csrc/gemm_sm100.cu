@@ -835,7 +835,15 @@ struct Variant {
   int ctas, block_n;
   double eff;
 };
-constexpr Variant kVariants[] = {{2, 256, 0.92}, {2, 128, 0.80}, {1, 256, 0.76}, {1, 128, 0.66}};
+// The 64- and 32-wide single-CTA variants exist for M <= 128 (the M = batch GEMMs of the greedy decode and the supervised-row
+// GEMMs of the last decoder layer): such a launch streams the whole weight matrix once and has only N / BLOCK_N tiles, so
+// narrow tiles are what puts every SM (and the full HBM bandwidth) to work; plain / general epilogues only.
+constexpr Variant kVariants[] = {{2, 256, 0.92}, {2, 128, 0.80}, {1, 256, 0.76}, {1, 128, 0.66}, {1, 64, 0.40}, {1, 32, 0.25}};
+inline bool variant_allowed(const Variant& v, int M, int kind, bool delta) {
+  if (delta && v.block_n != 256) return false;
+  if (v.block_n < 128) return M <= 128 && (kind == EPI_PLAIN || kind == EPI_GENERAL);
+  return true;
+}
 
 }  // namespace
 
@@ -909,6 +917,12 @@ int launch_variant(int ctas, int block_n, const GemmProblem& p0, const GemmProbl
     gg.tiles1 = 0;
   }
   if (ctas == 2) return block_n == 256 ? launch_gemm<256, 2>(kind, maps, gg, stream) : launch_gemm<128, 2>(kind, maps, gg, stream);
+  if (block_n == 64 || block_n == 32) {
+    VLA_REQUIRE(kind == EPI_PLAIN || kind == EPI_GENERAL, "gemm: the narrow-tile variants take the plain / general epilogues only");
+    if (block_n == 64)
+      return kind == EPI_PLAIN ? launch_gemm_epi<64, 1, EPI_PLAIN>(maps, gg, stream) : launch_gemm_epi<64, 1, EPI_GENERAL>(maps, gg, stream);
+    return kind == EPI_PLAIN ? launch_gemm_epi<32, 1, EPI_PLAIN>(maps, gg, stream) : launch_gemm_epi<32, 1, EPI_GENERAL>(maps, gg, stream);
+  }
   return block_n == 256 ? launch_gemm<256, 1>(kind, maps, gg, stream) : launch_gemm<128, 1>(kind, maps, gg, stream);
 }
 std::unordered_map<uint64_t, Variant> g_tuned;   // shape(s) -> fastest variant measured on this device
@@ -945,7 +959,8 @@ extern "C" int vla_gemm_set_autotune(int on) {
 static int g_forced_ctas = -1, g_forced_n = 0;
 // pin one kernel variant (ctas in {1,2}, block_n in {128,256}); (0,0) restores the automatic choice
 extern "C" int vla_gemm_set_mode(int ctas, int block_n) {
-  VLA_REQUIRE((ctas == 0 && block_n == 0) || ((ctas == 1 || ctas == 2) && (block_n == 128 || block_n == 256)),
+  VLA_REQUIRE((ctas == 0 && block_n == 0) || ((ctas == 1 || ctas == 2) && (block_n == 128 || block_n == 256)) ||
+                  (ctas == 1 && (block_n == 64 || block_n == 32)),
               "vla_gemm_set_mode: bad variant (%d, %d)", ctas, block_n);
   g_forced_ctas = ctas;
   g_forced_n = block_n;
@@ -980,6 +995,9 @@ static int gemm_launch(const GemmProblem& p0, const GemmProblem* p1, cudaStream_
   if (g_forced_ctas) {
     ctas = g_forced_ctas;
     block_n = delta ? 256 : g_forced_n;
+  } else if (p0.epi.force_ctas) {
+    ctas = p0.epi.force_ctas;
+    block_n = p0.epi.force_block_n;
   } else {
     auto shape_key = [](const GemmProblem& p) {
       return (static_cast<uint64_t>(p.M) << 42) ^ (static_cast<uint64_t>(p.N) << 21) ^ static_cast<uint64_t>(p.K);
@@ -1003,7 +1021,7 @@ static int gemm_launch(const GemmProblem& p0, const GemmProblem* p1, cudaStream_
         VLA_CHECK_CUDA(cudaEventCreate(&e0));
         VLA_CHECK_CUDA(cudaEventCreate(&e1));
         for (const Variant& v : kVariants) {
-          if (delta && v.block_n != 256) continue;
+          if (!variant_allowed(v, p1 ? 1 << 30 : p0.M, kind, delta)) continue;
           float ms_min = 1e30f;
           for (int rep = 0; rep < 4; ++rep) {
             VLA_CHECK_CUDA(cudaEventRecord(e0, stream));
@@ -1029,7 +1047,7 @@ static int gemm_launch(const GemmProblem& p0, const GemmProblem* p1, cudaStream_
       } else {
         double best = 1e300;
         for (const Variant& v : kVariants) {
-          if (delta && v.block_n != 256) continue;
+          if (!variant_allowed(v, p1 ? 1 << 30 : p0.M, kind, delta)) continue;
           long tiles = static_cast<long>(ceil_div(p0.M, BLOCK_M * v.ctas)) * ceil_div(p0.N, v.block_n);
           if (p1) tiles += static_cast<long>(ceil_div(p1->M, BLOCK_M * v.ctas)) * ceil_div(p1->N, v.block_n);
           const int sms = (g_vla_sm_limit > 0 && g_vla_sm_limit < g_num_sms) ? g_vla_sm_limit : g_num_sms;

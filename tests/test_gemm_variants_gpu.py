@@ -48,16 +48,19 @@ def rand(shape, scale, seed):
     return (torch.randn(*shape, device="cuda", generator=g) * scale).bfloat16()
 
 
-def close(got, ref, ulps, what, mean_ulps=0.25):
+def close(got, ref, ulps, what, mean_ulps=0.25, mag=None):
     """Element-wise: |got - ref| <= ulps x (the bf16 spacing at the element's own magnitude, 2^-7 |ref|) + fp32 accumulation
-    noise (2^-16 of the tensor scale); a result that rounds the other way at a bf16 tie is 1 spacing off.  Plus a bound on
-    the mean error in units of 2^-8 x the tensor scale."""
+    noise (2^-16 of the tensor scale); a result that rounds the other way at a bf16 tie is 1 spacing off.  Where the output is
+    a SUM of bf16 terms (rotary products, residual add) a flipped rounding of a term shows at the term's magnitude, not the
+    (possibly cancelling) sum's: `mag` = element-wise magnitude of the largest term.  Plus a bound on the mean error in units
+    of 2^-8 x the tensor scale."""
     got, ref = got.float(), ref.float()
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     assert torch.isfinite(got).all(), f"{what}: non-finite output"
     scale = ref.abs().max().item() + 1e-12
     err = (got - ref).abs()
-    tol = ulps * (2.0 ** -7 * ref.abs() + 2.0 ** -16 * scale)
+    m = ref.abs() if mag is None else torch.maximum(ref.abs(), mag.float().abs())
+    tol = ulps * (2.0 ** -7 * m + 2.0 ** -16 * scale)
     excess = (err - tol).max().item()
     assert excess <= 0, f"{what}: worst excess over {ulps} bf16 spacings: {excess:.4g} (max err {err.max().item():.4g}, scale {scale:.4g})"
     assert err.mean().item() <= mean_ulps * BF16_ULP * scale, f"{what}: mean err {err.mean().item() / scale / BF16_ULP:.3f} ulp of scale"
@@ -117,7 +120,9 @@ def test_rope_epilogue(variant):
     r1 = rbf(x1 * c) + rbf(-x2 * s)                 # q * cos + rotate_half(q) * sin, each product a bf16 tensor
     r2 = rbf(x2 * c) + rbf(x1 * s)
     ref = torch.cat([torch.cat([r1, r2], -1), y[:, 2:]], 1).reshape(M, N)
-    close(out, rbf(ref), 2.0, "rope q|k|v")
+    big = torch.maximum(x1.abs(), x2.abs())
+    mag = torch.cat([torch.cat([big, big], -1), y[:, 2:].abs()], 1).reshape(M, N)
+    close(out, rbf(ref), 2.0, "rope q|k|v", mag=mag)
     close(out[:, 8192:], rbf(lin(A, W))[:, 8192:], 1.01, "v passes through")
 
 
@@ -202,7 +207,7 @@ def test_general_epilogue_residual_layerscale_and_row_remap(variant):
     gemm(A, W, out, M, N, K, bias=b, gamma=gm, resid=r, ldr=N)
     x = rbf(lin(A, W) + b.float())
     x = rbf(x * gm.float())
-    close(out, rbf(r.float() + x), 1.5, "fc2 + LayerScale + residual")
+    close(out, rbf(r.float() + x), 1.5, "fc2 + LayerScale + residual", mag=torch.maximum(r.float().abs(), x.abs()))
     # patch embed: conv-as-GEMM rows [8 x 256] written past the 5 prefix tokens of each sample, + pos_embed broadcast over the batch
     Bn, P, npre, d, Kp = 8, 256, 5, 1024, 640
     A, W, b = rand((Bn * P, Kp), 0.5, 28), rand((d, Kp), Kp ** -0.5, 29), rand((d,), 0.2, 30)
@@ -212,4 +217,39 @@ def test_general_epilogue_residual_layerscale_and_row_remap(variant):
     ref = rbf(pos.float()[None] + rbf(lin(A, W) + b.float()).view(Bn, P, d))
     got = tok.view(Bn, P + npre, d)
     assert got[:, :npre].abs().max().item() == 0, "prefix-token rows must not be written"
-    close(got[:, npre:], ref, 1.5, "patch embed + pos_embed, remapped rows")
+    close(got[:, npre:], ref, 1.5, "patch embed + pos_embed, remapped rows",
+          mag=torch.maximum(pos.float().abs()[None].expand_as(ref), rbf(lin(A, W) + b.float()).view(Bn, P, d).abs()))
+
+
+@pytest.mark.parametrize("block_n", [64, 32])
+@pytest.mark.parametrize("M", [1, 8, 32, 100])
+def test_narrow_tile_variants_for_small_m(block_n, M):
+    """The 64- / 32-wide single-CTA tiles of the M = batch GEMMs (greedy decode, supervised rows of the last decoder layer):
+    plain, general (bias + residual, fp32 logits) and the cache-row remap of the decode's q|k|v projection."""
+    _lib.check(L.vla_gemm_set_mode(1, block_n))
+    try:
+        K, N = 4096, 4096
+        A, W = rand((M, K), 0.5, 40 + M), rand((N, K), K ** -0.5, 41)
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        gemm(A, W, out, M, N, K)
+        close(out, rbf(lin(A, W)), 1.01, f"plain M={M}")
+        b, r = rand((N,), 0.2, 42), rand((M, N), 1.0, 43)
+        gemm(A, W, out, M, N, K, bias=b, resid=r, ldr=N)
+        x = rbf(lin(A, W) + b.float())
+        close(out, rbf(r.float() + x), 1.5, f"bias + residual M={M}", mag=torch.maximum(r.float().abs(), x.abs()))
+        V = 32064
+        Wv = rand((V, K), K ** -0.5, 44)
+        of = torch.full((M, V), float("nan"), device="cuda", dtype=torch.float32)
+        gemm(A, Wv, of, M, V, K, out_f32=1)
+        assert torch.equal(of, rbf(of))
+        close(of, rbf(lin(A, Wv)), 1.01, f"fp32 logits M={M}")
+        # decode: row r of the result lands in cache row r * Lc + pos
+        Lc, pos, N3 = 40, 17, 3 * 1024
+        W3 = rand((N3, K), K ** -0.5, 45)
+        cache = torch.zeros(M * Lc, N3, device="cuda", dtype=torch.bfloat16)
+        gemm(A, W3, cache, M, N3, K, out_group=1, out_stride=Lc, out_offset=pos)
+        got = cache.view(M, Lc, N3)
+        close(got[:, pos], rbf(lin(A, W3)), 1.01, f"cache-row remap M={M}")
+        assert got[:, :pos].abs().max().item() == 0 and got[:, pos + 1:].abs().max().item() == 0
+    finally:
+        L.vla_gemm_set_mode(0, 0)
