@@ -138,3 +138,88 @@ int argmax_rows(const float* logits, int R, int V, int* ids, int* out, int out_l
   ++g_vla_launch_count;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Skinny GEMM for the decode steps: out[m, n] = epilogue(sum_k A[m, k] * W[n, k]) with M <= 4 rows (M = batch of the
+// closed-loop evaluation, 1).  Such a product streams the whole weight matrix for a handful of FLOPs per byte: it is bound by
+// HBM, and a tensor-core tile loop (one barrier round trip and four tcgen05.mma issues per 16 KB of weights) reaches ~2 TB/s
+// on it.  Here one warp owns one output column: it streams the column's weight row with 16-byte loads (8 loads in flight per
+// lane), multiplies with the activation rows (L1-resident) and reduces with shuffles; fp32 accumulation, bf16 rounding points
+// of the general GEMM epilogue (bias -> round -> residual -> round; fp32 output holds bf16 values).
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int GV_WARPS = 8;
+template <int MR>
+__global__ void __launch_bounds__(GV_WARPS * 32) gemv_bf16_kernel(const bf16* __restrict__ A, int64_t lda, const bf16* __restrict__ W,
+                                                                 int64_t ldw, void* __restrict__ out, int64_t ldc, int N, int K,
+                                                                 const bf16* __restrict__ bias, const bf16* __restrict__ resid,
+                                                                 int64_t ldr, int out_f32, int out_stride, int out_offset) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * GV_WARPS + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const bf16* w = W + static_cast<int64_t>(n) * ldw;
+  float acc[MR];
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = 0.f;
+  const int K8 = K / 8;
+  constexpr int UN = 8;
+  for (int c0 = lane; c0 < K8; c0 += 32 * UN) {
+    uint4 wv[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int c = c0 + u * 32;
+      wv[u] = c < K8 ? __ldcs(reinterpret_cast<const uint4*>(w) + c) : make_uint4(0u, 0u, 0u, 0u);   // streamed once: evict first
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int c = c0 + u * 32;
+      if (c >= K8) break;
+      const uint32_t ww[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+#pragma unroll
+      for (int m = 0; m < MR; ++m) {
+        const uint4 av = __ldg(reinterpret_cast<const uint4*>(A + m * lda) + c);
+        const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 a = unpack_bf16x2(aw[t]), b = unpack_bf16x2(ww[t]);
+          acc[m] = fmaf(a.x, b.x, acc[m]);
+          acc[m] = fmaf(a.y, b.y, acc[m]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = warp_sum(acc[m]);
+  if (lane == 0) {
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+      float v = acc[m];
+      if (bias) v += b2f(bias[n]);
+      v = rbf(v);
+      if (resid) v = rbf(b2f(resid[m * ldr + n]) + v);
+      const int64_t row = out_stride ? static_cast<int64_t>(m) * out_stride + out_offset : m;
+      if (out_f32) static_cast<float*>(out)[row * ldc + n] = v;
+      else static_cast<bf16*>(out)[row * ldc + n] = f2b(v);
+    }
+  }
+}
+}  // namespace
+
+bool gemv_supported(int M, int K, int64_t lda, int64_t ldw) { return M >= 1 && M <= 4 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0; }
+
+// out row m -> m * out_stride + out_offset when out_stride > 0 (the decode's cache-row remap), else m
+int gemv_bf16(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K, const bf16* bias,
+              const bf16* resid, int64_t ldr, int out_f32, int out_stride, int out_offset, cudaStream_t s) {
+  VLA_REQUIRE(gemv_supported(M, K, lda, ldw), "gemv: needs 1 <= M <= 4 and K, lda, ldw multiples of 8 (M=%d K=%d)", M, K);
+  VLA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemv: operands must be 16-byte aligned");
+  const dim3 grid(ceil_div(N, GV_WARPS)), block(GV_WARPS * 32);
+  switch (M) {
+    case 1: gemv_bf16_kernel<1><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset); break;
+    case 2: gemv_bf16_kernel<2><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset); break;
+    case 3: gemv_bf16_kernel<3><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset); break;
+    default: gemv_bf16_kernel<4><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset); break;
+  }
+  VLA_LAUNCH_CHECK();
+  ++g_vla_launch_count;
+  return 0;
+}

@@ -436,26 +436,6 @@ int G(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t
   return gemm_bf16_tn(A, lda, W, ldw, out, ldc, static_cast<int>(M), N, K, ep, s);
 }
 
-// Wave quantisation of the two widest Llama GEMMs: with 256 x 256 CTA-pair tiles on 74 SM pairs, gate|up (9 x 86 = 774 tiles =
-// 10.46 waves) and the SwiGLU-backward GEMM (9 x 43 = 387 tiles = 5.23 waves) leave 40 / 57 pairs idle for a whole tile time in
-// their last wave.  The leftover column blocks are issued as a second launch with 128-wide tiles (twice as many, half as long:
-// all pairs busy for half a tile time).  Returns the number of output columns of the main launch (a multiple of 256; N when
-// splitting does not pay).  Same tiles' arithmetic either way: results are bit-identical.
-int split_tail_n(int64_t M, int N) {
-  static const bool off = getenv("VLA_TAIL_SPLIT") && atoi(getenv("VLA_TAIL_SPLIT")) == 0;
-  int sms = 0, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int units = sms / 2;
-  if (off || units <= 0 || N % 256 != 0 || M <= 256) return N;
-  const int mb = static_cast<int>((M + 255) / 256), nb = N / 256;
-  const int tiles = mb * nb, rem = tiles % units;
-  if (tiles < 3 * units || rem == 0 || 2 * rem > units) return N;   // only long GEMMs whose last wave is less than half full
-  const int tail_nb = (rem + mb - 1) / mb;                          // column blocks that make up the partial wave
-  if (2 * tail_nb * mb > units + mb) return N;                      // the 128-wide tail must fit one wave (about)
-  return (nb - tail_nb) * 256;
-}
-
 // ---- vision tower -----------------------------------------------------------------------------------------
 int vit_forward(vla_engine* e, int t, Transients& tr, cudaStream_t s) {
   const VitDims& v = e->vit[t];
@@ -1164,14 +1144,7 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
       ep.pair_mode = 2;
       ep.act_out = e->tr[0].wide;
       ep.ld_act = f;
-      const int n1 = split_tail_n(ML, 2 * f);
-      CK(G(e->tr[0].norm, h, w.gu, h, la.gu[l], 2 * f, ML, n1, h, ep, s));
-      if (n1 < 2 * f) {   // leftover column blocks: 128-wide tiles (see split_tail_n); packed column c <-> activation column c / 2
-        ep.act_out = e->tr[0].wide + n1 / 2;
-        ep.force_ctas = 2;
-        ep.force_block_n = 128;
-        CK(G(e->tr[0].norm, h, w.gu + static_cast<size_t>(n1) * h, h, la.gu[l] + n1, 2 * f, ML, 2 * f - n1, h, ep, s));
-      }
+      CK(G(e->tr[0].norm, h, w.gu, h, la.gu[l], 2 * f, ML, 2 * f, h, ep, s));
     }
     {
       GemmEpilogue ep;
@@ -1240,14 +1213,7 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
       ep.aux_mode = 2;
       ep.aux = la.gu[l];
       ep.ldaux = 2 * f;
-      const int n1 = split_tail_n(ML, f);
-      CK(G(dx, h, w.down_t, h, e->tr[0].wide2, 2 * f, ML, n1, h, ep, s));
-      if (n1 < f) {   // leftover column blocks with 128-wide tiles; d(act) column c <-> packed gate|up column 2 c
-        ep.aux = la.gu[l] + 2 * n1;
-        ep.force_ctas = 2;
-        ep.force_block_n = 128;
-        CK(G(dx, h, w.down_t + static_cast<size_t>(n1) * h, h, e->tr[0].wide2 + 2 * n1, 2 * f, ML, f - n1, h, ep, s));
-      }
+      CK(G(dx, h, w.down_t, h, e->tr[0].wide2, 2 * f, ML, f, h, ep, s));
     } else {
       CK(G(dx, h, w.down_t, h, e->tr[0].wide, f, ML, f, h, plain, s));
       CK(swiglu_bwd(e->tr[0].wide, la.gu[l], e->tr[0].wide2, ML, f, s));
@@ -1520,6 +1486,23 @@ extern "C" int vla_engine_decode_greedy(vla_engine* e, int prompt_len, int n_tok
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // token 0: the argmax of the prefill's logits row (full vocabulary, as generate() does)
   CK(argmax_rows(e->logits, B, V, e->dec_ids, tokens, n_tokens, 0, s));
+  // M = B projections: the HBM-bound skinny kernel for B <= 4 (the evaluation loop runs B = 1), the tcgen05 GEMM otherwise
+  static const bool no_gemv = getenv("VLA_DECODE_GEMV") && atoi(getenv("VLA_DECODE_GEMV")) == 0;
+  const bool skinny = !no_gemv && gemv_supported(B, h, h, h) && f % 8 == 0;
+  auto linear = [&](const bf16* A, int K, const bf16* W, void* out, int64_t ldc, int N, const bf16* resid, int out_f32, int remap_stride,
+                    int remap_off) -> int {
+    if (skinny) return gemv_bf16(A, K, W, K, out, ldc, B, N, K, nullptr, resid, N, out_f32, remap_stride, remap_off, s);
+    GemmEpilogue ep;
+    ep.resid = resid;
+    ep.ldr = N;
+    ep.out_f32 = out_f32;
+    if (remap_stride) {
+      ep.out_group = 1;
+      ep.out_stride = remap_stride;
+      ep.out_offset = remap_off;
+    }
+    return G(A, K, W, K, out, ldc, B, N, K, ep, s);
+  };
   for (int k = 1; k < n_tokens; ++k) {
     const int pos = P + prompt_len + k - 1;   // cache row (within a sample) of the token generated in the previous step
     bf16* x = e->ll_xs;
@@ -1527,42 +1510,26 @@ extern "C" int vla_engine_decode_greedy(vla_engine* e, int prompt_len, int n_tok
     for (int l = 0; l < c.llm_layers; ++l) {
       const LlamaLayerW& w = e->lw[l];
       CK(rmsnorm_fwd(x, w.n1, e->ll_norm, e->ll_rstd2, B, h, c.rms_eps, s));
-      {   // q|k|v of the new position, written straight into the layer's cache row b * L + pos
-        GemmEpilogue ep;
-        ep.out_group = 1;
-        ep.out_stride = L;
-        ep.out_offset = pos;
-        CK(G(e->ll_norm, h, w.qkv, h, e->la.qkv[l], 3 * h, B, 3 * h, h, ep, s));
-      }
+      // q|k|v of the new position, written straight into the layer's cache row b * L + pos
+      CK(linear(e->ll_norm, h, w.qkv, e->la.qkv[l], 3 * h, 3 * h, nullptr, 0, L, pos));
       CK(rope_cache_rows(e->la.qkv[l], e->rope_cos, e->rope_sin, B, L, pos, NH, hd, s));
       CK(attention_decode(e->la.qkv[l], e->ll_as, B, L, pos, NH, hd, s));
-      {
-        GemmEpilogue ep;
-        ep.resid = x;
-        ep.ldr = h;
-        CK(G(e->ll_as, h, w.o, h, e->ll_xm, h, B, h, h, ep, s));
-      }
+      CK(linear(e->ll_as, h, w.o, e->ll_xm, h, h, x, 0, 0, 0));
       CK(rmsnorm_fwd(e->ll_xm, w.n2, e->ll_norm, e->ll_rstd2, B, h, c.rms_eps, s));
-      {
+      if (skinny) {   // raw gate|up (interleaved packing), then the SwiGLU as its own tiny kernel
+        CK(linear(e->ll_norm, h, w.gu, e->ll_gu, 2 * f, 2 * f, nullptr, 0, 0, 0));
+        CK(swiglu_fwd(e->ll_gu, e->ll_act, B, f, s));
+      } else {
         GemmEpilogue ep;
         ep.pair_mode = 2;
         ep.act_out = e->ll_act;
         ep.ld_act = f;
         CK(G(e->ll_norm, h, w.gu, h, e->ll_gu, 2 * f, B, 2 * f, h, ep, s));
       }
-      {
-        GemmEpilogue ep;
-        ep.resid = e->ll_xm;
-        ep.ldr = h;
-        CK(G(e->ll_act, f, w.down, f, x, h, B, h, f, ep, s));
-      }
+      CK(linear(e->ll_act, f, w.down, x, h, h, e->ll_xm, 0, 0, 0));
     }
     CK(rmsnorm_fwd(x, e->final_norm, e->hn, e->rstd_f, B, h, c.rms_eps, s));
-    {
-      GemmEpilogue ep;
-      ep.out_f32 = 1;
-      CK(G(e->hn, h, e->lm_head, h, e->logits, V, B, V, h, ep, s));
-    }
+    CK(linear(e->hn, h, e->lm_head, e->logits, V, V, nullptr, 1, 0, 0));
     CK(argmax_rows(e->logits, B, V, e->dec_ids, tokens, n_tokens, k, s));
   }
   return 0;

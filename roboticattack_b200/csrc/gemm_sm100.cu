@@ -1004,6 +1004,7 @@ static int gemm_launch(const GemmProblem& p0, const GemmProblem* p1, cudaStream_
     };
     uint64_t key = shape_key(p0) ^ (g_vla_sm_limit > 0 ? (1ull << 62) : 0ull) ^   // the best variant depends on the SM budget
                    (delta ? (1ull << 61) : 0ull);                                 // and the delta epilogue only has the 256-wide variants
+    if (!p1 && p0.M <= 128 && (kind == EPI_PLAIN || kind == EPI_GENERAL)) key ^= 1ull << 60;   // narrow-tile variants are candidates
     if (p1) key = key * 0x9E3779B97F4A7C15ull + shape_key(*p1) + 1;
     auto it = g_tuned.find(key);
     if (it != g_tuned.end()) {

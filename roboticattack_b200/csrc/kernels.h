@@ -157,3 +157,7 @@ int rope_cache_rows(bf16* qkv, const float* cos_tab, const float* sin_tab, int B
 // qkv = a layer's cache [B*L, 3*H*hd]; query = row b*L + pos; o [B, H*hd]
 int attention_decode(const bf16* qkv, bf16* o, int B, int L, int pos, int H, int hd, cudaStream_t s);
 int argmax_rows(const float* logits, int R, int V, int* ids, int* out, int out_ld, int out_col, cudaStream_t s);
+// skinny GEMM of the decode steps (decode.cu): M <= 4, HBM-bound weight streaming on the CUDA cores
+bool gemv_supported(int M, int K, int64_t lda, int64_t ldw);
+int gemv_bf16(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K, const bf16* bias,
+              const bf16* resid, int64_t ldr, int out_f32, int out_stride, int out_offset, cudaStream_t s);
