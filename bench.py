@@ -477,24 +477,26 @@ def engine_arm(args):
     roof = None
     eng.set_single_stream(True)               # per-kernel event timing needs the kernels of a stream back to back
     NPROF = 3                                 # three steps: one step's sum of ~660 event pairs moves by +-5 % from run to run
-    st_p = make_state(B, 1234 + rank, NPROF + 1)
+    st_p = make_state(B, 1234 + rank, NPROF + 4)
     step(st_p, graph=False)
     sync()
     if rank == 0:
         lib.vla_profile_gemm_begin()
-    ar_ms = []
-    for i in range(NPROF):                    # composed from the ABI's parts so that the collective can be bracketed by events
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        eng.fwd_bwd(st_p["patch"], 1 + i, _lib.FE_WARP, loss, st_p["grad"], st_p["hist"][1 + i], st_p["pred"])
-        a0.record()
-        if comm is not None:
-            comm.all_reduce_(st_p["grad"])
-        a1.record()
-        eng.patch_update(st_p["patch"], st_p["grad"], st_p["m"], st_p["v"], 2 + i, lr, grad_scale=1.0 / world, scalars=st_p["hist"][1 + i])
-        ar_ms.append((a0, a1))
-    torch.cuda.synchronize()
-    ar_wait = float(np.mean([a.elapsed_time(b_) for a, b_ in ar_ms]))
-    eng.set_single_stream(False)
+    def composed_steps(first, n, timed):      # composed from the ABI's parts so that the collective can be bracketed by events
+        evs = []
+        for i in range(first, first + n):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            eng.fwd_bwd(st_p["patch"], i, _lib.FE_WARP, loss, st_p["grad"], st_p["hist"][i], st_p["pred"])
+            a0.record()
+            if comm is not None:
+                comm.all_reduce_(st_p["grad"])
+            a1.record()
+            eng.patch_update(st_p["patch"], st_p["grad"], st_p["m"], st_p["v"], 1 + i, lr, grad_scale=1.0 / world, scalars=st_p["hist"][i])
+            evs.append((a0, a1))
+        torch.cuda.synchronize()
+        return float(np.mean([a.elapsed_time(b_) for a, b_ in evs])) if timed else 0.0
+    composed_steps(1, NPROF, False)           # rank 0: per-GEMM events (these steps are slower on rank 0, so they are not the ones
+    eng.set_single_stream(False)              # whose all-reduce wait is reported)
     if rank == 0:
         tm, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
         _lib.check(lib.vla_profile_gemm_end(ctypes.byref(tm), ctypes.byref(fl), ctypes.byref(n)), "profile end")
@@ -519,7 +521,8 @@ def engine_arm(args):
                 "gemm_flops_per_step": fl.value / NPROF, "profiled_steps": NPROF, "algorithmic_flops_per_step": f["iter"] * B,
                 "executed_flops_per_step": f["iter_executed"] * B,   # last decoder layer pruned to the supervised rows (exact)
                 "step_tflops": round(f["iter_executed"] * B / (ms_max / K * 1e-3) / 1e12, 1)}
-    ar_all = gather(ar_wait)
+    sync()
+    ar_all = gather(composed_steps(1 + NPROF, 3, True))   # un-profiled eager steps on every rank: wait for the slowest rank + collective
     sync()
 
     # ---- e2e: the reference-facing plugin class with a PIL loader; every step uploads its batch and reads its results --------

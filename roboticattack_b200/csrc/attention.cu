@@ -602,7 +602,7 @@ int launch_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* ls
 // bit 0: tcgen05 forward (attention_fwd_tc3 for N <= 320, else the streaming attention_fwd_tc2); bit 1: tcgen05 backward.
 // Default 3; VLA_ATTN_IMPL overrides it at first use.
 int g_attn_impl = -1;
-static int attn_impl() {
+int attention_impl() {
   if (g_attn_impl < 0) {
     const char* e = getenv("VLA_ATTN_IMPL");
     g_attn_impl = e ? (atoi(e) & 3) : 3;
@@ -613,8 +613,8 @@ static int attn_impl() {
 int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                   cudaStream_t s) {
   VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
-  if ((attn_impl() & 1) && attention_fwd_tc3_supported(N, hd)) return attention_fwd_tc3(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
-  if ((attn_impl() & 1) && attention_fwd_tc2_supported(N, hd)) return attention_fwd_tc2(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
+  if ((attention_impl() & 1) && attention_fwd_tc3_supported(N, hd)) return attention_fwd_tc3(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
+  if ((attention_impl() & 1) && attention_fwd_tc2_supported(N, hd)) return attention_fwd_tc2(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   if (hd <= 64) return launch_fwd<64>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   if (hd <= 80) return launch_fwd<80>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   return launch_fwd<128>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
@@ -628,7 +628,7 @@ int attention_tile_shift(int N, int causal) {
 }
 
 // true when attention_bwd() can be called with o == NULL and `delta` already holding rowsum(dO * O) per (b, h, n)
-bool attention_bwd_takes_delta(int N, int hd) { return (attn_impl() & 2) && attention_bwd_tc_supported(N, hd); }
+bool attention_bwd_takes_delta(int N, int hd) { return (attention_impl() & 2) && attention_bwd_tc_supported(N, hd); }
 
 int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                   const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
@@ -637,7 +637,7 @@ int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float*
   VLA_REQUIRE(rope_cos == nullptr || (hd == 128 && rope_sin != nullptr && rope_L > 0),
               "attention_bwd: the fused RoPE backward needs head dim 128 and both tables");
   VLA_REQUIRE(o != nullptr || attention_bwd_takes_delta(N, hd), "attention_bwd: a precomputed delta (o == NULL) needs the tcgen05 backward");
-  if ((attn_impl() & 2) && attention_bwd_tc_supported(N, hd))
+  if ((attention_impl() & 2) && attention_bwd_tc_supported(N, hd))
     return attention_bwd_tc(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, rope_cos, rope_sin, rope_L, s);
   if (hd <= 64) return launch_bwd<64>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, nullptr, nullptr, 0, s);
   if (hd <= 80) return launch_bwd<80>(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, nullptr, nullptr, 0, s);

@@ -1403,7 +1403,7 @@ extern "C" int vla_attack_step(vla_engine* e, float* patch, float* exp_avg, floa
     k.patch = patch; k.m = exp_avg; k.v = exp_avg_sq; k.dpatch = dpatch; k.acc = accumulate; k.comm = comm; k.hist = scalars_hist;
     k.pred = pred_ids;
     k.single_stream = e->single_stream ? 1 : 0;
-    k.attn_impl = g_attn_impl;
+    k.attn_impl = attention_impl();
     vla_engine::StepGraph* g = nullptr;
     for (auto& cand : e->graphs)
       if (cand.key.size() == sizeof(k) && memcmp(cand.key.data(), &k, sizeof(k)) == 0) g = &cand;

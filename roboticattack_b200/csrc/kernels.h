@@ -102,6 +102,7 @@ int attention_tile_shift(int N, int causal);   // attention_bwd(o == NULL): delt
 int attention_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                      const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
                      int rope_L, cudaStream_t s);
+int attention_impl();      // resolved kernel selection (default / env VLA_ATTN_IMPL on first use)
 extern int g_attn_impl;   // bit 0 = tcgen05 forward, bit 1 = tcgen05 backward where supported; -1 = unset (default 3 / env)
 // dqkv [B*N, 3*H*hd]; delta scratch [B, H, N] fp32
 // rope_cos / rope_sin (nullable; head dim 128 only): when given, d(q) and d(k) are returned with the rotary embedding's
