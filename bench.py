@@ -447,7 +447,7 @@ def engine_arm(args):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return 0
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local)             # every rank samples its own board (the slowest one paces a data-parallel step)
     launches0, replays0 = lib.vla_launch_count(), lib.vla_graph_replays()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.time()
@@ -459,9 +459,10 @@ def engine_arm(args):
     wall1 = time.time()
     ms_rank = e0.elapsed_time(e1)
     launches, replays = lib.vla_launch_count() - launches0, lib.vla_graph_replays() - replays0
-    clocks = sampler.stop(wall0, wall1) if sampler else None
+    clocks = sampler.stop(wall0, wall1)
     ms_max = max_over_ranks(ms_rank)
     per_rank_ms = gather(ms_rank / K)
+    per_rank_mhz = gather(clocks["sm_mhz"] or 0.0)
     losses = st["hist"][W:W + K, _lib.S_LOSS].cpu()
     assert torch.isfinite(losses).all(), "non-finite loss in the timed region"
     # all ranks must hold bit-identical patches (same reduced gradient, same replicated update; UADA_ddp.py:140-166,206)
@@ -524,6 +525,24 @@ def engine_arm(args):
     sync()
     ar_all = gather(composed_steps(1 + NPROF, 3, True))   # un-profiled eager steps on every rank: wait for the slowest rank + collective
     sync()
+    # the same graph-replayed step WITHOUT the collective: each rank's own pace (attributes the weak-scaling loss: the step of a
+    # data-parallel run is the slowest rank's compute + the collective, and the boards run power-capped at different clocks)
+    uncoupled = None
+    if world > 1:
+        keep, comm = comm, None
+        st_u = make_state(B, 1234 + rank, 14)
+        for _ in range(4):
+            step(st_u)
+        torch.cuda.synchronize()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for _ in range(10):
+            step(st_u)
+        u1.record()
+        torch.cuda.synchronize()
+        comm = keep
+        uncoupled = gather(u0.elapsed_time(u1) / 10)
+        sync()
 
     # ---- e2e: the reference-facing plugin class with a PIL loader; every step uploads its batch and reads its results --------
     Ke = min(K, 20)
@@ -589,10 +608,15 @@ def engine_arm(args):
                 "e2e_innerloop50": e2e50,
                 "gpu_launches": int(launches), "launches_per_step": launches / K, "graph_launches_per_step": replays / K,
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "ref_gpu_path": refgpu, "strong": strong,
-                "per_rank": {"ms_per_step": [round(x, 3) for x in per_rank_ms], "allreduce_wait_ms": [round(x, 4) for x in ar_all],
+                "per_rank": {"ms_per_step": [round(x, 3) for x in per_rank_ms], "sm_mhz": [round(x) for x in per_rank_mhz],
+                             "uncoupled_ms_per_step": None if uncoupled is None else [round(x, 3) for x in uncoupled],
+                             "allreduce_wait_ms_eager": [round(x, 4) for x in ar_all],
                              "patches_bit_identical": patches_identical,
-                             "note": "ms_per_step: each rank's own CUDA-event time of the timed region / K; allreduce_wait_ms: events around "
-                                     "vla_allreduce_patch_grad in eager steps = wait for the slowest rank + the 30 KB collective"},
+                             "note": "ms_per_step: each rank's own CUDA-event time of the timed region / K (coupled by the all-reduce inside the "
+                                     "graph); sm_mhz: each board's median SM clock in that region; uncoupled_ms_per_step: the same graph-replayed "
+                                     "step without the collective, every rank at its own pace (10 steps) -- the coupled step tracks the slowest "
+                                     "rank; allreduce_wait_ms_eager: events around vla_allreduce_patch_grad in eager, Python-driven steps = wait "
+                                     "for the slowest rank + the 30 KB collective"},
                 "loss_first_last": [losses[0].item(), losses[-1].item()]}
         emit(line)
     if world > 1:
