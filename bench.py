@@ -581,7 +581,7 @@ def engine_arm(args):
 
     refgpu = None
     if rank == 0 and world == 1 and not args.no_extras and args.model == "openvla-7b":
-        eng.ensure_plan(1, T)                 # release most of the activation arena's pages? (the arena tensor itself is kept)
+        eng.shrink_plan(1, T)                 # hand the activation arena (82 GB after the bs-64 leg) back before the eager path allocates
         try:
             refgpu = ref_gpu_path(cfg, args, dev)
         except torch.cuda.OutOfMemoryError as ex:     # noqa: PERF203

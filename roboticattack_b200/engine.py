@@ -122,6 +122,16 @@ class VLAEngine:
             self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         self._bind(batch, text_len)
 
+    def shrink_plan(self, batch, text_len):
+        """Re-plan for (batch, text_len) AND give the activation arena back down to that plan's size (``ensure_plan`` only ever
+        grows it): e.g. after a one-off large-batch run."""
+        torch.cuda.synchronize(self.device)
+        need = self._lib.vla_engine_workspace_bytes(self._h, batch, text_len)
+        self.workspace = None
+        torch.cuda.empty_cache()
+        self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._bind(batch, text_len)
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
