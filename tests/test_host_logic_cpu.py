@@ -129,6 +129,55 @@ def test_resume_reproduces_uninterrupted_run(tmp_path):
     assert not torch.equal(full, torch.load(os.path.join(part_dir, "last", "patch.pt")))
 
 
+def test_resume_mid_accumulation_keeps_the_partial_gradient(tmp_path):
+    """TMA / UPA with accumulate_steps > 1 step only on every accumulate_steps-th OUTER iteration (TMA.py:165); a checkpoint
+    written in between must carry the partial gradient sum, or the resumed run silently drops it."""
+    import os
+    import random
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from roboticattack_b200.attacker import TMAAttacker
+    from roboticattack_b200.config import tiny
+    from roboticattack_b200.synthetic import synthetic_batch
+    from roboticattack_b200.weights import random_state_dict
+    cfg = tiny(img=28, llm_layers=1, vit_depth=2)
+    sd = random_state_dict(cfg, seed=0, dtype=torch.float32, init="test")
+    batches = []
+    for i in range(4):
+        b = synthetic_batch(cfg, 2, 14, seed=70 + i)
+        batches.append({"pixel_values": b["obs"], "input_ids": b["input_ids"], "attention_mask": b["attention_mask"], "labels": b["labels"]})
+    kw = dict(num_iter=4, patch_size=[3, 8, 8], alpha=2e-3, maskidx=[0, 1, 2], warmup=0, geometry=True, innerLoop=1, accumulate_steps=2)
+
+    def make(save_dir, resume=None):
+        a = TMAAttacker(sd, save_dir=save_dir, optimizer="adamW", cfg=cfg, device="cpu", engine_factory=OracleEngine, resume=resume)
+        a.val_every = 1
+        return a
+
+    def seed(v=42):
+        random.seed(v), np.random.seed(v), torch.manual_seed(v)
+
+    seed()
+    full = make(str(tmp_path / "full")).patchattack_unconstrained(batches, None, **kw)
+
+    class Preempted(Exception):
+        pass
+
+    def crashing_loader():            # dies while fetching the second batch: the state on disk is the accumulate-only iteration 0
+        yield batches[0]
+        raise Preempted()
+
+    seed()
+    part_dir = str(tmp_path / "part")
+    with pytest.raises(Preempted):
+        make(part_dir).patchattack_unconstrained(crashing_loader(), None, **kw)
+    st = torch.load(os.path.join(part_dir, "last", "attack_state.pt"), weights_only=True)      # no pickled objects inside
+    assert st["outer_iter"] == 0 and st["opt_step"] == 0 and st["accumulate"].abs().sum() > 0
+    seed(1)
+    resumed = make(str(tmp_path / "resumed"), resume=os.path.join(part_dir, "last")).patchattack_unconstrained(batches[1:], None, **kw)
+    assert torch.equal(full, resumed)
+
+
 def test_filter_train_matches_reference_branches():
     """filterGripTrainTo1 (UADA.py:311-341): 2..7 gripper-closed samples -> keep them; > 8 -> random.sample of 8; else unchanged."""
     import random
