@@ -10,7 +10,10 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
 from pathlib import Path
 
 _LIB = None
-LIB_PATH = Path(__file__).resolve().parent / "libvla_b200.so"
+import os as _os
+
+# VLA_LIB_PATH: load another build of the library (A/B measurements of compile-time variants)
+LIB_PATH = Path(_os.environ.get("VLA_LIB_PATH") or (Path(__file__).resolve().parent / "libvla_b200.so"))
 
 FE_WARP, FE_PASTE20, FE_FIX, FE_NONE = 0, 1, 2, 3
 LOSS_UADA, LOSS_UADA_DDP, LOSS_UPA, LOSS_CE, LOSS_NEG_CE = 0, 1, 2, 3, 4

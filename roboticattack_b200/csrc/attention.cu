@@ -610,9 +610,18 @@ int attention_impl() {
   return g_attn_impl;
 }
 
+static int attention_fwd_once(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
+                              cudaStream_t s);
 int attention_fwd(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
                   cudaStream_t s) {
+  if (vla_doubled("attn_fwd"))
+    if (int rc = attention_fwd_once(qkv, o, lse, kv_len, B, N, H, hd, causal, s)) return rc;
+  return attention_fwd_once(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
+}
+static int attention_fwd_once(const bf16* qkv, bf16* o, float* lse, const int* kv_len, int B, int N, int H, int hd, int causal,
+                              cudaStream_t s) {
   VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
+  if (vla_ablated("attn_fwd")) return 0;
   if ((attention_impl() & 1) && attention_fwd_tc3_supported(N, hd)) return attention_fwd_tc3(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   if ((attention_impl() & 1) && attention_fwd_tc2_supported(N, hd)) return attention_fwd_tc2(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
   if (hd <= 64) return launch_fwd<64>(qkv, o, lse, kv_len, B, N, H, hd, causal, s);
@@ -630,10 +639,21 @@ int attention_tile_shift(int N, int causal) {
 // true when attention_bwd() can be called with o == NULL and `delta` already holding rowsum(dO * O) per (b, h, n)
 bool attention_bwd_takes_delta(int N, int hd) { return (attention_impl() & 2) && attention_bwd_tc_supported(N, hd); }
 
+static int attention_bwd_once(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
+                              const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
+                              int rope_L, cudaStream_t s);
 int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                   const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
                   int rope_L, cudaStream_t s) {
+  if (vla_doubled("attn_bwd"))
+    if (int rc = attention_bwd_once(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, rope_cos, rope_sin, rope_L, s)) return rc;
+  return attention_bwd_once(qkv, o, dout, lse, delta, dqkv, kv_len, B, N, H, hd, causal, rope_cos, rope_sin, rope_L, s);
+}
+static int attention_bwd_once(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
+                              const int* kv_len, int B, int N, int H, int hd, int causal, const float* rope_cos, const float* rope_sin,
+                              int rope_L, cudaStream_t s) {
   VLA_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: unsupported head dim %d", hd);
+  if (vla_ablated("attn_bwd")) return 0;
   VLA_REQUIRE(rope_cos == nullptr || (hd == 128 && rope_sin != nullptr && rope_L > 0),
               "attention_bwd: the fused RoPE backward needs head dim 128 and both tables");
   VLA_REQUIRE(o != nullptr || attention_bwd_takes_delta(N, hd), "attention_bwd: a precomputed delta (o == NULL) needs the tcgen05 backward");

@@ -14,6 +14,24 @@ static int init_pdl() {
 }
 int g_vla_pdl = init_pdl();
 
+bool vla_ablated(const char* what) {
+  static const char* env = getenv("VLA_ABLATE");
+  if (!env || !*env) return false;
+  const char* hit = strstr(env, what);
+  if (!hit) return false;
+  const char end = hit[strlen(what)];
+  return (hit == env || hit[-1] == ',') && (end == '\0' || end == ',');
+}
+
+bool vla_doubled(const char* what) {
+  static const char* env = getenv("VLA_DOUBLE");
+  if (!env || !*env) return false;
+  const char* hit = strstr(env, what);
+  if (!hit) return false;
+  const char end = hit[strlen(what)];
+  return (hit == env || hit[-1] == ',') && (end == '\0' || end == ',');
+}
+
 void vla_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -61,6 +61,12 @@ inline cudaError_t vla_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 #endif
 
+// Timing-only diagnostics: VLA_ABLATE="attn_fwd,attn_bwd,norm" makes the named kernel classes no-ops (the step's results are then
+// garbage, its duration is the step without them: the in-step cost of a class including its launch gaps).
+bool vla_ablated(const char* what);
+// VLA_DOUBLE="attn_fwd,attn_bwd,norm": launch the named (idempotent) kernel classes twice -- results unchanged, the step grows by
+// the class's in-step cost with real data (skipping a class feeds zeros to the GEMMs, which then draw less power and clock higher)
+bool vla_doubled(const char* what);
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -89,8 +89,13 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
+#ifndef VLA_EPI_WARPS
+#define VLA_EPI_WARPS 8
+#endif
+constexpr int NUM_EPI_WARPS = VLA_EPI_WARPS;            // multiple of 4: EPI_PARTS warps per TMEM lane quarter
+constexpr int EPI_PARTS = NUM_EPI_WARPS / 4;            // ... which take the tile's 32-column chunks round robin
+static_assert(NUM_EPI_WARPS % 4 == 0 && NUM_EPI_WARPS >= 8, "epilogue warps: a multiple of 4, at least 8");
+constexpr int GEMM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // warp 0: TMA, warp 1: MMA, warps 2..: epilogue
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 struct GemmArgs {
@@ -686,10 +691,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
         tc_fence_after();
       }
       if constexpr (EPI == EPI_PAIR) {
-        // chunks (4p + half) and (4p + half + 2) of every 128-column group: columns n and n + 64 in the same thread
+        // chunks (4p + h) and (4p + h + 2), h in {0, 1}, of every 128-column group: columns n and n + 64 in the same thread;
+        // the BLOCK_N / 64 such pairs go round robin over the EPI_PARTS warps of this lane quarter
 #pragma unroll 1
-        for (int p = 0; p < BLOCK_N / 128; ++p) {
-          const int ca = 4 * p + half;
+        for (int q = half; q < BLOCK_N / 64; q += EPI_PARTS) {
+          const int p = q >> 1;
+          const int ca = 4 * p + (q & 1);
           const int col_a = n_blk * BLOCK_N + ca * 32;
           if (col_a >= g.N) break;  // warp-uniform (N is a multiple of 128 in pair mode)
           uint32_t va[32], vb[32];
@@ -701,6 +708,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
       } else if constexpr (EPI == EPI_DELTA) {
         // the warp of column half `half` owns the head [half * 128, half * 128 + 128) of the 256-wide tile: 4 contiguous chunks
         if constexpr (BLOCK_N == 256) {
+         if (half < 2) {
           const int head_col = n_blk * BLOCK_N + half * 128;
           uint4 side_cur[8], side_nxt[8];
           load_side<EPI>(g, side_ptr<EPI>(g, row, head_col), head_col, side_nxt);   // overlaps the wait for the MMAs
@@ -724,6 +732,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
               g.epi.delta_out[(static_cast<int64_t>(b) * (g.N / 128) + head_col / 128) * g.epi.delta_L + n] = dsum;
             }
           }
+         }
         }
       } else {
         uint4 side_cur[8], side_nxt[8];
@@ -733,12 +742,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
           tc_fence_after();
         }
 #pragma unroll 1
-        for (int c = half; c < BLOCK_N / 32; c += 2) {
+        for (int c = half; c < BLOCK_N / 32; c += EPI_PARTS) {
           const int col0 = n_blk * BLOCK_N + c * 32;
           if (col0 >= g.N) break;  // warp-uniform
 #pragma unroll
           for (int q = 0; q < 8; ++q) side_cur[q] = side_nxt[q];
-          if (c + 2 < BLOCK_N / 32) load_side<EPI>(g, side_ptr<EPI>(g, row, col0 + 64), col0 + 64, side_nxt);
+          if (c + EPI_PARTS < BLOCK_N / 32) load_side<EPI>(g, side_ptr<EPI>(g, row, col0 + 32 * EPI_PARTS), col0 + 32 * EPI_PARTS, side_nxt);
           uint32_t v[32];
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();

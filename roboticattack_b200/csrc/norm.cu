@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(const bf16* _
 }
 
 int check_dims(int64_t M, int d, const char* what) {
+  if (vla_ablated("norm")) return -1;   // diagnostics: skip the launch (callers return 0)
   VLA_REQUIRE(M > 0 && d > 0 && d % 8 == 0 && d <= NORM_THREADS * MAX_VEC * 8, "%s: unsupported row width %d", what, d);
   return 0;
 }
@@ -254,34 +255,45 @@ int check_dims(int64_t M, int d, const char* what) {
 
 int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* mean, float* rstd, int64_t M, int d, float eps,
                   cudaStream_t s) {
-  if (int rc = check_dims(M, d, "layernorm_fwd")) return rc;
+  if (int rc = check_dims(M, d, "layernorm_fwd")) return rc < 0 ? 0 : rc;
   VLA_CHECK_CUDA(vla_launch(layernorm_fwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, x, w, b, y, mean, rstd, d, eps));
+  if (vla_doubled("norm")) {
+    VLA_CHECK_CUDA(vla_launch(layernorm_fwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, x, w, b, y, mean, rstd, d, eps));
+  }
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
 }
 int layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* mean, const float* rstd, const bf16* dres,
                   bf16* dx, int64_t M, int d, cudaStream_t s, const bf16* gamma2, bf16* scaled) {
-  if (int rc = check_dims(M, d, "layernorm_bwd")) return rc;
+  if (int rc = check_dims(M, d, "layernorm_bwd")) return rc < 0 ? 0 : rc;
   VLA_REQUIRE((gamma2 == nullptr) == (scaled == nullptr), "layernorm_bwd: gamma2 and scaled go together");
   VLA_CHECK_CUDA(vla_launch(layernorm_bwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, dy, x, w, mean, rstd, dres, dx, d,
                             gamma2, scaled));
+  if (vla_doubled("norm")) {
+    VLA_CHECK_CUDA(vla_launch(layernorm_bwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, dy, x, w, mean, rstd, dres, dx, d,
+                              gamma2, scaled));
+  }
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
 }
 int layernorm_fwd2(const LnFwdProblem& p0, const LnFwdProblem& p1, float eps, cudaStream_t s) {
-  if (int rc = check_dims(p0.M, p0.d, "layernorm_fwd2")) return rc;
+  if (int rc = check_dims(p0.M, p0.d, "layernorm_fwd2")) return rc < 0 ? 0 : rc;
   if (int rc = check_dims(p1.M, p1.d, "layernorm_fwd2")) return rc;
   const LnFwdArgs a0{p0.x, p0.w, p0.b, p0.y, p0.mean, p0.rstd, p0.d}, a1{p1.x, p1.w, p1.b, p1.y, p1.mean, p1.rstd, p1.d};
   VLA_CHECK_CUDA(vla_launch(layernorm_fwd2_kernel, dim3(static_cast<unsigned>(p0.M + p1.M)), dim3(NORM_THREADS), 0, s, a0, a1,
                             static_cast<int>(p0.M), eps));
+  if (vla_doubled("norm")) {
+    VLA_CHECK_CUDA(vla_launch(layernorm_fwd2_kernel, dim3(static_cast<unsigned>(p0.M + p1.M)), dim3(NORM_THREADS), 0, s, a0, a1,
+                              static_cast<int>(p0.M), eps));
+  }
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
 }
 int layernorm_bwd2(const LnBwdProblem& p0, const LnBwdProblem& p1, cudaStream_t s) {
-  if (int rc = check_dims(p0.M, p0.d, "layernorm_bwd2")) return rc;
+  if (int rc = check_dims(p0.M, p0.d, "layernorm_bwd2")) return rc < 0 ? 0 : rc;
   if (int rc = check_dims(p1.M, p1.d, "layernorm_bwd2")) return rc;
   VLA_REQUIRE((p0.gamma2 == nullptr) == (p0.scaled == nullptr) && (p1.gamma2 == nullptr) == (p1.scaled == nullptr),
               "layernorm_bwd2: gamma2 and scaled go together");
@@ -289,21 +301,31 @@ int layernorm_bwd2(const LnBwdProblem& p0, const LnBwdProblem& p1, cudaStream_t 
       a1{p1.dy, p1.x, p1.w, p1.mean, p1.rstd, p1.dres, p1.dx, p1.d, p1.gamma2, p1.scaled};
   VLA_CHECK_CUDA(vla_launch(layernorm_bwd2_kernel, dim3(static_cast<unsigned>(p0.M + p1.M)), dim3(NORM_THREADS), 0, s, a0, a1,
                             static_cast<int>(p0.M)));
+  if (vla_doubled("norm")) {
+    VLA_CHECK_CUDA(vla_launch(layernorm_bwd2_kernel, dim3(static_cast<unsigned>(p0.M + p1.M)), dim3(NORM_THREADS), 0, s, a0, a1,
+                              static_cast<int>(p0.M)));
+  }
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
 }
 int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int64_t M, int d, float eps, cudaStream_t s) {
-  if (int rc = check_dims(M, d, "rmsnorm_fwd")) return rc;
+  if (int rc = check_dims(M, d, "rmsnorm_fwd")) return rc < 0 ? 0 : rc;
   VLA_CHECK_CUDA(vla_launch(rmsnorm_fwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, x, w, y, rstd, d, eps));
+  if (vla_doubled("norm")) {
+    VLA_CHECK_CUDA(vla_launch(rmsnorm_fwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, x, w, y, rstd, d, eps));
+  }
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
 }
 int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx, int64_t M, int d,
                 cudaStream_t s) {
-  if (int rc = check_dims(M, d, "rmsnorm_bwd")) return rc;
+  if (int rc = check_dims(M, d, "rmsnorm_bwd")) return rc < 0 ? 0 : rc;
   VLA_CHECK_CUDA(vla_launch(rmsnorm_bwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, dy, x, w, rstd, dres, dx, d));
+  if (vla_doubled("norm")) {
+    VLA_CHECK_CUDA(vla_launch(rmsnorm_bwd_kernel, dim3(static_cast<unsigned>(M)), dim3(NORM_THREADS), 0, s, dy, x, w, rstd, dres, dx, d));
+  }
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
