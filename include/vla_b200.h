@@ -188,6 +188,10 @@ int vla_engine_set_batch(vla_engine* e, const uint8_t* obs, int obs_on_device, c
 /* placements of the next nsteps inner iterations: xy i32 [nsteps,B,2], theta f32 [nsteps,B,2,3] (host) */
 int vla_engine_set_placements(vla_engine* e, const int32_t* xy_host, const float* theta_host, int nsteps, void* stream);
 int vla_engine_num_supervised(const vla_engine* e);
+/* ids i32 [num_supervised] (device): argmax over the FULL vocabulary of every supervised logits row of the last pass -- the
+ * `action_preds = logits.argmax(dim=2)` the reference's metrics are built on (UADA.py:168,229; TMA.py:150,274); pred_ids of
+ * vla_fwd_bwd is the argmax inside the 256 action classes (what weighted_loss / UAD use) */
+int vla_engine_full_vocab_pred(vla_engine* e, int32_t* dst, void* stream);
 /* The DINOv2 and SigLIP towers are independent until the feature concat; by default the SigLIP tower runs on an
  * engine-owned side stream (fork / join with events on the caller's stream).  on = 1 keeps everything on the caller's
  * stream (used for per-kernel timing). */

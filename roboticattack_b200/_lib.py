@@ -109,6 +109,7 @@ SIGNATURES = {
     "vla_engine_set_batch": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "vla_engine_set_placements": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vla_engine_num_supervised": (c_int, [c_void_p]),
+    "vla_engine_full_vocab_pred": (c_int, [c_void_p, c_void_p, c_void_p]),
     "vla_engine_set_single_stream": (c_int, [c_void_p, c_int]),
     "vla_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(LossParams), c_void_p, c_void_p,
                             c_void_p, c_int, c_void_p]),

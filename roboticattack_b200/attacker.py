@@ -232,7 +232,9 @@ class AttackEngineHost:
         the argmax inside the 256 action classes (what ``weighted_loss`` / UAD use).  The two differ whenever a non-action token
         wins -- which an attack can provoke -- and TMA selects its best patch by an L1 built on these predictions, so the ids of
         the action rows are taken from the engine's fp32 logits rows here (one [R, V] argmax per validation batch / outer
-        iteration; not on the per-inner-step path)."""
+        iteration; not on the per-inner-step path).  The engine computes that argmax on the device (``vla_engine_full_vocab_pred``)."""
+        if hasattr(eng, "full_vocab_pred"):          # computed on the device next to the loss head (one [R] copy)
+            return torch.where(pred >= 0, eng.full_vocab_pred().to(pred.device), pred)
         if not hasattr(eng, "tap"):
             return pred
         V = self.cfg.llm.vocab

@@ -67,7 +67,7 @@ def build_extension(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH)] + [str(o) for o in objs] + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+    cmd = [nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", str(LIB_PATH)] + [str(o) for o in objs] + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
     subprocess.run(cmd, check=True)
     STAMP.write_text(fp)
     return LIB_PATH

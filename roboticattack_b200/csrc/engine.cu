@@ -134,6 +134,7 @@ struct vla_engine {
   int last_kernel_nodes = 0;
   // greedy decode (vla_engine_decode_greedy)
   int* dec_ids = nullptr;           // device: the B token ids fed to the next decode step
+  int* pred_full = nullptr;         // device: argmax over the FULL vocabulary of every supervised row (what the reference's metrics use)
   std::vector<int> h_sup_rows;      // host copy of the supervised-row table of the current batch
   bool last_pass_forward_only = false;
 };
@@ -315,6 +316,7 @@ size_t plan(vla_engine* e, uint8_t* base, int B, int T) {
   e->rope_cos = bp.take<float>(static_cast<size_t>(L) * (h / c.llm_heads / 2));
   e->rope_sin = bp.take<float>(static_cast<size_t>(L) * (h / c.llm_heads / 2));
   e->dec_ids = bp.take<int>(B);
+  e->pred_full = bp.take<int>(Rmax);
   e->dstate = bp.take<StepState>(1);
   e->xy_cur = bp.take<int>(static_cast<size_t>(B) * 2);
   e->theta_cur = bp.take<float>(static_cast<size_t>(B) * 6);
@@ -975,6 +977,13 @@ extern "C" int vla_engine_set_placements(vla_engine* e, const int* xy_host, cons
 
 extern "C" int vla_engine_num_supervised(const vla_engine* e) { return e->R; }
 
+// ids i32 [num_supervised] (device): argmax over the full vocabulary of every supervised logits row of the last pass
+extern "C" int vla_engine_full_vocab_pred(vla_engine* e, int* dst, void* stream) {
+  VLA_REQUIRE(e && e->ws && dst, "vla_engine_full_vocab_pred: null argument");
+  VLA_CHECK_CUDA(cudaMemcpyAsync(dst, e->pred_full, sizeof(int) * e->R, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 // 1 = keep both vision towers on the caller's stream (clean per-kernel timing for profiling); 0 = fork the SigLIP
 // tower onto the engine's side stream (default).
 extern "C" int vla_engine_set_single_stream(vla_engine* e, int on) {
@@ -1162,6 +1171,8 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
     CK(G(e->hn, h, e->lm_head, h, e->logits, V, R, V, h, ep, s));
   }
   CK(loss_head_fwd_bwd(e->logits, e->meta, R, V, B, lp, e->row_stats, e->dlogits, scalars, pred_ids, s));
+  // `action_preds = logits.argmax(dim=2)` of the reference's metrics (UADA.py:168,229; TMA.py:150,274): full vocabulary
+  CK(argmax_rows(e->logits, R, V, e->pred_full, nullptr, 0, 0, s));
   e->last_pass_forward_only = (flags & VLA_FLAG_FORWARD_ONLY) != 0;
   if (flags & VLA_FLAG_FORWARD_ONLY) return 0;
 

@@ -256,6 +256,12 @@ class VLAEngine:
                                              _lib.ptr(accumulate), byref(sp), comm.handle if comm is not None else None,
                                              _lib.ptr(scalars_hist), _lib.ptr(pred_ids), _lib.cur_stream()), "vla_attack_step")
 
+    def full_vocab_pred(self):
+        """int32 [num_supervised] (device): full-vocabulary argmax of every supervised logits row of the last pass."""
+        out = torch.empty(max(self.num_supervised, 1), dtype=torch.int32, device=self.device)
+        _lib.check(self._lib.vla_engine_full_vocab_pred(self._h, _lib.ptr(out), _lib.cur_stream()), "vla_engine_full_vocab_pred")
+        return out[:self.num_supervised]
+
     def decode_greedy(self, prompt_len: int, n_tokens: int, tokens):
         """KV-cache greedy decode after a forward-only prefill (``vla_engine_decode_greedy``); tokens int32 [B, n_tokens] (device)."""
         assert tokens.dtype == torch.int32 and tokens.is_cuda and tuple(tokens.shape) == (self.B, n_tokens) and tokens.is_contiguous()

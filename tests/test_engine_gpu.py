@@ -327,3 +327,22 @@ def test_lockstep_towers_equal_two_stream_towers(tiny_setup, monkeypatch):
     assert torch.equal(outs[0][3], outs[1][3]) and torch.equal(outs[0][4], outs[1][4])
     torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-8)
     assert outs[0][0].abs().sum() > 0
+
+
+def test_full_vocab_prediction_matches_the_logits(tiny_setup):
+    """The reference's metrics use `logits.argmax(dim=2)` over the FULL vocabulary (UADA.py:168,229; TMA.py:150,274); the engine
+    computes it on the device next to the loss head: identical to the argmax of the tapped fp32 logits rows."""
+    cfg, sd, eng, B, T = tiny_setup
+    batch = synthetic_batch(cfg, B, T, seed=41, ragged=True)
+    eng.set_batch(batch["obs"], batch["input_ids"], batch["attention_mask"], batch["labels"])
+    R = eng.num_supervised
+    xy, theta = np.zeros((1, B, 2), dtype=np.int32), np.tile(np.eye(2, 3, dtype=np.float32), (1, B, 1, 1))
+    eng.set_placements(xy, theta)
+    patch = torch.rand(3, 8, 8, device="cuda")
+    dp = torch.zeros_like(patch)
+    sc = torch.zeros(_lib.NUM_SCALARS, device="cuda")
+    pred = torch.zeros(R, dtype=torch.int32, device="cuda")
+    eng.fwd_bwd(patch, 0, _lib.FE_FIX, SPECS["ce"], dp, sc, pred, forward_only=True)
+    full = eng.full_vocab_pred()
+    logits = eng.tap("logits", dtype=torch.float32).view(R, cfg.llm.vocab)
+    assert torch.equal(full.long(), logits.argmax(dim=1)) and full.shape == (R,)
