@@ -101,6 +101,39 @@ class LookaheadLoader:
         self._slot = None
 
 
+class InnerLoopJob:
+    """Results of one outer iteration on their way to the host.  On a CUDA device the device tensors are copied to pinned
+    memory on a read-back stream that waits only for the iteration's own last kernel (an event on the compute stream), so
+    ``result()`` returns when THIS iteration is done even if the next one is already queued behind it."""
+
+    def __init__(self, host, scalars_dev, pred_dev):
+        self.ctx = None                               # the caller's bookkeeping (iteration index, batch, learning rate ...)
+        if scalars_dev.is_cuda:
+            if host._rb_stream is None:
+                host._rb_stream = torch.cuda.Stream(device=host.device)
+            rb = host._rb_stream
+            ready = torch.cuda.Event()
+            ready.record()
+            self._sc = torch.empty(scalars_dev.shape, dtype=scalars_dev.dtype, pin_memory=True)
+            self._pr = torch.empty(pred_dev.shape, dtype=pred_dev.dtype, pin_memory=True)
+            with torch.cuda.stream(rb):
+                rb.wait_event(ready)
+                self._sc.copy_(scalars_dev, non_blocking=True)
+                self._pr.copy_(pred_dev, non_blocking=True)
+                scalars_dev.record_stream(rb)
+                pred_dev.record_stream(rb)
+                self._done = torch.cuda.Event()
+                self._done.record(rb)
+        else:
+            self._sc, self._pr, self._done = scalars_dev.clone(), pred_dev.clone(), None
+
+    def result(self):
+        if self._done is not None:
+            self._done.synchronize()
+            self._done = None
+        return self._sc, self._pr
+
+
 class AttackEngineHost:
     """Shared machinery: engine creation from ``vla`` (an HF-style module, a state dict, or a loaded VLAEngine),
     patch / optimiser state, one outer iteration = set_batch + placements + ``innerLoop`` engine steps."""
@@ -120,7 +153,8 @@ class AttackEngineHost:
         self.opt_step = 0
         self.world_size, self.rank = 1, 0
         self.comm = None
-        self._scalars = self._pred = None
+        self._slots, self._slot = [{}, {}], 0
+        self._rb_stream = None
 
     # -- engine ---------------------------------------------------------------------------------------------
     def ensure_engine(self, B: int, T: int):
@@ -197,12 +231,13 @@ class AttackEngineHost:
             self.comm = self.engine.make_comm(self.rank, self.world_size)
         return self.comm
 
-    def run_inner_loop(self, batch, n_inner, fe_mode, loss: LossSpec, lr, opt_kind, clip_l1=0.0, do_step=True,
-                       accumulate=None, after_launch=None):
-        """One outer iteration: upload the batch and the placements of all inner steps, then ``n_inner`` calls of
-        ``vla_attack_step`` (one CUDA graph launch each), nothing read back in between.  ``after_launch`` runs on the host
-        while the device works (the loaders' lookahead).  Returns (scalars [n_inner, 8] on the host, pred_ids [R] of the last
-        inner step)."""
+    def submit_inner_loop(self, batch, n_inner, fe_mode, loss: LossSpec, lr, opt_kind, clip_l1=0.0, do_step=True,
+                          accumulate=None, after_launch=None):
+        """One outer iteration, asynchronously: upload the batch and the placements of all inner steps, then ``n_inner`` calls of
+        ``vla_attack_step`` (one CUDA graph launch each), nothing read back in between.  ``after_launch`` runs on the host while
+        the device works (the loaders' lookahead).  Returns an ``InnerLoopJob``: the per-step scalar records and the predicted ids
+        of the last step travel to pinned host memory on a side stream as soon as the last step finishes, so that the caller
+        can launch the NEXT outer iteration before it looks at this one's numbers (``job.result()``)."""
         obs = observations_to_uint8(batch["pixel_values"], self.cfg.img)
         B, T = batch["input_ids"].shape
         eng = self.ensure_engine(B, T)
@@ -212,19 +247,29 @@ class AttackEngineHost:
         xy, theta = draw_placements(B, (self.cfg.img, self.cfg.img), tuple(self.patch.shape[1:]), geometry, steps=n_inner)
         eng.set_placements(xy, theta)
         eng.set_step_state(0, self.opt_step)
-        if self._scalars is None or self._scalars.shape[0] < n_inner:
-            self._scalars = torch.zeros(n_inner, _lib.NUM_SCALARS, device=self.device)
-        if self._pred is None or self._pred.numel() < R:
-            self._pred = torch.full((max(R, B * 8),), -1, dtype=torch.int32, device=self.device)
-        scalars, pred = self._scalars, self._pred
+        # two sets of result buffers, used alternately: the previous iteration's are still being read back
+        self._slot ^= 1
+        sl = self._slots[self._slot]
+        if sl.get("scalars") is None or sl["scalars"].shape[0] < n_inner:
+            sl["scalars"] = torch.zeros(n_inner, _lib.NUM_SCALARS, device=self.device)
+        if sl.get("pred") is None or sl["pred"].numel() < R:
+            sl["pred"] = torch.full((max(R, B * 8),), -1, dtype=torch.int32, device=self.device)
+        scalars, pred = sl["scalars"], sl["pred"]
         for s in range(n_inner):
             eng.attack_step(self.patch, self.m, self.v, self.grad, scalars, pred, fe_mode, loss, lr, opt_kind=opt_kind,
                             clip_l1=clip_l1, accumulate=accumulate, comm=comm, do_update=do_step)
             if do_step:
                 self.opt_step += 1
+        full = self._full_vocab_pred(eng, R, pred[:R])
+        job = InnerLoopJob(self, scalars[:n_inner], full)
         if after_launch is not None:
             after_launch()
-        return scalars[:n_inner].cpu(), self._full_vocab_pred(eng, R, pred[:R]).cpu()
+        return job
+
+    def run_inner_loop(self, batch, n_inner, fe_mode, loss: LossSpec, lr, opt_kind, clip_l1=0.0, do_step=True,
+                       accumulate=None, after_launch=None):
+        """``submit_inner_loop(...).result()``: (scalars [n_inner, 8] on the host, pred_ids [R] of the last inner step)."""
+        return self.submit_inner_loop(batch, n_inner, fe_mode, loss, lr, opt_kind, clip_l1, do_step, accumulate, after_launch).result()
 
     def _full_vocab_pred(self, eng, R, pred):
         """The reference's metrics take ``action_preds = logits.argmax(dim=2)`` over the FULL vocabulary (UADA.py:168,229;
@@ -442,6 +487,14 @@ class _AttackerBase(object):
     def _next(iterator, loader):
         return iterator.next(), iterator
 
+    def _drain(self, pending, process):
+        """Process the read-back of the previous outer iteration (if any).  The loops launch iteration i + 1 BEFORE they look at
+        iteration i's numbers (logging, metric lists): the host-side bookkeeping then overlaps the device's work, and the
+        order of everything that is logged or appended is unchanged."""
+        if pending is not None:
+            process(pending)
+        return None
+
     def _lookahead(self, i, train_it, has_val=True):
         """Host work to overlap with the device's inner loop: fetch the next training batch -- except on iterations that end
         with a validation pass, whose ``next()`` calls on the validation loader come first in the reference's RNG order."""
@@ -477,22 +530,14 @@ class UADAAttacker(_AttackerBase):
         self._sched_step = sched_step
         train_it = self._open(train_dataloader)
         val_it = self._open(val_dataloader)
-        for i in range(start_iter, num_iter):
-            data, train_it = self._next(train_it, train_dataloader)
-            data = dict(data)
-            if filterGripTrainTo1 and len(maskidx) == 1 and maskidx[0] == 6:
-                data = self.filter_train(data)
-            data["labels"] = self.mask_labels(data["labels"].clone(), maskidx)
-            cur_lr = lr * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else lr
-            scalars, pred = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind,
-                                             after_launch=self._lookahead(i, train_it, val_dataloader is not None))
+
+        def process(job):      # logging of one outer iteration (UADA.py:165-186)
+            i, labels, cur_lr = job.ctx
+            scalars, pred = job.result()
             self.train_CE_loss += scalars[:, _lib.S_CE].tolist()
             self.train_MSE_distance_loss += scalars[:, _lib.S_LOSS].tolist()
             self.train_UAD += scalars[:, _lib.S_UAD].tolist()
-            if self.optimizer == "adamW" and ((i + 1) % accumulate_steps == 0):
-                sched_step += 1
-            self._sched_step = sched_step
-            pr, gt = _decoded_pairs(pred, data["labels"])
+            pr, gt = _decoded_pairs(pred, labels)
             rd = lab.relative_distance(pr, gt).view(-1, max(1, len(maskidx)))
             log = {"TRAIN_attack_loss(CE)": scalars[-1, _lib.S_CE].item(),
                    "TRAIN_patch_gradient": scalars[-1, _lib.S_GRAD_MEAN].item(),
@@ -503,10 +548,30 @@ class UADAAttacker(_AttackerBase):
                 log[f"train_rd_{idx}"] = rd[:, k].mean().item()
             self.loss_buffer.append(log["TRAIN_attack_loss (MSE_Distance)"])
             self._log(args, log, i)
-            if i % self.val_every == 0 and val_dataloader is not None:
-                val_it = self._validate(i, val_it, val_dataloader, maskidx, fe_mode, loss, args)
-            elif i % self.val_every == 0 and self.save_dir:
-                self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
+
+        pending = None
+        for i in range(start_iter, num_iter):
+            data, train_it = self._next(train_it, train_dataloader)
+            data = dict(data)
+            if filterGripTrainTo1 and len(maskidx) == 1 and maskidx[0] == 6:
+                data = self.filter_train(data)
+            data["labels"] = self.mask_labels(data["labels"].clone(), maskidx)
+            cur_lr = lr * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else lr
+            job = h.submit_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind,
+                                      after_launch=self._lookahead(i, train_it, val_dataloader is not None))
+            job.ctx = (i, data["labels"], cur_lr)
+            if self.optimizer == "adamW" and ((i + 1) % accumulate_steps == 0):
+                sched_step += 1
+            self._sched_step = sched_step
+            pending = self._drain(pending, process)          # iteration i - 1, while the device runs iteration i
+            pending = job
+            if i % self.val_every == 0:
+                pending = self._drain(pending, process)
+                if val_dataloader is not None:
+                    val_it = self._validate(i, val_it, val_dataloader, maskidx, fe_mode, loss, args)
+                elif self.save_dir:
+                    self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
+        self._drain(pending, process)
         self._close(train_it, val_it)
         return h.patch.detach().cpu()
 
@@ -590,6 +655,18 @@ class UPAAttacker(_AttackerBase):
         acc = self._acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
         start_iter, sched_step = self._maybe_resume()
         train_it = self._open(train_dataloader)
+
+        def process(job):      # logging of one outer iteration (UPA.py:170-191)
+            i, cur_lr = job.ctx
+            scalars, _ = job.result()
+            log = {"TRAIN_attack_loss(CE)": scalars[-1, _lib.S_LOSS].item(),
+                   "TRAIN_patch_gradient": scalars[-1, _lib.S_GRAD_MEAN].item(), "TRAIN_LR": cur_lr,
+                   "TRAIN_ANGLE_LOSS": scalars[-1, _lib.S_AUX0].item(), "TRAIN_DISTANCE_LOSS": scalars[-1, _lib.S_AUX1].item()}
+            self.train_CE_loss.append(log["TRAIN_attack_loss(CE)"])
+            self.loss_buffer.append(log["TRAIN_attack_loss(CE)"])
+            self._log(args, log, i)
+
+        pending = None
         for i in range(start_iter, num_iter):
             data, train_it = self._next(train_it, train_dataloader)
             data = dict(data)
@@ -603,23 +680,22 @@ class UPAAttacker(_AttackerBase):
             data["labels"] = labels
             stepping = (i + 1) % accumulate_steps == 0
             cur_lr = lr * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else lr
-            scalars, _ = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind,
-                                          clip_l1=1e-3 if self.optimizer == "adamW" else 0.0, do_step=stepping, accumulate=acc,
-                                          after_launch=self._lookahead(i, train_it, val_dataloader is not None and reverse_direction and not guide))
+            job = h.submit_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind,
+                                      clip_l1=1e-3 if self.optimizer == "adamW" else 0.0, do_step=stepping, accumulate=acc,
+                                      after_launch=self._lookahead(i, train_it, val_dataloader is not None and reverse_direction and not guide))
+            job.ctx = (i, cur_lr)
             if self.optimizer == "adamW" and stepping:
                 sched_step += 1
-            log = {"TRAIN_attack_loss(CE)": scalars[-1, _lib.S_LOSS].item(),
-                   "TRAIN_patch_gradient": scalars[-1, _lib.S_GRAD_MEAN].item(), "TRAIN_LR": cur_lr,
-                   "TRAIN_ANGLE_LOSS": scalars[-1, _lib.S_AUX0].item(), "TRAIN_DISTANCE_LOSS": scalars[-1, _lib.S_AUX1].item()}
-            self.train_CE_loss.append(log["TRAIN_attack_loss(CE)"])
-            self.loss_buffer.append(log["TRAIN_attack_loss(CE)"])
-            self._log(args, log, i)
+            pending = self._drain(pending, process)          # iteration i - 1, while the device runs iteration i
+            pending = job
             if i % self.val_every == 0:
+                pending = self._drain(pending, process)
                 if val_dataloader is not None and reverse_direction and not guide:
                     val_it = self._validate(i, val_it, val_dataloader, fe_mode, loss, sched_step, args)
                 else:
                     self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
                 self._dump(train_CE_loss=self.train_CE_loss)
+        self._drain(pending, process)
         self._close(train_it, val_it)
         return h.patch.detach().cpu()
 
@@ -693,21 +769,13 @@ class TMAAttacker(_AttackerBase):
         acc = self._acc = torch.zeros_like(h.patch) if accumulate_steps > 1 else None
         start_iter, sched_step = self._maybe_resume()
         train_it = self._open(train_dataloader)
-        for i in range(start_iter, num_iter):
-            data, train_it = self._next(train_it, train_dataloader)
-            data = dict(data)
-            if filterGripTrainTo1 and len(maskidx) == 1 and maskidx[0] == 6:
-                data = self.filter_train(data)
-            data["labels"] = lab.tma_labels(data["labels"], target)
-            stepping = (i + 1) % accumulate_steps == 0
-            cur_lr = alpha * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else alpha
-            scalars, pred = h.run_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind, do_step=stepping, accumulate=acc,
-                                             after_launch=self._lookahead(i, train_it, val_dataloader is not None))
-            if self.optimizer == "adamW" and stepping:
-                sched_step += 1
+
+        def process(job):      # logging of one outer iteration (TMA.py:176-200)
+            i, labels, cur_lr = job.ctx
+            scalars, pred = job.result()
             # logging only: the reference averages this metric over the inner steps (TMA.py:161,177); reading the predictions of
             # every inner step would put a device->host sync into the inner loop, so the last inner step's are used
-            pr, gt = _decoded_pairs(pred, data["labels"])
+            pr, gt = _decoded_pairs(pred, labels)
             rd = lab.relative_distance(pr, gt).mean().item() if pr.numel() else 0.0
             log = {"TRAIN_attack_loss(CE)": scalars[-1, _lib.S_LOSS].item(),
                    "TRAIN_patch_gradient": scalars[-1, _lib.S_GRAD_MEAN].item(), "TRAIN_LR": cur_lr,
@@ -717,13 +785,32 @@ class TMAAttacker(_AttackerBase):
             self.train_inner_relatived_distance.append(rd)
             self.loss_buffer.append(log["TRAIN_attack_loss(CE)"])
             self._log(args, log, i)
+
+        pending = None
+        for i in range(start_iter, num_iter):
+            data, train_it = self._next(train_it, train_dataloader)
+            data = dict(data)
+            if filterGripTrainTo1 and len(maskidx) == 1 and maskidx[0] == 6:
+                data = self.filter_train(data)
+            data["labels"] = lab.tma_labels(data["labels"], target)
+            stepping = (i + 1) % accumulate_steps == 0
+            cur_lr = alpha * cosine_with_warmup(sched_step, warmup, total) if self.optimizer == "adamW" else alpha
+            job = h.submit_inner_loop(data, innerLoop, fe_mode, loss, cur_lr, opt_kind, do_step=stepping, accumulate=acc,
+                                      after_launch=self._lookahead(i, train_it, val_dataloader is not None))
+            job.ctx = (i, data["labels"], cur_lr)
+            if self.optimizer == "adamW" and stepping:
+                sched_step += 1
+            pending = self._drain(pending, process)          # iteration i - 1, while the device runs iteration i
+            pending = job
             if i % self.val_every == 0:
+                pending = self._drain(pending, process)
                 if val_dataloader is not None:
                     val_it = self._validate(i, val_it, val_dataloader, target, maskidx, fe_mode, sched_step, args)
                 else:
                     self._save_patch(h.patch, "last", outer_iter=i, sched_step=sched_step)
                 self._dump(train_CE_loss=self.train_CE_loss, train_inner_avg_loss=self.train_inner_avg_loss,
                            train_inner_relatived_distance=self.train_inner_relatived_distance)
+        self._drain(pending, process)
         self._close(train_it, val_it)
         return h.patch.detach().cpu()
 
@@ -913,6 +1000,27 @@ class UADADDPAttacker(_AttackerBase):
         fe_mode = _lib.FE_WARP if self.geometry else _lib.FE_PASTE20
         logs = []
         train_it = self._open(train_dataloader, restart=False)
+
+        def process(job):
+            """The four scalar all-reduces of the reference (UADA_ddp.py:214-221), packed into one exchange.  On a GPU it runs on
+            the read-back stream: a collective issued on the compute stream would queue behind the NEXT iteration's kernels."""
+            import contextlib
+            i, cur_lr = job.ctx
+            scalars, _ = job.result()
+            last = scalars[-1]
+            side = torch.cuda.stream(h._rb_stream) if h._rb_stream is not None else contextlib.nullcontext()
+            with side:
+                pack = torch.tensor([last[_lib.S_CE], last[_lib.S_LOSS], last[_lib.S_UAD], last[_lib.S_GRAD_MEAN]], device=h.device)
+                if world_size > 1:
+                    gathered = [torch.zeros_like(pack) for _ in range(world_size)]
+                    dist.all_gather(gathered, pack)
+                    g = torch.stack(gathered)
+                    pack = torch.stack([g[:, 0].mean(), g[:, 1].mean(), g[:, 2].mean(), g[:, 3].max()])
+                vals = pack.tolist()
+            logs.append({"TRAIN_attack_loss(CE)": vals[0], "TRAIN_attack_loss (MSE_Distance)": vals[1], "TRAIN_UAD": vals[2],
+                         "TRAIN_patch_gradient": vals[3], "TRAIN_LR": cur_lr})
+
+        pending = None
         for i in range(start_iter, int(self.num_iter)):
             try:                                   # ``for i, data in enumerate(loader)`` of UADA_ddp.py:176: ends with the loader
                 data = train_it.next()
@@ -921,24 +1029,18 @@ class UADADDPAttacker(_AttackerBase):
             data = dict(data)
             data["labels"] = self.mask_labels(data["labels"].clone(), self.maskidx)
             cur_lr = self.lr * cosine_with_warmup(i, self.warmup, int(self.num_iter))
-            scalars, _ = h.run_inner_loop(data, self.innerLoop, fe_mode, loss, cur_lr, _lib.OPT_ADAMW,
-                                          after_launch=self._lookahead(i, train_it, val_dataloader is not None))
-            # four scalar all-reduces of the reference (UADA_ddp.py:214-221) packed into one
-            last = scalars[-1]
-            pack = torch.tensor([last[_lib.S_CE], last[_lib.S_LOSS], last[_lib.S_UAD], last[_lib.S_GRAD_MEAN]], device=h.device)
-            if world_size > 1:
-                gathered = [torch.zeros_like(pack) for _ in range(world_size)]
-                dist.all_gather(gathered, pack)
-                g = torch.stack(gathered)
-                pack = torch.stack([g[:, 0].mean(), g[:, 1].mean(), g[:, 2].mean(), g[:, 3].max()])
-            log = {"TRAIN_attack_loss(CE)": pack[0].item(), "TRAIN_attack_loss (MSE_Distance)": pack[1].item(),
-                   "TRAIN_UAD": pack[2].item(), "TRAIN_patch_gradient": pack[3].item(), "TRAIN_LR": cur_lr}
-            logs.append(log)
+            job = h.submit_inner_loop(data, self.innerLoop, fe_mode, loss, cur_lr, _lib.OPT_ADAMW,
+                                      after_launch=self._lookahead(i, train_it, val_dataloader is not None))
+            job.ctx = (i, cur_lr)
+            pending = self._drain(pending, process)          # iteration i - 1, while the device runs iteration i
+            pending = job
             if i % self.val_every == 0:
+                pending = self._drain(pending, process)
                 if val_dataloader is not None:
                     self._validate(i, rank, world_size, val_dataloader, fe_mode, loss)
                 elif rank == 0 and self.save_dir:
                     self._save_patch(h.patch, "last", outer_iter=i, sched_step=i + 1)
+        self._drain(pending, process)
         self.train_logs = logs
         self._close(train_it)
         return h.patch.detach().cpu()
