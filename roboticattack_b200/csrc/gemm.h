@@ -50,10 +50,6 @@ struct GemmEpilogue {
   //   a plain serial reduction: no atomics, no extra pass over dO and O.  Plain epilogue otherwise; 256-wide tiles only.
   float* delta_out = nullptr;
   int delta_L = 0;
-  // pin the kernel variant of THIS launch (0 = automatic).  (Tried with it: issuing the leftover column blocks of gate|up and of
-  // the SwiGLU-backward GEMM -- 10.46 / 5.23 waves of 256-wide tiles -- as a second launch of 128-wide tiles.  No gain in the step:
-  // the second launch and the 128-wide variant's lower main-loop efficiency cost what the half-empty last wave does.)
-  int force_ctas = 0, force_block_n = 0;
 };
 
 // One problem of a launch.

@@ -1004,9 +1004,6 @@ static int gemm_launch(const GemmProblem& p0, const GemmProblem* p1, cudaStream_
   if (g_forced_ctas) {
     ctas = g_forced_ctas;
     block_n = delta ? 256 : g_forced_n;
-  } else if (p0.epi.force_ctas) {
-    ctas = p0.epi.force_ctas;
-    block_n = p0.epi.force_block_n;
   } else {
     auto shape_key = [](const GemmProblem& p) {
       return (static_cast<uint64_t>(p.M) << 42) ^ (static_cast<uint64_t>(p.N) << 21) ^ static_cast<uint64_t>(p.K);
