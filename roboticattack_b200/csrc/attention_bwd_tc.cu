@@ -439,7 +439,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           bool chunk_masked;
           if (MODE == MODE_DQ) chunk_masked = (col0 >= klen) || (causal && col0 > warp_row0 + 31);
           else chunk_masked = causal && warp_row0 > col0 + 31;
+#ifdef VLA_ATTN_EXPERIMENT_NOSOFTMAX   // diagnostics only (results are wrong): the softmax stage does no TMEM reads and no math
+          if (false) {
+#else
           if (warp_active && !chunk_masked) {
+#endif
             uint32_t sv[32], dv[32];
             tmem_ld_32x32(tmem + lane_addr + t * 128 + half * 32, sv);
             tmem_ld_32x32(tmem + lane_addr + t * 128 + 64 + half * 32, dv);
