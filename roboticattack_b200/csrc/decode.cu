@@ -24,8 +24,9 @@ __global__ void embed_rows_kernel(const int* __restrict__ ids, const bf16* __res
 // -> bf16.  hd <= 128, hd % 32 == 0; dynamic shared memory: (pos + 1) floats.
 constexpr int DEC_THREADS = 128;
 __global__ void __launch_bounds__(DEC_THREADS) attn_decode_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int L, int pos,
-                                                                 int H, int hd, float scale) {
+                                                                 int H, int hd, float scale, const int* __restrict__ dstate) {
   extern __shared__ float sc[];
+  if (dstate) pos = dstate[0];   // graph-replayed decode step: the position lives in device memory
   __shared__ float red[32];
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -74,8 +75,9 @@ __global__ void __launch_bounds__(DEC_THREADS) attn_decode_kernel(const bf16* __
 
 // ids[b] = argmax_v logits[b, v] (first maximum, as torch.argmax); optionally also appended to out[b * out_ld + out_col]
 __global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restrict__ logits, int V, int* __restrict__ ids,
-                                                          int* __restrict__ out, int out_ld, int out_col) {
+                                                          int* __restrict__ out, int out_ld, int out_col, const int* __restrict__ dstate) {
   __shared__ float bv[32];
+  if (dstate) out_col = dstate[1];
   __shared__ int bi[32];
   const float* row = logits + static_cast<int64_t>(blockIdx.x) * V;
   float best = -INFINITY;
@@ -114,6 +116,17 @@ __global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restri
 
 }  // namespace
 
+__global__ void decode_advance_kernel(int* dstate) {
+  dstate[0] += 1;   // cache row of the next token
+  dstate[1] += 1;   // its column in the token buffer
+}
+int decode_advance(int* dstate, cudaStream_t s) {
+  decode_advance_kernel<<<1, 1, 0, s>>>(dstate);
+  VLA_LAUNCH_CHECK();
+  ++g_vla_launch_count;
+  return 0;
+}
+
 int embed_rows(const int* ids, const bf16* table, bf16* x, int B, int d, cudaStream_t s) {
   VLA_REQUIRE(d % 8 == 0, "embed_rows: d %% 8 != 0");
   const int n = B * (d / 8);
@@ -123,17 +136,18 @@ int embed_rows(const int* ids, const bf16* table, bf16* x, int B, int d, cudaStr
   return 0;
 }
 
-int attention_decode(const bf16* qkv, bf16* o, int B, int L, int pos, int H, int hd, cudaStream_t s) {
+int attention_decode(const bf16* qkv, bf16* o, int B, int L, int pos, int H, int hd, const int* dstate, cudaStream_t s) {
   VLA_REQUIRE(hd % 32 == 0 && hd <= 128, "attention_decode: head dim %d not supported (multiple of 32, <= 128)", hd);
-  VLA_REQUIRE(pos >= 0 && pos < L, "attention_decode: position %d outside the cache (%d rows)", pos, L);
-  attn_decode_kernel<<<B * H, DEC_THREADS, (pos + 1) * sizeof(float), s>>>(qkv, o, L, pos, H, hd, 1.f / sqrtf(static_cast<float>(hd)));
+  VLA_REQUIRE(dstate || (pos >= 0 && pos < L), "attention_decode: position %d outside the cache (%d rows)", pos, L);
+  VLA_REQUIRE(L * sizeof(float) <= 48 * 1024, "attention_decode: cache of %d rows exceeds the score buffer", L);
+  attn_decode_kernel<<<B * H, DEC_THREADS, L * sizeof(float), s>>>(qkv, o, L, pos, H, hd, 1.f / sqrtf(static_cast<float>(hd)), dstate);
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
 }
 
-int argmax_rows(const float* logits, int R, int V, int* ids, int* out, int out_ld, int out_col, cudaStream_t s) {
-  argmax_rows_kernel<<<R, 1024, 0, s>>>(logits, V, ids, out, out_ld, out_col);
+int argmax_rows(const float* logits, int R, int V, int* ids, int* out, int out_ld, int out_col, const int* dstate, cudaStream_t s) {
+  argmax_rows_kernel<<<R, 1024, 0, s>>>(logits, V, ids, out, out_ld, out_col, dstate);
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;
   return 0;
@@ -153,7 +167,9 @@ template <int MR>
 __global__ void __launch_bounds__(GV_WARPS * 32) gemv_bf16_kernel(const bf16* __restrict__ A, int64_t lda, const bf16* __restrict__ W,
                                                                  int64_t ldw, void* __restrict__ out, int64_t ldc, int N, int K,
                                                                  const bf16* __restrict__ bias, const bf16* __restrict__ resid,
-                                                                 int64_t ldr, int out_f32, int out_stride, int out_offset) {
+                                                                 int64_t ldr, int out_f32, int out_stride, int out_offset,
+                                                                 const int* __restrict__ dstate) {
+  if (dstate) out_offset = dstate[0];
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * GV_WARPS + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -209,15 +225,15 @@ bool gemv_supported(int M, int K, int64_t lda, int64_t ldw) { return M >= 1 && M
 
 // out row m -> m * out_stride + out_offset when out_stride > 0 (the decode's cache-row remap), else m
 int gemv_bf16(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K, const bf16* bias,
-              const bf16* resid, int64_t ldr, int out_f32, int out_stride, int out_offset, cudaStream_t s) {
+              const bf16* resid, int64_t ldr, int out_f32, int out_stride, int out_offset, const int* dstate, cudaStream_t s) {
   VLA_REQUIRE(gemv_supported(M, K, lda, ldw), "gemv: needs 1 <= M <= 4 and K, lda, ldw multiples of 8 (M=%d K=%d)", M, K);
   VLA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemv: operands must be 16-byte aligned");
   const dim3 grid(ceil_div(N, GV_WARPS)), block(GV_WARPS * 32);
   switch (M) {
-    case 1: gemv_bf16_kernel<1><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset); break;
-    case 2: gemv_bf16_kernel<2><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset); break;
-    case 3: gemv_bf16_kernel<3><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset); break;
-    default: gemv_bf16_kernel<4><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset); break;
+    case 1: gemv_bf16_kernel<1><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset, dstate); break;
+    case 2: gemv_bf16_kernel<2><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset, dstate); break;
+    case 3: gemv_bf16_kernel<3><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset, dstate); break;
+    default: gemv_bf16_kernel<4><<<grid, block, 0, s>>>(A, lda, W, ldw, out, ldc, N, K, bias, resid, ldr, out_f32, out_stride, out_offset, dstate); break;
   }
   VLA_LAUNCH_CHECK();
   ++g_vla_launch_count;

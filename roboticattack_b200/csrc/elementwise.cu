@@ -169,7 +169,8 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __r
 // one thread per (row, q|k, head, 8 consecutive rotation pairs): two 16-byte loads, two 16-byte stores
 // row_stride > 0 (decode): logical row m lives at row m * row_stride + row_off and is rotated at position `row_off`
 __global__ void rope_kernel(bf16* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
-                            int64_t M, int L, int H, int hd, float sgn, int row_stride, int row_off) {
+                            int64_t M, int L, int H, int hd, float sgn, int row_stride, int row_off, const int* __restrict__ dstate) {
+  if (dstate) row_off = dstate[0];
   const int half = hd / 2, oct = half / 8;
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (idx >= M * 2 * H * oct) return;
@@ -310,13 +311,15 @@ int swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int64_t M, int F, cu
 int rope_inplace(bf16* qkv, const float* cos_tab, const float* sin_tab, int64_t M, int L, int H, int hd, int dir,
                  cudaStream_t s) {
   VLA_REQUIRE(hd % 16 == 0, "rope: head dim must be a multiple of 16");
-  rope_kernel<<<blocks_for(M * 2 * H * (hd / 16)), EW_THREADS, 0, s>>>(qkv, cos_tab, sin_tab, M, L, H, hd, dir >= 0 ? 1.f : -1.f, 0, 0);
+  rope_kernel<<<blocks_for(M * 2 * H * (hd / 16)), EW_THREADS, 0, s>>>(qkv, cos_tab, sin_tab, M, L, H, hd, dir >= 0 ? 1.f : -1.f, 0, 0, nullptr);
   EW_DONE();
 }
 // rotary embedding of the q and k thirds of cache row b * L + pos (b < B) at position pos (greedy decode)
-int rope_cache_rows(bf16* qkv, const float* cos_tab, const float* sin_tab, int B, int L, int pos, int H, int hd, cudaStream_t s) {
-  VLA_REQUIRE(hd % 16 == 0 && pos >= 0 && pos < L, "rope_cache_rows: bad head dim / position");
-  rope_kernel<<<blocks_for(static_cast<int64_t>(B) * 2 * H * (hd / 16)), EW_THREADS, 0, s>>>(qkv, cos_tab, sin_tab, B, L, H, hd, 1.f, L, pos);
+int rope_cache_rows(bf16* qkv, const float* cos_tab, const float* sin_tab, int B, int L, int pos, int H, int hd, const int* dstate,
+                    cudaStream_t s) {
+  VLA_REQUIRE(hd % 16 == 0 && (dstate || (pos >= 0 && pos < L)), "rope_cache_rows: bad head dim / position");
+  rope_kernel<<<blocks_for(static_cast<int64_t>(B) * 2 * H * (hd / 16)), EW_THREADS, 0, s>>>(qkv, cos_tab, sin_tab, B, L, H, hd, 1.f, L, pos,
+                                                                                             dstate);
   EW_DONE();
 }
 int add_bf16(const bf16* a, const bf16* b, bf16* out, int64_t n, cudaStream_t s) {

@@ -134,6 +134,9 @@ struct vla_engine {
   int last_kernel_nodes = 0;
   // greedy decode (vla_engine_decode_greedy)
   int* dec_ids = nullptr;           // device: the B token ids fed to the next decode step
+  int* dec_state = nullptr;         // device int[2]: {cache row of the token being processed, its column in dec_tokens}
+  int* dec_tokens = nullptr;        // device [B, DEC_MAX_TOKENS]: generated ids
+  cudaGraphExec_t dec_graph = nullptr;   // one recorded decode step (skinny path), valid for the current plan
   int* pred_full = nullptr;         // device: argmax over the FULL vocabulary of every supervised row (what the reference's metrics use)
   std::vector<int> h_sup_rows;      // host copy of the supervised-row table of the current batch
   bool last_pass_forward_only = false;
@@ -316,6 +319,8 @@ size_t plan(vla_engine* e, uint8_t* base, int B, int T) {
   e->rope_cos = bp.take<float>(static_cast<size_t>(L) * (h / c.llm_heads / 2));
   e->rope_sin = bp.take<float>(static_cast<size_t>(L) * (h / c.llm_heads / 2));
   e->dec_ids = bp.take<int>(B);
+  e->dec_state = bp.take<int>(2);
+  e->dec_tokens = bp.take<int>(static_cast<size_t>(B) * 32);
   e->pred_full = bp.take<int>(Rmax);
   e->dstate = bp.take<StepState>(1);
   e->xy_cur = bp.take<int>(static_cast<size_t>(B) * 2);
@@ -756,6 +761,7 @@ extern "C" void vla_engine_destroy(vla_engine* e) {
   }
   for (auto& g : e->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (e->dec_graph) cudaGraphExecDestroy(e->dec_graph);
   if (e->cap) cudaStreamDestroy(e->cap);
   if (e->lr_ring) cudaFreeHost(e->lr_ring);
   delete e;
@@ -807,6 +813,10 @@ extern "C" int vla_engine_set_buffers(vla_engine* e, void* weight_arena, size_t 
   for (auto& g : e->graphs)   // the plan moved: recorded graphs hold stale pointers / shapes
     if (g.exec) cudaGraphExecDestroy(g.exec);
   e->graphs.clear();
+  if (e->dec_graph) {
+    cudaGraphExecDestroy(e->dec_graph);
+    e->dec_graph = nullptr;
+  }
   e->h_place = e->h_adam = 0;
   e->h_lr = -1.f;
   VLA_CHECK_CUDA(cudaMemset(e->dstate, 0, sizeof(StepState)));
@@ -1172,7 +1182,7 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
   }
   CK(loss_head_fwd_bwd(e->logits, e->meta, R, V, B, lp, e->row_stats, e->dlogits, scalars, pred_ids, s));
   // `action_preds = logits.argmax(dim=2)` of the reference's metrics (UADA.py:168,229; TMA.py:150,274): full vocabulary
-  CK(argmax_rows(e->logits, R, V, e->pred_full, nullptr, 0, 0, s));
+  CK(argmax_rows(e->logits, R, V, e->pred_full, nullptr, 0, 0, nullptr, s));
   e->last_pass_forward_only = (flags & VLA_FLAG_FORWARD_ONLY) != 0;
   if (flags & VLA_FLAG_FORWARD_ONLY) return 0;
 
@@ -1495,54 +1505,91 @@ extern "C" int vla_engine_decode_greedy(vla_engine* e, int prompt_len, int n_tok
   VLA_REQUIRE(P + prompt_len + n_tokens - 2 <= L - 1, "vla_engine_decode_greedy: plan too short: T must be >= prompt_len + n_tokens (= %d)",
               prompt_len + n_tokens);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  constexpr int DEC_MAX_TOKENS = 32;
+  VLA_REQUIRE(n_tokens <= DEC_MAX_TOKENS, "vla_engine_decode_greedy: at most %d tokens", DEC_MAX_TOKENS);
   // token 0: the argmax of the prefill's logits row (full vocabulary, as generate() does)
-  CK(argmax_rows(e->logits, B, V, e->dec_ids, tokens, n_tokens, 0, s));
+  CK(argmax_rows(e->logits, B, V, e->dec_ids, e->dec_tokens, DEC_MAX_TOKENS, 0, nullptr, s));
   // M = B projections: the HBM-bound skinny kernel for B <= 4 (the evaluation loop runs B = 1), the tcgen05 GEMM otherwise
   static const bool no_gemv = getenv("VLA_DECODE_GEMV") && atoi(getenv("VLA_DECODE_GEMV")) == 0;
+  static const bool no_graph = getenv("VLA_DECODE_GRAPH") && atoi(getenv("VLA_DECODE_GRAPH")) == 0;
   const bool skinny = !no_gemv && gemv_supported(B, h, h, h) && f % 8 == 0;
-  auto linear = [&](const bf16* A, int K, const bf16* W, void* out, int64_t ldc, int N, const bf16* resid, int out_f32, int remap_stride,
-                    int remap_off) -> int {
-    if (skinny) return gemv_bf16(A, K, W, K, out, ldc, B, N, K, nullptr, resid, N, out_f32, remap_stride, remap_off, s);
-    GemmEpilogue ep;
-    ep.resid = resid;
-    ep.ldr = N;
-    ep.out_f32 = out_f32;
-    if (remap_stride) {
-      ep.out_group = 1;
-      ep.out_stride = remap_stride;
-      ep.out_offset = remap_off;
-    }
-    return G(A, K, W, K, out, ldc, B, N, K, ep, s);
-  };
-  for (int k = 1; k < n_tokens; ++k) {
-    const int pos = P + prompt_len + k - 1;   // cache row (within a sample) of the token generated in the previous step
+  // One decode step.  ds != nullptr (skinny path): every position-dependent kernel reads the position from device memory, so the
+  // step can be recorded once per plan and replayed for every token of every action.
+  auto decode_step = [&](int pos, int k, const int* ds, cudaStream_t st) -> int {
+    auto linear = [&](const bf16* A, int K, const bf16* W, void* out, int64_t ldc, int N, const bf16* resid, int out_f32, int remap_stride) -> int {
+      if (skinny) return gemv_bf16(A, K, W, K, out, ldc, B, N, K, nullptr, resid, N, out_f32, remap_stride, pos, remap_stride ? ds : nullptr, st);
+      GemmEpilogue ep;
+      ep.resid = resid;
+      ep.ldr = N;
+      ep.out_f32 = out_f32;
+      if (remap_stride) {
+        ep.out_group = 1;
+        ep.out_stride = remap_stride;
+        ep.out_offset = pos;
+      }
+      return G(A, K, W, K, out, ldc, B, N, K, ep, st);
+    };
     bf16* x = e->ll_xs;
-    CK(embed_rows(e->dec_ids, e->embed, x, B, h, s));
+    CK(embed_rows(e->dec_ids, e->embed, x, B, h, st));
     for (int l = 0; l < c.llm_layers; ++l) {
       const LlamaLayerW& w = e->lw[l];
-      CK(rmsnorm_fwd(x, w.n1, e->ll_norm, e->ll_rstd2, B, h, c.rms_eps, s));
+      CK(rmsnorm_fwd(x, w.n1, e->ll_norm, e->ll_rstd2, B, h, c.rms_eps, st));
       // q|k|v of the new position, written straight into the layer's cache row b * L + pos
-      CK(linear(e->ll_norm, h, w.qkv, e->la.qkv[l], 3 * h, 3 * h, nullptr, 0, L, pos));
-      CK(rope_cache_rows(e->la.qkv[l], e->rope_cos, e->rope_sin, B, L, pos, NH, hd, s));
-      CK(attention_decode(e->la.qkv[l], e->ll_as, B, L, pos, NH, hd, s));
-      CK(linear(e->ll_as, h, w.o, e->ll_xm, h, h, x, 0, 0, 0));
-      CK(rmsnorm_fwd(e->ll_xm, w.n2, e->ll_norm, e->ll_rstd2, B, h, c.rms_eps, s));
+      CK(linear(e->ll_norm, h, w.qkv, e->la.qkv[l], 3 * h, 3 * h, nullptr, 0, L));
+      CK(rope_cache_rows(e->la.qkv[l], e->rope_cos, e->rope_sin, B, L, pos, NH, hd, ds, st));
+      CK(attention_decode(e->la.qkv[l], e->ll_as, B, L, pos, NH, hd, ds, st));
+      CK(linear(e->ll_as, h, w.o, e->ll_xm, h, h, x, 0, 0));
+      CK(rmsnorm_fwd(e->ll_xm, w.n2, e->ll_norm, e->ll_rstd2, B, h, c.rms_eps, st));
       if (skinny) {   // raw gate|up (interleaved packing), then the SwiGLU as its own tiny kernel
-        CK(linear(e->ll_norm, h, w.gu, e->ll_gu, 2 * f, 2 * f, nullptr, 0, 0, 0));
-        CK(swiglu_fwd(e->ll_gu, e->ll_act, B, f, s));
+        CK(linear(e->ll_norm, h, w.gu, e->ll_gu, 2 * f, 2 * f, nullptr, 0, 0));
+        CK(swiglu_fwd(e->ll_gu, e->ll_act, B, f, st));
       } else {
         GemmEpilogue ep;
         ep.pair_mode = 2;
         ep.act_out = e->ll_act;
         ep.ld_act = f;
-        CK(G(e->ll_norm, h, w.gu, h, e->ll_gu, 2 * f, B, 2 * f, h, ep, s));
+        CK(G(e->ll_norm, h, w.gu, h, e->ll_gu, 2 * f, B, 2 * f, h, ep, st));
       }
-      CK(linear(e->ll_act, f, w.down, x, h, h, e->ll_xm, 0, 0, 0));
+      CK(linear(e->ll_act, f, w.down, x, h, h, e->ll_xm, 0, 0));
     }
-    CK(rmsnorm_fwd(x, e->final_norm, e->hn, e->rstd_f, B, h, c.rms_eps, s));
-    CK(linear(e->hn, h, e->lm_head, e->logits, V, V, nullptr, 1, 0, 0));
-    CK(argmax_rows(e->logits, B, V, e->dec_ids, tokens, n_tokens, k, s));
+    CK(rmsnorm_fwd(x, e->final_norm, e->hn, e->rstd_f, B, h, c.rms_eps, st));
+    CK(linear(e->hn, h, e->lm_head, e->logits, V, V, nullptr, 1, 0));
+    CK(argmax_rows(e->logits, B, V, e->dec_ids, e->dec_tokens, DEC_MAX_TOKENS, k, ds, st));
+    if (ds) CK(decode_advance(e->dec_state, st));
+    return 0;
+  };
+  const int pos0 = P + prompt_len;   // cache row (within a sample) of the first generated token
+  if (skinny && !no_graph && n_tokens > 1) {
+    const int init[2] = {pos0, 1};
+    VLA_CHECK_CUDA(cudaMemcpyAsync(e->dec_state, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    if (!e->dec_graph) {   // record one step (nothing position-dependent is baked in; no autotuned kernels on this path)
+      if (!e->cap) VLA_CHECK_CUDA(cudaStreamCreateWithFlags(&e->cap, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      VLA_CHECK_CUDA(cudaStreamBeginCapture(e->cap, cudaStreamCaptureModeThreadLocal));
+      const long long launches0 = g_vla_launch_count;
+      const int rc = decode_step(0, 0, e->dec_state, e->cap);
+      const cudaError_t ce = cudaStreamEndCapture(e->cap, &graph);
+      g_vla_launch_count = launches0;
+      if (rc != 0 || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        if (rc == 0) vla_set_error("vla_engine_decode_greedy: stream capture failed: %s", cudaGetErrorString(ce));
+        cudaGetLastError();
+        return rc ? rc : 1;
+      }
+      const cudaError_t ie = cudaGraphInstantiate(&e->dec_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) {
+        e->dec_graph = nullptr;
+        vla_set_error("vla_engine_decode_greedy: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+        return 1;
+      }
+    }
+    for (int k = 1; k < n_tokens; ++k) VLA_CHECK_CUDA(cudaGraphLaunch(e->dec_graph, s));
+  } else {
+    for (int k = 1; k < n_tokens; ++k) CK(decode_step(pos0 + k - 1, k, nullptr, s));
   }
+  VLA_CHECK_CUDA(cudaMemcpy2DAsync(tokens, sizeof(int) * n_tokens, e->dec_tokens, sizeof(int) * DEC_MAX_TOKENS, sizeof(int) * n_tokens, B,
+                                   cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 

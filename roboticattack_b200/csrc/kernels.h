@@ -153,12 +153,16 @@ int step_end(StepState* st, const float* scal_cur, float* scal_hist, int adam_in
 int accumulate_f32(float* acc, const float* g, int n, cudaStream_t s);
 
 // ---- greedy decode with the KV cache (decode.cu, elementwise.cu) -------------------------------------------
+// dstate (nullable, device int[2] = {cache row of the token being processed, its column in the token buffer}): when given,
+// the kernels read the position from it instead of the host argument, so that ONE recorded decode step serves every token
 int embed_rows(const int* ids, const bf16* table, bf16* x, int B, int d, cudaStream_t s);
-int rope_cache_rows(bf16* qkv, const float* cos_tab, const float* sin_tab, int B, int L, int pos, int H, int hd, cudaStream_t s);
+int rope_cache_rows(bf16* qkv, const float* cos_tab, const float* sin_tab, int B, int L, int pos, int H, int hd, const int* dstate,
+                    cudaStream_t s);
 // qkv = a layer's cache [B*L, 3*H*hd]; query = row b*L + pos; o [B, H*hd]
-int attention_decode(const bf16* qkv, bf16* o, int B, int L, int pos, int H, int hd, cudaStream_t s);
-int argmax_rows(const float* logits, int R, int V, int* ids, int* out, int out_ld, int out_col, cudaStream_t s);
+int attention_decode(const bf16* qkv, bf16* o, int B, int L, int pos, int H, int hd, const int* dstate, cudaStream_t s);
+int argmax_rows(const float* logits, int R, int V, int* ids, int* out, int out_ld, int out_col, const int* dstate, cudaStream_t s);
+int decode_advance(int* dstate, cudaStream_t s);
 // skinny GEMM of the decode steps (decode.cu): M <= 4, HBM-bound weight streaming on the CUDA cores
 bool gemv_supported(int M, int K, int64_t lda, int64_t ldw);
 int gemv_bf16(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K, const bf16* bias,
-              const bf16* resid, int64_t ldr, int out_f32, int out_stride, int out_offset, cudaStream_t s);
+              const bf16* resid, int64_t ldr, int out_f32, int out_stride, int out_offset, const int* dstate, cudaStream_t s);
