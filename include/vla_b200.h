@@ -123,6 +123,17 @@ typedef struct vla_gemm_epilogue {
 } vla_gemm_epilogue;
 int vla_gemm_bf16_tn_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
                         const vla_gemm_epilogue* ep, void* stream);
+/* Skinny projection of the decode steps (M <= 4; HBM-bound weight streaming, csrc/decode.cu): out = epilogue(A' W^T) with
+ * A' = A, or norm_w * bf16(A * rstd(A)) when norm_w is given (LlamaRMSNorm fused, transformers modeling_llama.py).
+ * resid: out = bf16(resid + bf16(acc)); out_f32: fp32 output; swiglu: W rows are interleaved [gate 64 | up 64] groups and
+ * out [M, N/2] = bf16(bf16(silu(g)) * u) (LlamaMLP).  Same rounding points as vla_gemm_bf16_tn_ex + vla_rmsnorm_fwd. */
+int vla_gemv_bf16(const void* A, int64_t lda, const void* norm_w, float eps, const void* W, int64_t ldw, void* out, int64_t ldc, int M,
+                  int N, int K, const void* resid, int64_t ldr, int out_f32, int swiglu, void* stream);
+/* One decode position of causal attention over a KV cache, rotary embedding fused (csrc/decode.cu): qkv [B*L, 3*H*hd] bf16,
+ * row b*L + pos holds the new position's un-rotated q|k|v; q and k of that row are rotated in place (cos/sin f32 [L, hd/2])
+ * and o[b, h*hd..] = softmax(q k_j / sqrt(hd), j <= pos) v_j.  Replaces LlamaAttention.forward with past_key_values for one
+ * new token (HF generate, modeling_prismatic.py:506-536). */
+int vla_attention_decode(void* qkv, void* o, const float* cos_tab, const float* sin_tab, int B, int L, int pos, int H, int hd, void* stream);
 int vla_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t M, int d,
                       float eps, void* stream);
 int vla_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,

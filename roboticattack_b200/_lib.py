@@ -82,6 +82,9 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
     "vla_gemm_bf16_tn_ex": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                     POINTER(GemmEpilogue), c_void_p]),
+    "vla_gemv_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                              c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "vla_attention_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vla_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float,
                                   c_void_p]),
     "vla_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,

@@ -103,6 +103,13 @@ int vla_gemm_bf16_tn(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   e.out_f32 = out_f32;
   return gemm_bf16_tn(CBF(A), lda, CBF(W), ldw, out, ldc, M, N, K, e, S(stream));
 }
+int vla_gemv_bf16(const void* A, int64_t lda, const void* norm_w, float eps, const void* W, int64_t ldw, void* out, int64_t ldc, int M,
+                  int N, int K, const void* resid, int64_t ldr, int out_f32, int swiglu, void* stream) {
+  return gemv_bf16(CBF(A), lda, CBF(norm_w), eps, CBF(W), ldw, out, ldc, M, N, K, CBF(resid), ldr, out_f32, swiglu, 0, 0, nullptr, S(stream));
+}
+int vla_attention_decode(void* qkv, void* o, const float* cos_tab, const float* sin_tab, int B, int L, int pos, int H, int hd, void* stream) {
+  return attention_decode(BF(qkv), BF(o), cos_tab, sin_tab, B, L, pos, H, hd, nullptr, S(stream));
+}
 int vla_gemm_bf16_tn_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
                         const vla_gemm_epilogue* ep, void* stream) {
   VLA_REQUIRE(ep != nullptr, "vla_gemm_bf16_tn_ex: null epilogue");

@@ -167,22 +167,16 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __r
 }
 
 // one thread per (row, q|k, head, 8 consecutive rotation pairs): two 16-byte loads, two 16-byte stores
-// row_stride > 0 (decode): logical row m lives at row m * row_stride + row_off and is rotated at position `row_off`
 __global__ void rope_kernel(bf16* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
-                            int64_t M, int L, int H, int hd, float sgn, int row_stride, int row_off, const int* __restrict__ dstate) {
-  if (dstate) row_off = dstate[0];
+                            int64_t M, int L, int H, int hd, float sgn) {
   const int half = hd / 2, oct = half / 8;
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (idx >= M * 2 * H * oct) return;
   const int o = static_cast<int>(idx % oct);
   const int h = static_cast<int>((idx / oct) % H);
   const int which = static_cast<int>((idx / (static_cast<int64_t>(oct) * H)) % 2);
-  int64_t m = idx / (static_cast<int64_t>(oct) * H * 2);
-  int pos = static_cast<int>(m % L);
-  if (row_stride > 0) {
-    m = m * row_stride + row_off;
-    pos = row_off;
-  }
+  const int64_t m = idx / (static_cast<int64_t>(oct) * H * 2);
+  const int pos = static_cast<int>(m % L);
   bf16* p = qkv + m * 3 * H * hd + static_cast<int64_t>(which) * H * hd + h * hd + o * 8;
   const uint4 lo = *reinterpret_cast<const uint4*>(p), hi = *reinterpret_cast<const uint4*>(p + half);
   const float4 c0 = *reinterpret_cast<const float4*>(cos_tab + pos * half + o * 8);
@@ -311,15 +305,7 @@ int swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int64_t M, int F, cu
 int rope_inplace(bf16* qkv, const float* cos_tab, const float* sin_tab, int64_t M, int L, int H, int hd, int dir,
                  cudaStream_t s) {
   VLA_REQUIRE(hd % 16 == 0, "rope: head dim must be a multiple of 16");
-  rope_kernel<<<blocks_for(M * 2 * H * (hd / 16)), EW_THREADS, 0, s>>>(qkv, cos_tab, sin_tab, M, L, H, hd, dir >= 0 ? 1.f : -1.f, 0, 0, nullptr);
-  EW_DONE();
-}
-// rotary embedding of the q and k thirds of cache row b * L + pos (b < B) at position pos (greedy decode)
-int rope_cache_rows(bf16* qkv, const float* cos_tab, const float* sin_tab, int B, int L, int pos, int H, int hd, const int* dstate,
-                    cudaStream_t s) {
-  VLA_REQUIRE(hd % 16 == 0 && (dstate || (pos >= 0 && pos < L)), "rope_cache_rows: bad head dim / position");
-  rope_kernel<<<blocks_for(static_cast<int64_t>(B) * 2 * H * (hd / 16)), EW_THREADS, 0, s>>>(qkv, cos_tab, sin_tab, B, L, H, hd, 1.f, L, pos,
-                                                                                             dstate);
+  rope_kernel<<<blocks_for(M * 2 * H * (hd / 16)), EW_THREADS, 0, s>>>(qkv, cos_tab, sin_tab, M, L, H, hd, dir >= 0 ? 1.f : -1.f);
   EW_DONE();
 }
 int add_bf16(const bf16* a, const bf16* b, bf16* out, int64_t n, cudaStream_t s) {

@@ -1182,7 +1182,7 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
   }
   CK(loss_head_fwd_bwd(e->logits, e->meta, R, V, B, lp, e->row_stats, e->dlogits, scalars, pred_ids, s));
   // `action_preds = logits.argmax(dim=2)` of the reference's metrics (UADA.py:168,229; TMA.py:150,274): full vocabulary
-  CK(argmax_rows(e->logits, R, V, e->pred_full, nullptr, 0, 0, nullptr, s));
+  CK(argmax_rows(e->logits, R, V, e->pred_full, nullptr, 0, 0, s));
   e->last_pass_forward_only = (flags & VLA_FLAG_FORWARD_ONLY) != 0;
   if (flags & VLA_FLAG_FORWARD_ONLY) return 0;
 
@@ -1507,17 +1507,38 @@ extern "C" int vla_engine_decode_greedy(vla_engine* e, int prompt_len, int n_tok
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   constexpr int DEC_MAX_TOKENS = 32;
   VLA_REQUIRE(n_tokens <= DEC_MAX_TOKENS, "vla_engine_decode_greedy: at most %d tokens", DEC_MAX_TOKENS);
-  // token 0: the argmax of the prefill's logits row (full vocabulary, as generate() does)
-  CK(argmax_rows(e->logits, B, V, e->dec_ids, e->dec_tokens, DEC_MAX_TOKENS, 0, nullptr, s));
-  // M = B projections: the HBM-bound skinny kernel for B <= 4 (the evaluation loop runs B = 1), the tcgen05 GEMM otherwise
+  // M = B projections: the HBM-bound skinny kernels for B <= 4 (the evaluation loop runs B = 1), the tcgen05 GEMM otherwise
   static const bool no_gemv = getenv("VLA_DECODE_GEMV") && atoi(getenv("VLA_DECODE_GEMV")) == 0;
   static const bool no_graph = getenv("VLA_DECODE_GRAPH") && atoi(getenv("VLA_DECODE_GRAPH")) == 0;
-  const bool skinny = !no_gemv && gemv_supported(B, h, h, h) && f % 8 == 0;
-  // One decode step.  ds != nullptr (skinny path): every position-dependent kernel reads the position from device memory, so the
-  // step can be recorded once per plan and replayed for every token of every action.
-  auto decode_step = [&](int pos, int k, const int* ds, cudaStream_t st) -> int {
+  const bool skinny = !no_gemv && gemv_supported(B, h, h, h) && gemv_supported(B, f, f, f) && f % 64 == 0;
+  bf16* x = e->ll_xs;
+  // token 0: the argmax of the prefill's logits row (full vocabulary, as generate() does), and its embedding
+  if (skinny) {
+    CK(decode_select(e->logits, B, V, e->dec_ids, e->dec_tokens, DEC_MAX_TOKENS, 0, nullptr, e->embed, x, h, s));
+  } else {
+    CK(argmax_rows(e->logits, B, V, e->dec_ids, e->dec_tokens, DEC_MAX_TOKENS, 0, s));
+    CK(embed_rows(e->dec_ids, e->embed, x, B, h, s));
+  }
+  // One decode step: x holds the embeddings of the previous token on entry and of the new token on exit.
+  // Skinny path, five kernels per layer (decode.cu); ds != nullptr: every position-dependent kernel reads the position from
+  // device memory, so the step can be recorded once per plan and replayed for every token of every action.
+  auto decode_step_skinny = [&](int pos, int k, int* ds, cudaStream_t st) -> int {
+    for (int l = 0; l < c.llm_layers; ++l) {
+      const LlamaLayerW& w = e->lw[l];
+      // RMSNorm + q|k|v of the new position, written straight into the layer's cache row b * L + pos
+      CK(gemv_bf16(x, h, w.n1, c.rms_eps, w.qkv, h, e->la.qkv[l], 3 * h, B, 3 * h, h, nullptr, 0, 0, 0, L, pos, ds, st));
+      CK(attention_decode(e->la.qkv[l], e->ll_as, e->rope_cos, e->rope_sin, B, L, pos, NH, hd, ds, st));
+      CK(gemv_bf16(e->ll_as, h, nullptr, 0.f, w.o, h, e->ll_xm, h, B, h, h, x, h, 0, 0, 0, 0, nullptr, st));
+      CK(gemv_bf16(e->ll_xm, h, w.n2, c.rms_eps, w.gu, h, e->ll_act, f, B, 2 * f, h, nullptr, 0, 0, 1, 0, 0, nullptr, st));
+      CK(gemv_bf16(e->ll_act, f, nullptr, 0.f, w.down, f, x, h, B, h, f, e->ll_xm, h, 0, 0, 0, 0, nullptr, st));
+    }
+    CK(gemv_bf16(x, h, e->final_norm, c.rms_eps, e->lm_head, h, e->logits, V, B, V, h, nullptr, 0, 1, 0, 0, 0, nullptr, st));
+    CK(decode_select(e->logits, B, V, e->dec_ids, e->dec_tokens, DEC_MAX_TOKENS, k, ds, e->embed, x, h, st));
+    return 0;
+  };
+  // B > 4: the same step on the tcgen05 GEMM (M = B), norms and SwiGLU as in the prefill
+  auto decode_step_gemm = [&](int pos, int k, cudaStream_t st) -> int {
     auto linear = [&](const bf16* A, int K, const bf16* W, void* out, int64_t ldc, int N, const bf16* resid, int out_f32, int remap_stride) -> int {
-      if (skinny) return gemv_bf16(A, K, W, K, out, ldc, B, N, K, nullptr, resid, N, out_f32, remap_stride, pos, remap_stride ? ds : nullptr, st);
       GemmEpilogue ep;
       ep.resid = resid;
       ep.ldr = N;
@@ -1529,33 +1550,24 @@ extern "C" int vla_engine_decode_greedy(vla_engine* e, int prompt_len, int n_tok
       }
       return G(A, K, W, K, out, ldc, B, N, K, ep, st);
     };
-    bf16* x = e->ll_xs;
-    CK(embed_rows(e->dec_ids, e->embed, x, B, h, st));
     for (int l = 0; l < c.llm_layers; ++l) {
       const LlamaLayerW& w = e->lw[l];
       CK(rmsnorm_fwd(x, w.n1, e->ll_norm, e->ll_rstd2, B, h, c.rms_eps, st));
-      // q|k|v of the new position, written straight into the layer's cache row b * L + pos
       CK(linear(e->ll_norm, h, w.qkv, e->la.qkv[l], 3 * h, 3 * h, nullptr, 0, L));
-      CK(rope_cache_rows(e->la.qkv[l], e->rope_cos, e->rope_sin, B, L, pos, NH, hd, ds, st));
-      CK(attention_decode(e->la.qkv[l], e->ll_as, B, L, pos, NH, hd, ds, st));
+      CK(attention_decode(e->la.qkv[l], e->ll_as, e->rope_cos, e->rope_sin, B, L, pos, NH, hd, nullptr, st));
       CK(linear(e->ll_as, h, w.o, e->ll_xm, h, h, x, 0, 0));
       CK(rmsnorm_fwd(e->ll_xm, w.n2, e->ll_norm, e->ll_rstd2, B, h, c.rms_eps, st));
-      if (skinny) {   // raw gate|up (interleaved packing), then the SwiGLU as its own tiny kernel
-        CK(linear(e->ll_norm, h, w.gu, e->ll_gu, 2 * f, 2 * f, nullptr, 0, 0));
-        CK(swiglu_fwd(e->ll_gu, e->ll_act, B, f, st));
-      } else {
-        GemmEpilogue ep;
-        ep.pair_mode = 2;
-        ep.act_out = e->ll_act;
-        ep.ld_act = f;
-        CK(G(e->ll_norm, h, w.gu, h, e->ll_gu, 2 * f, B, 2 * f, h, ep, st));
-      }
+      GemmEpilogue ep;
+      ep.pair_mode = 2;
+      ep.act_out = e->ll_act;
+      ep.ld_act = f;
+      CK(G(e->ll_norm, h, w.gu, h, e->ll_gu, 2 * f, B, 2 * f, h, ep, st));
       CK(linear(e->ll_act, f, w.down, x, h, h, e->ll_xm, 0, 0));
     }
     CK(rmsnorm_fwd(x, e->final_norm, e->hn, e->rstd_f, B, h, c.rms_eps, st));
     CK(linear(e->hn, h, e->lm_head, e->logits, V, V, nullptr, 1, 0));
-    CK(argmax_rows(e->logits, B, V, e->dec_ids, e->dec_tokens, DEC_MAX_TOKENS, k, ds, st));
-    if (ds) CK(decode_advance(e->dec_state, st));
+    CK(argmax_rows(e->logits, B, V, e->dec_ids, e->dec_tokens, DEC_MAX_TOKENS, k, st));
+    CK(embed_rows(e->dec_ids, e->embed, x, B, h, st));
     return 0;
   };
   const int pos0 = P + prompt_len;   // cache row (within a sample) of the first generated token
@@ -1567,7 +1579,7 @@ extern "C" int vla_engine_decode_greedy(vla_engine* e, int prompt_len, int n_tok
       cudaGraph_t graph = nullptr;
       VLA_CHECK_CUDA(cudaStreamBeginCapture(e->cap, cudaStreamCaptureModeThreadLocal));
       const long long launches0 = g_vla_launch_count;
-      const int rc = decode_step(0, 0, e->dec_state, e->cap);
+      const int rc = decode_step_skinny(0, 0, e->dec_state, e->cap);
       const cudaError_t ce = cudaStreamEndCapture(e->cap, &graph);
       g_vla_launch_count = launches0;
       if (rc != 0 || ce != cudaSuccess || !graph) {
@@ -1586,7 +1598,10 @@ extern "C" int vla_engine_decode_greedy(vla_engine* e, int prompt_len, int n_tok
     }
     for (int k = 1; k < n_tokens; ++k) VLA_CHECK_CUDA(cudaGraphLaunch(e->dec_graph, s));
   } else {
-    for (int k = 1; k < n_tokens; ++k) CK(decode_step(pos0 + k - 1, k, nullptr, s));
+    for (int k = 1; k < n_tokens; ++k) {
+      if (skinny) CK(decode_step_skinny(pos0 + k - 1, k, nullptr, s));
+      else CK(decode_step_gemm(pos0 + k - 1, k, s));
+    }
   }
   VLA_CHECK_CUDA(cudaMemcpy2DAsync(tokens, sizeof(int) * n_tokens, e->dec_tokens, sizeof(int) * DEC_MAX_TOKENS, sizeof(int) * n_tokens, B,
                                    cudaMemcpyDeviceToDevice, s));

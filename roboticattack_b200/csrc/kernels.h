@@ -152,17 +152,21 @@ int step_begin(const StepState* st, const int* xy_all, const float* th_all, int*
 int step_end(StepState* st, const float* scal_cur, float* scal_hist, int adam_inc, cudaStream_t s);
 int accumulate_f32(float* acc, const float* g, int n, cudaStream_t s);
 
-// ---- greedy decode with the KV cache (decode.cu, elementwise.cu) -------------------------------------------
+// ---- greedy decode with the KV cache (decode.cu) -----------------------------------------------------------
 // dstate (nullable, device int[2] = {cache row of the token being processed, its column in the token buffer}): when given,
 // the kernels read the position from it instead of the host argument, so that ONE recorded decode step serves every token
 int embed_rows(const int* ids, const bf16* table, bf16* x, int B, int d, cudaStream_t s);
-int rope_cache_rows(bf16* qkv, const float* cos_tab, const float* sin_tab, int B, int L, int pos, int H, int hd, const int* dstate,
-                    cudaStream_t s);
-// qkv = a layer's cache [B*L, 3*H*hd]; query = row b*L + pos; o [B, H*hd]
-int attention_decode(const bf16* qkv, bf16* o, int B, int L, int pos, int H, int hd, const int* dstate, cudaStream_t s);
-int argmax_rows(const float* logits, int R, int V, int* ids, int* out, int out_ld, int out_col, const int* dstate, cudaStream_t s);
-int decode_advance(int* dstate, cudaStream_t s);
-// skinny GEMM of the decode steps (decode.cu): M <= 4, HBM-bound weight streaming on the CUDA cores
+// qkv = a layer's cache [B*L, 3*H*hd]; row b*L + pos holds the new position's un-rotated q|k|v: q and k are rotated in place
+// (tables [L, hd/2]) and the row attends to keys 0..pos; o [B, H*hd]
+int attention_decode(bf16* qkv, bf16* o, const float* cos_tab, const float* sin_tab, int B, int L, int pos, int H, int hd, const int* dstate,
+                     cudaStream_t s);
+int argmax_rows(const float* logits, int R, int V, int* ids, int* out, int out_ld, int out_col, cudaStream_t s);
+// closes a decode step (B <= 4): ids[b] = argmax, appended to out[b * out_ld + column]; x[b] = table[ids[b]]; dstate advances
+int decode_select(const float* logits, int B, int V, int* ids, int* out, int out_ld, int out_col, int* dstate, const bf16* table, bf16* x,
+                  int d, cudaStream_t s);
+// skinny projection of the decode steps (decode.cu): M <= 4, HBM-bound weight streaming on the CUDA cores; optional fused
+// RMSNorm of the activation rows (norm_w), residual, fp32 output, SwiGLU over interleaved gate|up weight rows, cache-row remap
 bool gemv_supported(int M, int K, int64_t lda, int64_t ldw);
-int gemv_bf16(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K, const bf16* bias,
-              const bf16* resid, int64_t ldr, int out_f32, int out_stride, int out_offset, const int* dstate, cudaStream_t s);
+int gemv_bf16(const bf16* A, int64_t lda, const bf16* norm_w, float eps, const bf16* W, int64_t ldw, void* out, int64_t ldc, int M, int N,
+              int K, const bf16* resid, int64_t ldr, int out_f32, int swiglu, int out_stride, int out_offset, const int* dstate,
+              cudaStream_t s);

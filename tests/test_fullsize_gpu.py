@@ -152,3 +152,44 @@ def test_baseline_configs_run_at_full_size(full, tmp_path):
                                     warmup=0, geometry=True, innerLoop=2, reverse_direction=True, args=args)
     assert torch.isfinite(p).all() and np.isfinite(u.train_CE_loss).all()
     eng.ensure_plan(8, 33)
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_fullsize_kv_decode_matches_teacher_forced_forward(full, B):
+    """Greedy action decode at OpenVLA-7B shapes (predict_action, modeling_prismatic.py:506-536): every single-position step on
+    the KV cache (fused skinny kernels of csrc/decode.cu, one recorded step replayed per token) must produce the logits of a
+    full forward pass over the same prefix (tcgen05 GEMMs + flash attention).  Both are bf16 pipelines that differ in
+    summation order only: logits agree to a few bf16 roundings, the chosen token is the argmax of the step's own logits, and
+    where the two paths pick different tokens the full forward itself calls the decision a tie (random weights make flat
+    logits, so such ties do occur)."""
+    from roboticattack_b200.policy import ActionPolicy
+    cfg, eng, batch, *_ = full
+    pol = ActionPolicy(eng)
+    obs = batch["obs"][:B].contiguous()
+    prompt = batch["input_ids"][:B, :25].clone()
+    n = 7
+    V = cfg.llm.vocab
+    toks = torch.from_numpy(pol.generate_action_tokens(obs, prompt, n))
+    assert toks.shape == (B, n) and toks.min() >= 0 and toks.max() < V
+    again = torch.from_numpy(pol.generate_action_tokens(obs, prompt, n))
+    assert torch.equal(toks, again), "replaying the recorded decode step must be deterministic"
+    worst = 0.0
+    for k in range(n):
+        part = torch.from_numpy(pol.generate_action_tokens(obs, prompt, k + 1))
+        assert torch.equal(part, toks[:, :k + 1]), f"decode of {k + 1} tokens is not a prefix of the decode of {n}"
+        kv = eng.tap("logits", dtype=torch.float32, max_elems=B * V).view(B, V).clone()
+        assert torch.equal(kv.argmax(dim=1).cpu(), toks[:, k]), f"token {k} is not the argmax of its step's logits"
+        # the same prefix through the full forward (one pass, no cache): generate 1 token from prompt + first k tokens
+        forced = torch.cat([prompt, toks[:, :k]], dim=1)
+        nxt = torch.from_numpy(pol.generate_action_tokens(obs, forced, 1, kv_cache=False))
+        ref = eng.tap("logits", dtype=torch.float32, max_elems=B * V).view(B, V).clone()
+        err = ((kv - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+        worst = max(worst, err)
+        print(f"B={B} token {k}: relative logits error {err:.4g}, cos {torch.nn.functional.cosine_similarity(kv, ref, dim=1).min().item():.6f}")
+        assert err < 5e-2, f"token {k}: kv-cache logits differ from the full forward by {err:.3g}"
+        tol = 4 * 2.0 ** -8 * ref.abs().max().item()
+        for b in range(B):
+            if nxt[b, 0] != toks[b, k]:
+                margin = (ref[b, nxt[b, 0]] - ref[b, toks[b, k]]).item()
+                assert 0 <= margin <= tol, f"token {k} sample {b}: paths disagree at a margin of {margin:.4g} (> {tol:.4g})"
+    print(f"kv decode vs teacher-forced forward, B={B}: worst relative logits error {worst:.3g}")
