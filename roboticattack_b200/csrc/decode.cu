@@ -320,9 +320,9 @@ int decode_select(const float* logits, int B, int V, int* ids, int* out, int out
 // closed-loop evaluation, 1).  Such a product streams the whole weight matrix for a handful of FLOPs per byte: it is bound by
 // HBM, and a tensor-core tile loop (one barrier round trip and four tcgen05.mma issues per 16 KB of weights) reaches ~2 TB/s.
 // Here a CTA of 8 warps owns groups of 4 weight rows and splits K over its warps: per group a warp streams its K segment of
-// the 4 rows with 16-byte loads (8 per lane in flight, 4 KB per warp, 96 KB per SM at 3 CTAs/SM), multiplies with the
-// activations staged in shared memory, and the 8 partial sums per output meet in shared memory in a fixed order.  CTAs are
-// persistent over the groups (grid = SMs x resident CTAs).
+// the 4 rows with 16-byte loads (two chunks of 8 loads per lane in flight, 8 KB per warp, 128 KB per SM at 2 CTAs/SM),
+// multiplies with the activations staged in shared memory, and the 8 partial sums per output meet in shared memory in a
+// fixed order.  CTAs are persistent over the groups (grid ~ SMs x resident CTAs, every CTA the same number of groups).
 //   prologue (before griddepcontrol.wait): the first group's weight loads, the norm weights;
 //   activations: plain bf16 rows, or RMSNorm fused -- A = w_norm * bf16(x * rstd) with the row's rstd computed by the CTA;
 //   epilogue: fp32 sum -> bf16 (-> + residual -> bf16), or SwiGLU over interleaved [gate 64 | up 64] weight-row groups
@@ -358,7 +358,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 }
 
 template <int MR>
-__global__ void __launch_bounds__(GV_THREADS, MR <= 2 ? 3 : 2) gemv_kernel(const GemvArgs a) {
+__global__ void __launch_bounds__(GV_THREADS, MR <= 2 ? 2 : 1) gemv_kernel(const GemvArgs a) {
   extern __shared__ __align__(16) unsigned char gv_smem[];
   uint4* sA = reinterpret_cast<uint4*>(gv_smem);   // [MR][K / 8] activations, 8 bf16 per element
   __shared__ float red[2][GV_WARPS][GV_UN * MR];
@@ -397,15 +397,31 @@ __global__ void __launch_bounds__(GV_THREADS, MR <= 2 ? 3 : 2) gemv_kernel(const
       }
   };
 
-  int g = blockIdx.x;
-  int r[GV_UN];
-  uint4 wv[GV_UN][GV_KC];
-  bool have = false;
-  if (g < ngroups) {
-    rows_of(g, r);
-    load(wv, r, kbeg);
-    have = true;
-  }
+  // The warp's work is a sequence of chunks (group, K offset): GV_UN rows x GV_KC x 32 lanes x 16 bytes each.  Two chunks are
+  // in flight per warp (two register buffers): the loads of chunk i + 2 are issued as soon as chunk i has been consumed,
+  // so the stream does not pause while a group is reduced and stored.  Both buffers are filled before the wait.
+  struct Chunk {
+    int g, c0;
+  };
+  auto next_chunk = [&](Chunk c) {
+    c.c0 += 32 * GV_KC;
+    if (c.c0 >= kend) {
+      c.g += gridDim.x;
+      c.c0 = kbeg;
+    }
+    return c;
+  };
+  auto load_chunk = [&](uint4 (&wv)[GV_UN][GV_KC], const Chunk& c) {
+    if (c.g >= ngroups) return;
+    int r[GV_UN];
+    rows_of(c.g, r);
+    load(wv, r, c.c0);
+  };
+  Chunk cur = {static_cast<int>(blockIdx.x), kbeg};
+  Chunk nxt = next_chunk(cur);
+  uint4 w0[GV_UN][GV_KC], w1[GV_UN][GV_KC];
+  load_chunk(w0, cur);
+  load_chunk(w1, nxt);
   uint4 nw[GV_NORM_VEC];
   if (a.norm_w) {
 #pragma unroll
@@ -457,42 +473,40 @@ __global__ void __launch_bounds__(GV_THREADS, MR <= 2 ? 3 : 2) gemv_kernel(const
   __syncthreads();
 
   int par = 0;
-  for (; g < ngroups; g += gridDim.x) {
-    rows_of(g, r);
-    float acc[GV_UN][MR];
+  float acc[GV_UN][MR];
 #pragma unroll
-    for (int u = 0; u < GV_UN; ++u)
+  for (int u = 0; u < GV_UN; ++u)
 #pragma unroll
-      for (int m = 0; m < MR; ++m) acc[u][m] = 0.f;
-    for (int c0 = kbeg; c0 < kend; c0 += 32 * GV_KC) {
-      if (!have) load(wv, r, c0);
-      have = false;
+    for (int m = 0; m < MR; ++m) acc[u][m] = 0.f;
+  auto consume = [&](const uint4 (&wv)[GV_UN][GV_KC], int c0) {
 #pragma unroll
-      for (int i = 0; i < GV_KC; ++i) {
-        const int c = c0 + i * 32 + lane;
-        if (c < kend) {
-          float af[MR][8];
+    for (int i = 0; i < GV_KC; ++i) {
+      const int c = c0 + i * 32 + lane;
+      if (c < kend) {
+        float af[MR][8];
 #pragma unroll
-          for (int m = 0; m < MR; ++m) unpack8(sA[m * K8 + c], af[m]);
+        for (int m = 0; m < MR; ++m) unpack8(sA[m * K8 + c], af[m]);
 #pragma unroll
-          for (int u = 0; u < GV_UN; ++u) {
-            float wf[8];
-            unpack8(wv[u][i], wf);
+        for (int u = 0; u < GV_UN; ++u) {
+          float wf[8];
+          unpack8(wv[u][i], wf);
 #pragma unroll
-            for (int m = 0; m < MR; ++m)
+          for (int m = 0; m < MR; ++m)
 #pragma unroll
-              for (int k = 0; k < 8; ++k) acc[u][m] = fmaf(af[m][k], wf[k], acc[u][m]);
-          }
+            for (int k = 0; k < 8; ++k) acc[u][m] = fmaf(af[m][k], wf[k], acc[u][m]);
         }
       }
     }
-    have = false;
+  };
+  // all chunks of group g consumed: reduce over lanes and warps, epilogue, reset the accumulators
+  auto finish_group = [&](int g) {
 #pragma unroll
     for (int u = 0; u < GV_UN; ++u)
 #pragma unroll
       for (int m = 0; m < MR; ++m) {
         const float v = warp_sum(acc[u][m]);
         if (lane == 0) red[par][warp][u * MR + m] = v;
+        acc[u][m] = 0.f;
       }
     __syncthreads();
     if (!a.swiglu) {
@@ -523,7 +537,20 @@ __global__ void __launch_bounds__(GV_THREADS, MR <= 2 ? 3 : 2) gemv_kernel(const
         static_cast<bf16*>(a.out)[m * a.ldc + j] = f2b(v);
       }
     }
-    par ^= 1;
+    par ^= 1;   // two reduction buffers: one barrier per group is enough
+  };
+  while (cur.g < ngroups) {
+    consume(w0, cur.c0);
+    Chunk after = next_chunk(nxt);
+    load_chunk(w0, after);
+    if (nxt.g != cur.g) finish_group(cur.g);
+    cur = nxt, nxt = after;
+    if (cur.g >= ngroups) break;
+    consume(w1, cur.c0);
+    after = next_chunk(nxt);
+    load_chunk(w1, after);
+    if (nxt.g != cur.g) finish_group(cur.g);
+    cur = nxt, nxt = after;
   }
 }
 }  // namespace
@@ -552,7 +579,7 @@ int gemv_bf16(const bf16* A, int64_t lda, const bf16* norm_w, float eps, const b
   a.A = A, a.lda = lda, a.norm_w = norm_w, a.eps = eps, a.W = W, a.ldw = ldw, a.out = out, a.ldc = ldc, a.resid = resid, a.ldr = ldr;
   a.N = N, a.K = K, a.out_f32 = out_f32, a.swiglu = swiglu, a.out_stride = out_stride, a.out_offset = out_offset, a.dstate = dstate;
   const int ngroups = swiglu ? ceil_div(N / 2, GV_UN / 2) : ceil_div(N, GV_UN);
-  const int resident = M <= 2 ? 3 : 2;
+  const int resident = M <= 2 ? 2 : 1;
   // every CTA takes the same number of groups (+-1): with ceil(ngroups / CTAs) rounds the grid is ngroups / rounds, not the
   // full SMs x resident -- CTAs progress in lock step on an HBM-bound stream, so a last partial round would run at the
   // bandwidth the few remaining CTAs can pull
