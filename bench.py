@@ -12,7 +12,8 @@ update -> clamp = ONE call of vla_attack_step = one CUDA graph launch.  `value` 
 collator-style loader of PIL images with innerLoop=1, so that EVERY step uploads its batch from host memory and reads its
 scalars and predictions back inside the timed region; `e2e_innerloop50` is the same call at the reference's own setting
 (one upload per 50 steps).  Extra keys: `strong` (global batch 64 split over the ranks, config #5), `per_rank` (step time
-and all-reduce wait per rank), `ref_gpu_path` (the oracle in the reference's eager style on this GPU; N=1 only).
+and all-reduce wait per rank), `ref_gpu_path` (the oracle in the reference's eager style on this GPU; N=1 only),
+`predict_action` (greedy 7-token action decode with the KV cache at batch 1, against the HBM roofline; N=1 only).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -364,6 +365,39 @@ def ref_gpu_path(cfg, args, dev, iters=5):
     return out
 
 
+def predict_action_leg(cfg, eng, text_len, n_tokens=7, iters=5):
+    """The consumer of ``patch.pt``: ``predict_action`` (modeling_prismatic.py:506-536) at batch 1 on the engine -- one prefill over
+    image + prompt, then ``n_tokens - 1`` single-position steps on the KV cache (five fused HBM-bound kernels per layer, one
+    recorded step replayed per token).  Wall clock around synchronised calls; the decode streams every Llama weight once per
+    token, so the per-token figure is reported against the measured HBM bandwidth.  Outside every timed region of the attack step."""
+    from roboticattack_b200.policy import ActionPolicy
+    from roboticattack_b200.synthetic import synthetic_batch
+    b = synthetic_batch(cfg, 1, text_len, seed=3)
+    prompt = b["input_ids"][:, :text_len - n_tokens - 1]
+    pol = ActionPolicy(eng)
+
+    def timed(n):
+        for _ in range(2):
+            pol.generate_action_tokens(b["obs"], prompt, n)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            pol.generate_action_tokens(b["obs"], prompt, n)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / iters * 1e3
+    t_all, t_first = timed(n_tokens), timed(1)
+    per_tok = (t_all - t_first) / (n_tokens - 1)
+    h, f, V, nl = cfg.llm.hidden, cfg.llm.ffn, cfg.llm.vocab, cfg.llm.layers
+    wbytes = 2 * (nl * (3 * h * h + h * h + 2 * f * h + h * f) + V * h)     # bf16 weights a decode step streams once
+    pk = peaks()
+    return {"ms_per_action": round(t_all, 3), "actions_per_sec": round(1e3 / t_all, 2), "prefill_plus_first_token_ms": round(t_first, 3),
+            "ms_per_token": round(per_tok, 4), "weight_bytes_per_token": wbytes,
+            "roofline": {"bound": "hbm", "achieved": round(wbytes / per_tok / 1e6, 1), "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": round(wbytes / per_tok / 1e6 / pk["hbm"], 4), "peak_source": pk["src"]},
+            "note": f"ActionPolicy.generate_action_tokens, batch 1, prompt of {prompt.shape[1]} tokens, {n_tokens} greedy tokens, "
+                    f"{iters} calls after 2 warm-up calls; per token = (action - (prefill + first token)) / {n_tokens - 1}"}
+
+
 def engine_arm(args):
     import ctypes
     import torch.distributed as dist
@@ -579,6 +613,10 @@ def engine_arm(args):
                   "note": "UADA_ddp global bs 64 (BASELINE config #5): the same global batch on N GPUs vs on one GPU of this box "
                           "(max over ranks, 3 steps after 2 warm-up steps, CUDA events)"}
 
+    decode = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        decode = predict_action_leg(cfg, eng, T)
+
     refgpu = None
     if rank == 0 and world == 1 and not args.no_extras and args.model == "openvla-7b":
         eng.shrink_plan(1, T)                 # hand the activation arena (82 GB after the bs-64 leg) back before the eager path allocates
@@ -607,7 +645,7 @@ def engine_arm(args):
                                 "its placements and label tables, and reads back its scalar record and predicted ids"},
                 "e2e_innerloop50": e2e50,
                 "gpu_launches": int(launches), "launches_per_step": launches / K, "graph_launches_per_step": replays / K,
-                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "ref_gpu_path": refgpu, "strong": strong,
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "ref_gpu_path": refgpu, "strong": strong, "predict_action": decode,
                 "per_rank": {"ms_per_step": [round(x, 3) for x in per_rank_ms], "sm_mhz": [round(x) for x in per_rank_mhz],
                              "uncoupled_ms_per_step": None if uncoupled is None else [round(x, 3) for x in uncoupled],
                              "allreduce_wait_ms_eager": [round(x, 4) for x in ar_all],
