@@ -14,7 +14,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#define VLA_B200_ABI_VERSION 2
+#define VLA_B200_ABI_VERSION 3
 
 #ifdef __cplusplus
 extern "C" {
@@ -120,6 +120,8 @@ typedef struct vla_gemm_epilogue {
   int64_t ld_act;
   float* delta_out;                   /* f32 [M / delta_L, N / 128, delta_L]: rowsum(dO * O) per head; aux = O */
   int delta_L;
+  int w_constant;                     /* scheduling hint: W is a constant of the stream (a weight matrix, not the output of a kernel
+                                         launched just before): its first tiles may be requested before griddepcontrol.wait */
 } vla_gemm_epilogue;
 int vla_gemm_bf16_tn_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldc, int M, int N, int K,
                         const vla_gemm_epilogue* ep, void* stream);

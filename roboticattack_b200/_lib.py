@@ -22,7 +22,7 @@ S_LOSS, S_CE, S_AUX0, S_AUX1, S_UAD, S_NTOK, S_NACT, S_GRAD_MEAN, NUM_SCALARS = 
 FLAG_FORWARD_ONLY = 1
 STEP_NO_GRAPH, STEP_NO_UPDATE = 1, 2
 COMM_ID_BYTES = 128
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class VLAError(RuntimeError):
@@ -44,7 +44,7 @@ class GemmEpilogue(Structure):
                 ("preact_out", c_void_p), ("out_f32", c_int), ("out_group", c_int), ("out_stride", c_int), ("out_offset", c_int),
                 ("resid_mod", c_int), ("aux_mode", c_int), ("aux", c_void_p), ("ldaux", c_int64), ("pair_mode", c_int),
                 ("rope_cos", c_void_p), ("rope_sin", c_void_p), ("rope_L", c_int), ("rope_cols", c_int), ("act_out", c_void_p),
-                ("ld_act", c_int64), ("delta_out", c_void_p), ("delta_L", c_int)]
+                ("ld_act", c_int64), ("delta_out", c_void_p), ("delta_L", c_int), ("w_constant", c_int)]
 
 
 class Config(Structure):

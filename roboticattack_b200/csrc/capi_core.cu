@@ -137,6 +137,7 @@ int vla_gemm_bf16_tn_ex(const void* A, int64_t lda, const void* W, int64_t ldw, 
   e.ld_act = ep->ld_act;
   e.delta_out = ep->delta_out;
   e.delta_L = ep->delta_L;
+  e.w_constant = ep->w_constant;
   return gemm_bf16_tn(CBF(A), lda, CBF(W), ldw, out, ldc, M, N, K, e, S(stream));
 }
 int vla_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t M, int d,

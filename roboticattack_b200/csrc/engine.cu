@@ -438,9 +438,17 @@ size_t plan(vla_engine* e, uint8_t* base, int B, int T) {
   return align_up(bp.off, 256);
 }
 
+// Every W operand of the engine's GEMMs is a weight matrix (or its transpose, built at load time): a constant of the stream,
+// so the kernel may request its first W tiles before griddepcontrol.wait (GemmEpilogue::w_constant).  VLA_GEMM_PREFETCH_W=0: A/B.
+bool prefetch_w() {
+  static const bool on = !(getenv("VLA_GEMM_PREFETCH_W") && atoi(getenv("VLA_GEMM_PREFETCH_W")) == 0);
+  return on;
+}
 int G(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out, int64_t ldc, int64_t M, int N, int K,
       const GemmEpilogue& ep, cudaStream_t s) {
-  return gemm_bf16_tn(A, lda, W, ldw, out, ldc, static_cast<int>(M), N, K, ep, s);
+  GemmEpilogue e2 = ep;
+  e2.w_constant = prefetch_w();
+  return gemm_bf16_tn(A, lda, W, ldw, out, ldc, static_cast<int>(M), N, K, e2, s);
 }
 
 // ---- vision tower -----------------------------------------------------------------------------------------
@@ -564,8 +572,13 @@ GemmProblem GP(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, void* out
 template <typename F>
 int gemm_towers(const TowerCtx (&tc)[2], int i, F f, cudaStream_t s) {
   const bool h0 = i < tc[0].v->used, h1 = i < tc[1].v->used;
-  if (h0 && h1) return gemm_bf16_tn_dual(f(tc[0]), f(tc[1]), s);
-  const GemmProblem p = f(tc[h0 ? 0 : 1]);
+  if (h0 && h1) {
+    GemmProblem p0 = f(tc[0]), p1 = f(tc[1]);
+    p0.epi.w_constant = p1.epi.w_constant = prefetch_w();
+    return gemm_bf16_tn_dual(p0, p1, s);
+  }
+  GemmProblem p = f(tc[h0 ? 0 : 1]);
+  p.epi.w_constant = prefetch_w();
   return gemm_bf16_tn(p.A, p.lda, p.W, p.ldw, p.out, p.ldc, p.M, p.N, p.K, p.epi, s);
 }
 

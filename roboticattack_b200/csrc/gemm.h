@@ -50,6 +50,12 @@ struct GemmEpilogue {
   //   a plain serial reduction: no atomics, no extra pass over dO and O.  Plain epilogue otherwise; 256-wide tiles only.
   float* delta_out = nullptr;
   int delta_L = 0;
+
+  // ---- scheduling hint (not part of the maths) ----
+  // W does not depend on the preceding kernels of the stream (a weight matrix): every CTA may request the W tiles of its first
+  // pipeline fill BEFORE griddepcontrol.wait, i.e. while the previous kernel is still draining; A (and every epilogue tensor) is
+  // only touched after the wait.  Leave 0 when W was produced by a kernel launched just before.
+  int w_constant = 0;
 };
 
 // One problem of a launch.

@@ -590,11 +590,37 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
   if (CTAS == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
-  pdl_wait();      // everything above overlapped the predecessor's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ===== TMA producer (one per CTA) =====
     if (lane == 0) {
+      // W tiles of the first pipeline fill, requested before the wait when W is a constant of the stream (w_constant): the
+      // HBM latency of a launch's first k-blocks is then paid while the previous kernel drains, not after it.
+      int prefetched = 0;
+      if (tile0 < num_tiles) {
+        const int pi = tile0 >= gg.tiles0 ? 1 : 0;
+        const GemmArgs& g = gg.p[pi];
+        if (g.epi.w_constant) {
+          const CUtensorMap* map_b = pi ? &map_b1 : &map_b0;
+          const int t = tile0 - (pi ? gg.tiles0 : 0);
+          const int n_blk = t / g.num_m_blocks;
+          const int num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
+          const int row_b = n_blk * BLOCK_N + static_cast<int>(cta_rank) * Cfg::B_ROWS;
+          prefetched = num_k_blocks < STAGES ? num_k_blocks : STAGES;
+          for (int kb = 0; kb < prefetched; ++kb) {
+            const uint32_t sa = smem_base + kb * Cfg::STAGE_BYTES;
+            if (CTAS == 1) {
+              mbar_arrive_expect_tx(full_bar(kb), Cfg::STAGE_BYTES);
+              tma_load_2d(sa + A_TILE_BYTES, map_b, full_bar(kb), kb * BLOCK_K, row_b);
+            } else {
+              if (leader) mbar_arrive_expect_tx(full_bar(kb), 2 * Cfg::STAGE_BYTES);
+              else mbar_arrive_remote(full_bar(kb), 0);
+              tma_load_2d_pair(sa + A_TILE_BYTES, map_b, full_bar(kb), kb * BLOCK_K, row_b);
+            }
+          }
+        }
+      }
+      pdl_wait();      // everything above overlapped the predecessor's tail; its outputs are visible from here on
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -608,9 +634,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
         const int row_a = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
         const int row_b = n_blk * BLOCK_N + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          if (tile == tile0 && kb < prefetched) {   // slot kb of the first fill: W is on its way, the barrier armed; add A
+            if (CTAS == 1) tma_load_2d(sa, map_a, full_bar(stage), kb * BLOCK_K, row_a);
+            else tma_load_2d_pair(sa, map_a, full_bar(stage), kb * BLOCK_K, row_a);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            continue;
+          }
           // PAIR_RELEASE: slots are released two at a time on the odd slot's barrier (see GemmCfg)
           if (!Cfg::PAIR_RELEASE || (stage & 1) == 0) mbar_wait(empty_bar(stage | (Cfg::PAIR_RELEASE ? 1 : 0)), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           if (CTAS == 1) {
             mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
             tma_load_2d(sa, map_a, full_bar(stage), kb * BLOCK_K, row_a);
@@ -631,6 +666,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
+    pdl_wait();
     // ===== MMA issuer (single thread; the leader CTA issues for the pair) =====
     // The whole warp runs the loop converged; the tcgen05 instructions of a k-block are guarded by one elect.sync so
     // that ptxas emits them back to back (under a plain `lane == 0` branch every tcgen05.mma is wrapped in its own
@@ -674,6 +710,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     __syncwarp();
   } else {
     // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4; the two warps of a quarter take alternate chunks =====
+    pdl_wait();   // side tensors are read and the output written only after the predecessor has completed
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     int acc = 0;

@@ -32,7 +32,7 @@ def test_binding_covers_header(built):
     from roboticattack_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     h = _lib.lib()
-    assert h.vla_abi_version() == 2
+    assert h.vla_abi_version() == 3
     assert h.vla_launch_count() >= 0
 
 

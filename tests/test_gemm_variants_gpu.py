@@ -253,3 +253,31 @@ def test_narrow_tile_variants_for_small_m(block_n, M):
         assert got[:, :pos].abs().max().item() == 0 and got[:, pos + 1:].abs().max().item() == 0
     finally:
         L.vla_gemm_set_mode(0, 0)
+
+
+@pytest.mark.parametrize("kind", ["plain", "resid", "rope", "dual_shapes"])
+def test_weight_tiles_requested_before_the_wait(variant, kind):
+    """`w_constant`: the producer warp requests the W tiles of the first pipeline fill before griddepcontrol.wait (they do not
+    depend on the previous kernel) and adds the A tiles after it.  Same tiles, same accumulation order: results are
+    bit-identical to the plain launch, for one tile per CTA (short K, fewer k-blocks than ring slots) and for many."""
+    shapes = {"plain": [(2304, 4096, 4096), (300, 512, 192), (128, 256, 64)], "resid": [(2048, 1152, 4304)], "rope": [(2304, 12288, 4096)],
+              "dual_shapes": [(2088, 1024, 1024), (32, 32064, 4096)]}[kind]
+    for (M, N, K) in shapes:
+        A, W = rand((M, K), 0.5, 90), rand((N, K), K ** -0.5, 91)
+        kw = {}
+        if kind == "resid":
+            kw = dict(bias=rand((N,), 0.2, 92), resid=rand((M, N), 1.0, 93), ldr=N)
+        if kind == "rope":
+            inv = 1.0 / (10000 ** (torch.arange(0, 128, 2, dtype=torch.float32) / 128))
+            fr = torch.outer(torch.arange(288, dtype=torch.float32), inv)
+            kw = dict(pair_mode=1, rope_cos=rbf(fr.cos()).cuda().contiguous(), rope_sin=rbf(fr.sin()).cuda().contiguous(), rope_L=288, rope_cols=8192)
+        torch.cuda.synchronize()                      # W really is a constant of the stream by now
+        base = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        gemm(A, W, base, M, N, K, **kw)
+        for _ in range(3):
+            # a kernel right before the GEMM keeps the device busy while the GEMM's CTAs start and prefetch
+            busy = torch.randn(1 << 24, device="cuda").sin_()
+            got = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+            gemm(A, W, got, M, N, K, w_constant=1, **kw)
+            assert torch.equal(got, base), f"{kind} {M}x{N}x{K}: prefetching W changed the result"
+        del busy
