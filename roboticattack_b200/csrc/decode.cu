@@ -358,7 +358,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 }
 
 template <int MR>
-__global__ void __launch_bounds__(GV_THREADS, MR <= 2 ? 2 : 1) gemv_kernel(const GemvArgs a) {
+__global__ void __launch_bounds__(GV_THREADS, 2) gemv_kernel(const GemvArgs a) {
   extern __shared__ __align__(16) unsigned char gv_smem[];
   uint4* sA = reinterpret_cast<uint4*>(gv_smem);   // [MR][K / 8] activations, 8 bf16 per element
   __shared__ float red[2][GV_WARPS][GV_UN * MR];
@@ -579,7 +579,7 @@ int gemv_bf16(const bf16* A, int64_t lda, const bf16* norm_w, float eps, const b
   a.A = A, a.lda = lda, a.norm_w = norm_w, a.eps = eps, a.W = W, a.ldw = ldw, a.out = out, a.ldc = ldc, a.resid = resid, a.ldr = ldr;
   a.N = N, a.K = K, a.out_f32 = out_f32, a.swiglu = swiglu, a.out_stride = out_stride, a.out_offset = out_offset, a.dstate = dstate;
   const int ngroups = swiglu ? ceil_div(N / 2, GV_UN / 2) : ceil_div(N, GV_UN);
-  const int resident = M <= 2 ? 2 : 1;
+  const int resident = 2;
   // every CTA takes the same number of groups (+-1): with ceil(ngroups / CTAs) rounds the grid is ngroups / rounds, not the
   // full SMs x resident -- CTAs progress in lock step on an HBM-bound stream, so a last partial round would run at the
   // bandwidth the few remaining CTAs can pull
