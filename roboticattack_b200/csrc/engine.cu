@@ -1521,8 +1521,8 @@ extern "C" int vla_engine_decode_greedy(vla_engine* e, int prompt_len, int n_tok
   constexpr int DEC_MAX_TOKENS = 32;
   VLA_REQUIRE(n_tokens <= DEC_MAX_TOKENS, "vla_engine_decode_greedy: at most %d tokens", DEC_MAX_TOKENS);
   // M = B projections: the HBM-bound skinny kernels for B <= 4 (the evaluation loop runs B = 1), the tcgen05 GEMM otherwise
-  static const bool no_gemv = getenv("VLA_DECODE_GEMV") && atoi(getenv("VLA_DECODE_GEMV")) == 0;
-  static const bool no_graph = getenv("VLA_DECODE_GRAPH") && atoi(getenv("VLA_DECODE_GRAPH")) == 0;
+  const bool no_gemv = getenv("VLA_DECODE_GEMV") && atoi(getenv("VLA_DECODE_GEMV")) == 0;     // read per call: A/B switches
+  const bool no_graph = getenv("VLA_DECODE_GRAPH") && atoi(getenv("VLA_DECODE_GRAPH")) == 0;
   const bool skinny = !no_gemv && gemv_supported(B, h, h, h) && gemv_supported(B, f, f, f) && f % 64 == 0;
   bf16* x = e->ll_xs;
   // token 0: the argmax of the prefill's logits row (full vocabulary, as generate() does), and its embedding

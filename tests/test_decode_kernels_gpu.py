@@ -102,7 +102,8 @@ def rope_ref(x, cos, sin):
 
 
 @pytest.mark.parametrize("B,Lc,pos,H,hd", [(1, 300, 281, 32, 128), (2, 64, 0, 4, 128), (3, 40, 39, 3, 64), (1, 50, 17, 2, 32),
-                                            (4, 200, 131, 8, 128)])
+                                            (4, 200, 131, 8, 128), (1, 700, 650, 4, 128), (2, 400, 333, 2, 64), (1, 330, 320, 2, 128),
+                                            (1, 330, 319, 2, 128)])   # > 320 cached rows: more than one round of loads per warp
 def test_attention_decode_fused_rope(B, Lc, pos, H, hd):
     g = torch.Generator(device="cuda").manual_seed(B + Lc + pos)
     qkv = torch.randn(B * Lc, 3 * H * hd, device="cuda", generator=g).bfloat16()

@@ -298,6 +298,33 @@ def test_greedy_action_decode_vs_oracle(tiny_setup):
     np.testing.assert_allclose(act, expect, rtol=0, atol=1e-12)
 
 
+def test_decode_paths_agree(tiny_setup, monkeypatch):
+    """The three forms of the single-position decode step: the recorded step replayed per token (default), the same fused
+    kernels launched one by one (VLA_DECODE_GRAPH=0; host-side position instead of the device-side one) and the tcgen05-GEMM
+    step of batches > 4 (VLA_DECODE_GEMV=0).  The first two are the same arithmetic: bit-identical tokens AND logits; the
+    third differs in summation order only."""
+    from roboticattack_b200.policy import ActionPolicy
+    cfg, sd, eng, B, T = tiny_setup
+    batch = synthetic_batch(cfg, B, T, seed=11)
+    prompt = batch["input_ids"][:, :T - 8].clone()
+    n, V = 7, cfg.llm.vocab
+    outs = {}
+    for name, env in (("graph", {}), ("eager", {"VLA_DECODE_GRAPH": "0"}), ("gemm", {"VLA_DECODE_GEMV": "0"})):
+        for k in ("VLA_DECODE_GRAPH", "VLA_DECODE_GEMV"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        toks = torch.from_numpy(ActionPolicy(eng).generate_action_tokens(batch["obs"], prompt, n))
+        outs[name] = (toks, eng.tap("logits", dtype=torch.float32, max_elems=B * V).view(B, V).clone())
+    eng.ensure_plan(B, T)
+    assert torch.equal(outs["graph"][0], outs["eager"][0]) and torch.equal(outs["graph"][1], outs["eager"][1])
+    same_prefix = (outs["graph"][0] == outs["gemm"][0]).all(dim=1)
+    if same_prefix.any():      # last-step logits are comparable where both paths decoded the same tokens
+        a, b = outs["graph"][1][same_prefix], outs["gemm"][1][same_prefix]
+        assert ((a - b).norm() / b.norm()).item() < 3e-2
+    assert (outs["graph"][0][:, 0] == outs["gemm"][0][:, 0]).all(), "token 0 comes from the same prefill"
+
+
 def test_lockstep_towers_equal_two_stream_towers(tiny_setup, monkeypatch):
     """The DINOv2 and SigLIP kernels of the same depth share one launch (two GEMM / LayerNorm problems per kernel, default)
     instead of running as two chains on two streams (VLA_TOWERS=streams).  Same tiles, same accumulation order: the forward is
