@@ -615,7 +615,10 @@ def engine_arm(args):
 
     decode = None
     if rank == 0 and world == 1 and not args.no_extras:
-        decode = predict_action_leg(cfg, eng, T)
+        try:
+            decode = predict_action_leg(cfg, eng, T)
+        except Exception as ex:      # noqa: BLE001 -- an extra leg must never cost the headline line
+            decode = {"unavailable": f"{type(ex).__name__}: {str(ex)[:120]}"}
 
     refgpu = None
     if rank == 0 and world == 1 and not args.no_extras and args.model == "openvla-7b":

@@ -4,7 +4,8 @@ Mirrors ``OpenVLAForActionPrediction.predict_action`` (prismatic/extern/hf/model
 empty token 29871 when missing, generate ``action_dim`` tokens greedily, map token ids to bin centres
 (``vocab_size - id``, clip, centres) and un-normalise with the dataset statistics.  Like HF ``generate`` the decode
 re-uses a KV cache: one prefill pass of the engine over image + prompt, then one single-position step per further token
-(``vla_engine_decode_greedy``: M = batch GEMMs against the cached k / v rows).  The image is expected to carry the patch already
+(``vla_engine_decode_greedy``: for batch <= 4 five fused HBM-bound kernels per decoder layer, one recorded step replayed per token;
+the tcgen05 GEMM with M = batch otherwise).  The image is expected to carry the patch already
 (``RandomPatchTransform.simulation_random_patch``), so the front end runs in its no-patch mode (``im_process``).
 """
 from __future__ import annotations
