@@ -323,7 +323,7 @@ int decode_select(const float* logits, int B, int V, int* ids, int* out, int out
 // the 4 rows with 16-byte loads (two chunks of 8 loads per lane in flight, 8 KB per warp, 128 KB per SM at 2 CTAs/SM),
 // multiplies with the activations staged in shared memory, and the 8 partial sums per output meet in shared memory in a
 // fixed order.  CTAs are persistent over the groups (grid ~ SMs x resident CTAs, every CTA the same number of groups).
-//   prologue (before griddepcontrol.wait): the first group's weight loads, the norm weights;
+//   prologue (before griddepcontrol.wait): the loads of the warp's first two chunks, the norm weights;
 //   activations: plain bf16 rows, or RMSNorm fused -- A = w_norm * bf16(x * rstd) with the row's rstd computed by the CTA;
 //   epilogue: fp32 sum -> bf16 (-> + residual -> bf16), or SwiGLU over interleaved [gate 64 | up 64] weight-row groups
 //   (out[m, j] = bf16(bf16(silu(g)) * u), the PAIR epilogue of the tcgen05 GEMM), optionally fp32 output (holding bf16 values)
