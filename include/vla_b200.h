@@ -134,7 +134,10 @@ int vla_gemv_bf16(const void* A, int64_t lda, const void* norm_w, float eps, con
 /* One decode position of causal attention over a KV cache, rotary embedding fused (csrc/decode.cu): qkv [B*L, 3*H*hd] bf16,
  * row b*L + pos holds the new position's un-rotated q|k|v; q and k of that row are rotated in place (cos/sin f32 [L, hd/2])
  * and o[b, h*hd..] = softmax(q k_j / sqrt(hd), j <= pos) v_j.  Replaces LlamaAttention.forward with past_key_values for one
- * new token (HF generate, modeling_prismatic.py:506-536). */
+ * new token (HF generate, modeling_prismatic.py:506-536).  The kernel is a programmatic dependent launch that requests the
+ * cache rows BELOW pos before griddepcontrol.wait: those rows must be complete before the kernel launched immediately before
+ * this one started (true for a cache: they were written by earlier decode steps / the prefill); row pos itself may come from
+ * the preceding kernel. */
 int vla_attention_decode(void* qkv, void* o, const float* cos_tab, const float* sin_tab, int B, int L, int pos, int H, int hd, void* stream);
 int vla_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t M, int d,
                       float eps, void* stream);
