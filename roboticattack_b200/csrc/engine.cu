@@ -1066,8 +1066,11 @@ int fwd_bwd_impl(vla_engine* e, const float* patch, int ph, int pw, const int* x
   // The two towers are independent until the feature concat: DINOv2 stays on the caller's stream, SigLIP runs on the
   // engine's side stream (fork / join with events), so the many small kernels of one tower fill the launch gaps, ramps
   // and tails of the other.  VLA_SINGLE_STREAM=1 keeps everything on one stream.
-  const char* towers_env = getenv("VLA_TOWERS");   // read per call (A/B switch, tests): "streams" = the round-1 two-stream path
-  const bool towers_dual = !(towers_env && strcmp(towers_env, "streams") == 0);
+  // Default: both towers' kernels of the same depth in one launch (lock step) -- except for a single sample, where a tower's
+  // GEMMs have a handful of tiles and the two towers on two streams fill more of the machine (18.17 -> 17.63 ms per iteration
+  // at bs 1; 25.20 / 25.11 at bs 2, 37.20 / 37.05 at bs 4, 66.2 / 66.5 at bs 8: no difference from two samples on).
+  const char* towers_env = getenv("VLA_TOWERS");   // read per call (A/B switch, tests): "streams" / "lockstep" force one form
+  const bool towers_dual = towers_env ? strcmp(towers_env, "streams") != 0 : B > 1;
   const bool two_streams = !towers_dual && e->side != nullptr && !e->single_stream;
   cudaStream_t s1 = two_streams ? e->side : s;
   if (two_streams) {

@@ -90,6 +90,43 @@ def test_graph_replay_equals_eager_equals_composed(setup):
     assert (ref[0] - patch0.cpu()).abs().max() > 0
 
 
+def test_single_sample_step_runs_the_towers_on_two_streams_inside_the_graph():
+    """Per-GPU batch 1 (BASELINE config #1): the two vision towers run as two chains on two streams (a tower's GEMMs have a
+    handful of tiles there), fork / join recorded into the step's CUDA graph.  Same arithmetic as the lock-step form: the
+    forward is bit-identical, graph replay == eager, and forcing the lock-step form gives the same scalars."""
+    import os
+    cfg = tiny(**CFG)
+    sd = random_state_dict(cfg, seed=0, dtype=torch.bfloat16, init="test")
+    eng = VLAEngine(cfg, 1, T)
+    eng.load_state_dict(sd)
+    batch = synthetic_batch(cfg, 1, T, seed=12)
+    batch["labels"] = lab.mask_labels_uada(batch["labels"].clone(), [0, 1, 2])
+    random.seed(7)
+    np.random.seed(7)
+    xy, theta = draw_placements(1, (cfg.img, cfg.img), (P, P), True, steps=STEPS)
+    eng.set_batch(batch["obs"], batch["input_ids"], batch["attention_mask"], batch["labels"])
+    eng.set_placements(xy, theta)
+    torch.manual_seed(1)
+    patch0 = torch.rand(3, P, P).cuda()
+    loss = LossSpec(_lib.LOSS_UADA, 5.0)
+    assert "VLA_TOWERS" not in os.environ
+    eag = run_steps(eng, patch0, "eager", loss)
+    r0 = _lib.lib().vla_graph_replays()
+    gra = run_steps(eng, patch0, "graph", loss)
+    assert _lib.lib().vla_graph_replays() - r0 == STEPS - 1
+    os.environ["VLA_TOWERS"] = "lockstep"
+    try:
+        lock = run_steps(eng, patch0, "eager", loss)
+    finally:
+        del os.environ["VLA_TOWERS"]
+    for name, out in (("graph", gra), ("lock-step towers", lock)):
+        assert torch.equal(out[1][0, :_lib.S_GRAD_MEAN], eag[1][0, :_lib.S_GRAD_MEAN]), f"{name}: first-step scalars must be bit-identical"
+        torch.testing.assert_close(out[1], eag[1], rtol=2e-4, atol=1e-6, msg=lambda m: f"{name}: scalar history\n{m}")
+        assert (out[0] - eag[0]).abs().max().item() <= 2 * LR * 1.001, name
+        assert torch.equal(out[2], eag[2]), f"{name}: predicted ids"
+    assert (eag[0] - patch0.cpu()).abs().max() > 0
+
+
 def test_learning_rate_and_counters_live_on_the_device(setup):
     """sign-PGD moves every pixel with a non-zero gradient by exactly lr: the per-outer-iteration learning rate reaches the
     replayed graph through device memory."""
